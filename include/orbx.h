@@ -1,0 +1,135 @@
+/*
+ * orbx.h -- C-ABI of liborbx.so: B200-native (sm_100a) ORB extraction + brute-force Hamming matching.
+ *
+ * This is the drop-in boundary for the ONE hot path of BowenBZ/RGBD_VisualOdometry.  The reference has
+ * no FFI/plugin layer; the operator interface the path sits behind is OpenCV's C++ one, called from the
+ * front-end thread at exactly two sites (plus the same pair in a dead function):
+ *
+ *   orb_->detectAndCompute(frameCurr_->color_, Mat(), keypointsCurr_, descriptorsCurr_)   src/frontend.cpp:153 (dead: :422)
+ *   flannMatcher_.match(mptCandidatesDescriptors, descriptorsCurr_, matches)             src/frontend.cpp:187 (dead: :439)
+ *
+ * with the operators constructed at src/frontend.cpp:33 (matcher) and :35-37 (ORB: number_of_features,
+ * scale_factor, level_pyramid from config/default.yaml:18-20; everything else is an OpenCV default:
+ * edgeThreshold 31, firstLevel 0, WTA_K 2, HARRIS_SCORE, patchSize 31, fastThreshold 20).
+ * INTEGRATION.md shows the <=40-line shim that binds these entry points into FrontEnd.
+ *
+ * Conventions (mirroring how the reference uses the OpenCV operators):
+ *   - plain pointers and sizes only; no C++ / torch / OpenCV types; the library never throws.
+ *   - every function returns ORBX_OK (0) or a negative orbx_status; orbx_last_error() gives the text.
+ *   - outputs are caller-allocated with an explicit capacity.  OpenCV's retainBest keeps ties, so the
+ *     keypoint count can EXCEED nfeatures (e.g. 521 for nfeatures = 500); if it exceeds the capacity the
+ *     call returns ORBX_E_CAPACITY with *n_out = needed and writes nothing partial to rely on.
+ *   - orbx_keypoint / orbx_match are byte-identical to cv::KeyPoint (28 B) / cv::DMatch (16 B), so the shim
+ *     is a memcpy; all seven KeyPoint fields are filled exactly as OpenCV fills them (util.h:52-68 hashes them all).
+ *   - one context per (GPU, caller thread); a context is NOT thread-safe (the reference only ever calls
+ *     these operators from the front-end thread, src/frontend.cpp:94-144).
+ *   - empty image / no keypoints -> ORBX_OK with *n_out = 0; empty query or train set -> ORBX_OK, 0 matches
+ *     (cv::DescriptorMatcher::match semantics).
+ *   - there is NO CPU fallback: without a CUDA device orbx_create fails with ORBX_E_CUDA.
+ */
+#ifndef ORBX_H_
+#define ORBX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBX_MAX_LEVELS 16
+#define ORBX_DESC_BYTES 32
+
+typedef struct orbx_ctx orbx_ctx; /* opaque */
+
+/* == cv::KeyPoint: pt.x, pt.y, size, angle, response, octave, class_id */
+typedef struct { float x, y, size, angle, response; int32_t octave, class_id; } orbx_keypoint;
+/* == cv::DMatch: queryIdx, trainIdx, imgIdx, distance */
+typedef struct { int32_t queryIdx, trainIdx, imgIdx; float distance; } orbx_match;
+
+typedef enum {
+    ORBX_OK = 0,
+    ORBX_E_ARG = -1,         /* bad argument (null pointer, size over the context maximum, ...) */
+    ORBX_E_CAPACITY = -2,    /* caller's output capacity too small; *n_out holds the needed count */
+    ORBX_E_CUDA = -3,        /* CUDA runtime / driver error, or no device */
+    ORBX_E_NOMEM = -4,       /* host or device allocation failed */
+    ORBX_E_UNSUPPORTED = -5, /* valid OpenCV input this build does not cover (e.g. channels not 1 or 3) */
+    ORBX_E_INTERNAL = -6,    /* an internal device-side bound was exceeded (never silently truncated) */
+    ORBX_E_ORDER = -7        /* libstdc++ introselect would have taken its heap-select fallback; order not reproduced */
+} orbx_status;
+
+/* ---- lifecycle ----------------------------------------------------------------------------------- */
+
+/* Replaces cv::ORB::create(nfeatures, scaleFactor, nlevels) + the matcher construction
+ * (src/frontend.cpp:33-37).  max_w/max_h/max_batch size the device-resident buffers. */
+int orbx_create(orbx_ctx** out, int device, int nfeatures, float scale_factor, int nlevels,
+                int max_w, int max_h, int max_batch);
+void orbx_destroy(orbx_ctx* ctx);
+const char* orbx_last_error(const orbx_ctx* ctx);
+const char* orbx_version(void);
+/* Blocks until all work queued on the context's stream is done; returns any deferred device status. */
+int orbx_synchronize(orbx_ctx* ctx);
+/* The CUDA stream (cudaStream_t) the context launches on, for callers that time with CUDA events. */
+void* orbx_stream(orbx_ctx* ctx);
+/* Number of kernels this library has launched on the context since creation (bench bookkeeping). */
+uint64_t orbx_launch_count(const orbx_ctx* ctx);
+
+/* ---- ORB extraction: replaces cv::Feature2D::detectAndCompute(image, Mat(), kps, desc) ----------- */
+
+/* One frame, HOST buffers (the literal drop-in for src/frontend.cpp:153).
+ * img: h rows of `step` bytes; channels 3 = BGR 8UC3 (as cv::imread gives, app/run_vo.cpp:91), 1 = gray 8UC1.
+ * kps: cap records, desc: cap*32 bytes.  *n_out = number of keypoints (order == OpenCV's). */
+int orbx_detect_and_compute(orbx_ctx* ctx, const uint8_t* img, int w, int h, size_t step, int channels,
+                            orbx_keypoint* kps, uint8_t* desc, int cap, int* n_out);
+
+/* `batch` same-sized frames, HOST buffers.  imgs[i] as above; outputs are [batch][cap] / [batch][cap][32];
+ * n_out[batch].  Returns ORBX_E_CAPACITY if any frame needs more than cap (n_out[] then holds the needs). */
+int orbx_detect_and_compute_batch(orbx_ctx* ctx, const uint8_t* const* imgs, int batch, int w, int h, size_t step,
+                                  int channels, orbx_keypoint* kps, uint8_t* desc, int cap, int* n_out);
+
+/* `batch` frames already DEVICE-resident (frame i at d_imgs + i*frame_stride); outputs to device memory
+ * ([batch][cap] records, [batch][cap][32] bytes, d_counts[batch]).  Asynchronous on orbx_stream(); per-frame
+ * status is deferred to orbx_synchronize().  d_counts[i] may exceed cap (records beyond cap are not written). */
+int orbx_detect_and_compute_device(orbx_ctx* ctx, const uint8_t* d_imgs, int batch, int w, int h, size_t step,
+                                   size_t frame_stride, int channels, orbx_keypoint* d_kps, uint8_t* d_desc,
+                                   int cap, int* d_counts);
+
+/* ---- matching: replaces cv::DescriptorMatcher::match(query, train, matches) as exact
+ *      BFMatcher(NORM_HAMMING): one DMatch per query row, ties -> lowest trainIdx, distance = (float)hamming,
+ *      imgIdx = 0.  query = the map-point candidates (M x 32), train = the frame descriptors (N x 32)
+ *      (src/frontend.cpp:183-187). -------------------------------------------------------------------- */
+
+/* HOST buffers.  out: nq records.  *n_out = nq, or 0 when either set is empty. */
+int orbx_match_hamming(orbx_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt,
+                       orbx_match* out, int* n_out);
+/* knnMatch(k = 2): out holds 2*nq records, [2*i] best, [2*i+1] second best by (distance, index);
+ * when nt == 1 the second record has trainIdx = -1. */
+int orbx_match_hamming_knn2(orbx_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int nt,
+                            orbx_match* out, int* n_out);
+/* DEVICE-resident, asynchronous, batched over `nsets` independent train sets (frames) that share one
+ * query set (the map): d_train is [nsets][nt][32], d_best / d_second are [nsets][nq] (d_second may be NULL). */
+int orbx_match_hamming_device(orbx_ctx* ctx, const uint8_t* d_query, int nq, const uint8_t* d_train, int nt,
+                              int nsets, orbx_match* d_best, orbx_match* d_second);
+/* The reference's host-side post-filter (src/frontend.cpp:190-211): keep distance <= max(min*ratio, 30).
+ * Pure host helper for the shim; in place compaction, returns the kept count. */
+int orbx_filter_matches(orbx_match* matches, int n, float match_ratio);
+
+/* ---- introspection for stage-level parity tests (not needed by the shim) ------------------------- */
+
+/* Geometry of the pyramid the context would build for a w x h frame. */
+int orbx_level_geometry(const orbx_ctx* ctx, int w, int h, int* ws, int* hs, float* scales, int* quotas);
+/* Copies pyramid level `level` of frame `frame` of the LAST extraction call to host (w_l*h_l bytes, tight). */
+int orbx_debug_read_level(orbx_ctx* ctx, int frame, int level, uint8_t* out, size_t out_bytes);
+/* Raster-ordered, border-filtered FAST+NMS survivors of the last call: x[], y[], score[] (cap entries each);
+ * *n_out = count. */
+int orbx_debug_read_fast(orbx_ctx* ctx, int frame, int level, int32_t* x, int32_t* y, int32_t* score, int cap, int* n_out);
+/* Average device time (ms) of each pipeline stage over the last extraction / match call, measured with CUDA
+ * events on the context's stream; names[i] are static strings.  Returns the number of stages written. */
+int orbx_debug_stage_times(orbx_ctx* ctx, const char** names, float* ms, int cap);
+/* Enable (1) / disable (0) per-stage CUDA-event timing (adds event records between kernels). */
+int orbx_set_profiling(orbx_ctx* ctx, int enable);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBX_H_ */

@@ -1,0 +1,581 @@
+// orbx.cu -- host side of liborbx.so: context, device-memory layout, kernel launches and the C-ABI of include/orbx.h.
+//
+// The two operator calls of the reference front-end that this library stands in for:
+//   cv::ORB::detectAndCompute            src/frontend.cpp:153   -> orbx_detect_and_compute*
+//   cv::DescriptorMatcher::match         src/frontend.cpp:187   -> orbx_match_hamming*
+// There is no CPU fallback anywhere in this file: every entry point either runs the sm_100a kernels or fails.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/orbx.h"
+#include "orbx_geom.h"
+#include "orbx_kernels.cuh"
+#include "orbx_match.cuh"
+
+using namespace orbx;
+
+namespace {
+
+const int8_t k_pattern_host[256 * 4] = {
+#include "brief_pattern.inc"
+};
+const int k_umax_host[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+
+constexpr int FAST_R = 16, FAST_CW = 256, FAST_NT = 256;
+constexpr int N_STAGES = 6;
+const char* const k_stage_names[N_STAGES] = {"gray", "pyramid", "fast_nms", "select_harris", "describe", "match"};
+
+size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Buf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct orbx_ctx {
+    int device = 0, nfeatures = 0, nlevels = 0, max_w = 0, max_h = 0, max_batch = 0;
+    float scale_factor = 1.2f;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+
+    Geom geom{};             // geometry of the current frame size
+    Geom geom_max{};         // geometry of (max_w, max_h): sizes the buffers
+    int geom_w = 0, geom_h = 0;
+    size_t tabs_len = 0;
+
+    Buf pyr, rowcnt, rowent, work, fincnt, status, tabs, pattern;
+    Buf in, kps, desc, counts;               // host-path staging on the device
+    int out_cap = 0;
+    Buf mq, mt, mbest, msecond, mkeys, mstatus;
+    int* h_small = nullptr;                  // pinned: counts[max_batch] + status[max_batch] + 1
+    int last_batch = 0;
+
+    bool profiling = false;
+    cudaEvent_t ev[N_STAGES + 2] = {};   // 0..5 bracket the extraction stages, 6..7 the matcher
+    float stage_ms[N_STAGES] = {};
+    bool stage_valid[N_STAGES] = {};
+};
+
+namespace {
+
+int fail(orbx_ctx* c, int code, const char* fmt, const char* a = "", const char* b = "")
+{
+    if (c) {
+        char buf[512];
+        snprintf(buf, sizeof buf, fmt, a, b);
+        c->err = buf;
+    }
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) return fail(c, ORBX_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+int ensure(orbx_ctx* c, Buf& b, size_t bytes)
+{
+    if (b.bytes >= bytes && b.p) return ORBX_OK;
+    if (b.p) { cudaFree(b.p); b.p = nullptr; b.bytes = 0; }
+    bytes = std::max<size_t>(bytes, 256);
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e != cudaSuccess) return fail(c, ORBX_E_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e));
+    b.bytes = bytes;
+    return ORBX_OK;
+}
+
+// ---- geometry, identical arithmetic to OpenCV: float scale chain, cvRound sizes, float quotas
+void level_sizes(int w, int h, int nlevels, float sf, int* ws, int* hs, float* sc)
+{
+    for (int l = 0; l < nlevels; ++l) {
+        const float s = (float)pow((double)sf, (double)l);
+        const float inv = 1.0f / s;
+        sc[l] = s;
+        ws[l] = (int)lrintf((float)w * inv);
+        hs[l] = (int)lrintf((float)h * inv);
+    }
+}
+
+void level_quotas(int nfeatures, float sf, int nlevels, int* q)
+{
+    const float factor = (float)(1.0 / (double)sf);
+    const float one_minus = 1.0f - factor;
+    const float num = (float)nfeatures * one_minus;
+    const float den = 1.0f - (float)pow((double)factor, (double)nlevels);
+    float nd = num / den;
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; ++l) {
+        q[l] = (int)lrintf(nd);
+        sum += q[l];
+        nd = nd * factor;
+    }
+    q[nlevels - 1] = std::max(nfeatures - sum, 0);
+}
+
+// INTER_LINEAR_EXACT taps of one axis, packed i0 | c1 << 16 (c1 in 8.8 fixed point, c0 = 256 - c1)
+void resize_taps(int s, int d, uint32_t* out)
+{
+    const double inv_scale = (double)d / (double)s;
+    const double scale = 1.0 / inv_scale;
+    for (int x = 0; x < d; ++x) {
+        const double f = scale * ((double)x + 0.5) - 0.5;
+        const int i = (int)floor(f);
+        uint32_t i0, c1;
+        if (i < 0 || s <= 1) { i0 = 0; c1 = 0; }
+        else if (i >= s - 1) { i0 = (uint32_t)(s - 1); c1 = 0; }
+        else { i0 = (uint32_t)i; c1 = (uint32_t)lrint((f - (double)i) * 256.0); }
+        out[x] = i0 | (c1 << 16);
+    }
+}
+
+void build_geom(const orbx_ctx* c, int w, int h, Geom* g, std::vector<uint32_t>* tabs)
+{
+    memset(g, 0, sizeof *g);
+    int ws[ORBX_LEVELS_MAX], hs[ORBX_LEVELS_MAX], q[ORBX_LEVELS_MAX];
+    float sc[ORBX_LEVELS_MAX];
+    level_sizes(w, h, c->nlevels, c->scale_factor, ws, hs, sc);
+    level_quotas(c->nfeatures, c->scale_factor, c->nlevels, q);
+    g->nlevels = c->nlevels; g->w = w; g->h = h; g->band_rows = FAST_R;
+    size_t pyr = 0, cnt = 0, ent = 0, wsz = 0, tab = 0;
+    int bands = 0;
+    for (int l = 0; l < c->nlevels; ++l) {
+        LevelGeom& L = g->L[l];
+        L.w = std::max(ws[l], 0); L.h = std::max(hs[l], 0);
+        L.pitch = (int)round_up((size_t)std::max(L.w, 1), 16);
+        L.quota = q[l]; L.scale = sc[l];
+        L.in_w = std::max(L.w - 2 * ORBX_EDGE, 0); L.in_h = std::max(L.h - 2 * ORBX_EDGE, 0);
+        if (L.in_w == 0 || L.in_h == 0) { L.in_w = 0; L.in_h = 0; }
+        L.ent_pitch = (int)round_up((size_t)(L.in_w + 1) / 2 + 1, 8);
+        L.ws_cap = std::max(((L.in_w + 1) / 2) * ((L.in_h + 1) / 2), 1);
+        L.band0 = bands; L.nbands = (L.in_h + FAST_R - 1) / FAST_R; bands += L.nbands;
+        L.img_off = pyr; pyr += round_up((size_t)L.pitch * std::max(L.h, 1), 256);
+        L.cnt_off = cnt; cnt += round_up((size_t)std::max(L.in_h, 1), 8);
+        L.ent_off = ent; ent += (size_t)L.ent_pitch * std::max(L.in_h, 1);
+        L.ws_off = wsz; wsz += round_up((size_t)L.ws_cap, 4);
+        if (l > 0) { L.xtab = (uint32_t)tab; tab += L.w; L.ytab = (uint32_t)tab; tab += L.h; }
+    }
+    g->total_bands = bands;
+    g->pyr_frame = round_up(pyr, 256); g->cnt_frame = cnt; g->ent_frame = ent; g->ws_frame = wsz;
+    if (tabs) {
+        tabs->assign(std::max<size_t>(tab, 1), 0);
+        for (int l = 1; l < c->nlevels; ++l) {
+            const LevelGeom& L = g->L[l];
+            const LevelGeom& S = g->L[l - 1];
+            if (L.w > 0 && L.h > 0 && S.w > 0 && S.h > 0) {
+                resize_taps(S.w, L.w, tabs->data() + L.xtab);
+                resize_taps(S.h, L.h, tabs->data() + L.ytab);
+            }
+        }
+    }
+}
+
+int set_geometry(orbx_ctx* c, int w, int h)
+{
+    if (c->geom_w == w && c->geom_h == h) return ORBX_OK;
+    std::vector<uint32_t> tabs;
+    build_geom(c, w, h, &c->geom, &tabs);
+    int rc = ensure(c, c->tabs, tabs.size() * 4);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->tabs.p, tabs.data(), tabs.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));       // `tabs` is a local
+    c->geom_w = w; c->geom_h = h;
+    return ORBX_OK;
+}
+
+void stage_mark(orbx_ctx* c, int i)
+{
+    if (c->profiling) cudaEventRecord(c->ev[i], c->stream);
+}
+
+// The extraction pipeline on device-resident frames; everything asynchronous on c->stream.
+int run_extract(orbx_ctx* c, const uint8_t* d_imgs, int batch, int w, int h, size_t step, size_t frame_stride, int channels,
+                float* d_kps, uint8_t* d_desc, int cap, int* d_counts)
+{
+    int rc = set_geometry(c, w, h);
+    if (rc) return rc;
+    const Geom& g = c->geom;
+    uint8_t* pyr = (uint8_t*)c->pyr.p;
+    CU(cudaMemsetAsync(c->status.p, 0, sizeof(int) * (size_t)batch, c->stream));
+    stage_mark(c, 0);
+    {
+        const dim3 blk(64, 4);
+        const dim3 grd((unsigned)((g.L[0].pitch / 4 + 63) / 64), (unsigned)((g.L[0].h + 3) / 4), (unsigned)batch);
+        const int aligned4 = ((reinterpret_cast<uintptr_t>(d_imgs) | step | frame_stride) & 3) == 0;
+        if (channels == 3) k_gray<3><<<grd, blk, 0, c->stream>>>(d_imgs, frame_stride, step, aligned4, g, pyr);
+        else               k_gray<1><<<grd, blk, 0, c->stream>>>(d_imgs, frame_stride, step, aligned4, g, pyr);
+        ++c->launches;
+    }
+    stage_mark(c, 1);
+    for (int l = 1; l < g.nlevels; ++l) {
+        if (g.L[l].w <= 0 || g.L[l].h <= 0) continue;
+        const dim3 blk(64, 4);
+        const dim3 grd((unsigned)((g.L[l].pitch / 4 + 63) / 64), (unsigned)((g.L[l].h + 3) / 4), (unsigned)batch);
+        k_pyr_down<<<grd, blk, 0, c->stream>>>(g, l, pyr, (const uint32_t*)c->tabs.p);
+        ++c->launches;
+    }
+    stage_mark(c, 2);
+    if (g.total_bands > 0) {
+        k_fast_bands<FAST_R, FAST_CW, FAST_NT><<<dim3((unsigned)g.total_bands, (unsigned)batch), FAST_NT, 0, c->stream>>>(
+            g, pyr, (uint32_t*)c->rowcnt.p, (uint32_t*)c->rowent.p);
+        ++c->launches;
+    }
+    stage_mark(c, 3);
+    k_select<<<dim3((unsigned)g.nlevels, (unsigned)batch), SEL_NT, 0, c->stream>>>(
+        g, pyr, (const uint32_t*)c->rowcnt.p, (const uint32_t*)c->rowent.p, (Elem*)c->work.p, (int*)c->fincnt.p, (int*)c->status.p);
+    ++c->launches;
+    stage_mark(c, 4);
+    k_describe<<<dim3((unsigned)((std::max(cap, 1) + DESC_KPB - 1) / DESC_KPB), (unsigned)batch), DESC_NT, 0, c->stream>>>(
+        g, pyr, (const Elem*)c->work.p, (const int*)c->fincnt.p, (const int8_t*)c->pattern.p, d_kps, d_desc, d_counts, cap);
+    ++c->launches;
+    stage_mark(c, 5);
+    CU(cudaGetLastError());
+    c->last_batch = batch;
+    if (c->profiling) for (int i = 0; i < 5; ++i) c->stage_valid[i] = true;
+    return ORBX_OK;
+}
+
+int check_args_extract(orbx_ctx* c, int batch, int w, int h, int channels, int cap)
+{
+    if (!c) return ORBX_E_ARG;
+    if (batch < 0 || batch > c->max_batch) return fail(c, ORBX_E_ARG, "batch outside [0, max_batch]");
+    if (w < 0 || h < 0 || w > c->max_w || h > c->max_h) return fail(c, ORBX_E_ARG, "frame larger than the context maximum");
+    if (channels != 1 && channels != 3) return fail(c, ORBX_E_UNSUPPORTED, "channels must be 1 (gray) or 3 (BGR)");
+    if (cap < 0) return fail(c, ORBX_E_ARG, "negative capacity");
+    return ORBX_OK;
+}
+
+int run_match(orbx_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int nsets, int4* d_best, int4* d_second)
+{
+    if (nt >= MT_MAX_TRAIN) return fail(c, ORBX_E_UNSUPPORTED, "train set larger than 2^20 - 1 rows");
+    const bool knn2 = d_second != nullptr;
+    const int tiles_m = (nq + MT_QROWS - 1) / MT_QROWS;
+    const int ntile_n = (nt + MT_BN - 1) / MT_BN;
+    int nsplit = 1;
+    if (!knn2) {
+        const long base = (long)tiles_m * nsets;
+        nsplit = (int)std::min<long>(ntile_n, std::max<long>(1, (2 * 148 + base - 1) / base));
+    }
+    const int tiles_per_split = (ntile_n + nsplit - 1) / nsplit;
+    const int rows_per_split = tiles_per_split * MT_BN;
+    nsplit = (nt + rows_per_split - 1) / rows_per_split;
+    int* keys = nullptr;
+    const size_t nout = (size_t)nq * nsets;
+    int rc;
+    if ((rc = ensure(c, c->mstatus, sizeof(int)))) return rc;
+    CU(cudaMemsetAsync(c->mstatus.p, 0, sizeof(int), c->stream));
+    stage_mark(c, 6);
+    if (nsplit > 1) {
+        if ((rc = ensure(c, c->mkeys, nout * sizeof(int)))) return rc;
+        keys = (int*)c->mkeys.p;
+        k_match_keys_init<<<(unsigned)((nout + 255) / 256), 256, 0, c->stream>>>(keys, nout);
+        ++c->launches;
+    }
+    const dim3 grd((unsigned)tiles_m, (unsigned)nsplit, (unsigned)nsets);
+    if (knn2) k_hamming_umma<true><<<grd, MT_THREADS, MT_SMEM_BYTES, c->stream>>>(d_q, nq, d_t, nt, nsplit, rows_per_split, d_best, d_second, keys, (int*)c->mstatus.p);
+    else      k_hamming_umma<false><<<grd, MT_THREADS, MT_SMEM_BYTES, c->stream>>>(d_q, nq, d_t, nt, nsplit, rows_per_split, d_best, d_second, keys, (int*)c->mstatus.p);
+    ++c->launches;
+    if (nsplit > 1) {
+        k_match_finalize<<<(unsigned)((nout + 255) / 256), 256, 0, c->stream>>>(keys, nq, nout, d_best);
+        ++c->launches;
+    }
+    stage_mark(c, 7);
+    if (c->profiling) c->stage_valid[5] = true;
+    CU(cudaGetLastError());
+    return ORBX_OK;
+}
+
+int match_host(orbx_ctx* c, const uint8_t* query, int nq, const uint8_t* train, int nt, orbx_match* out, int* n_out, bool knn2)
+{
+    if (!c) return ORBX_E_ARG;
+    if (n_out) *n_out = 0;
+    if (nq < 0 || nt < 0) return fail(c, ORBX_E_ARG, "negative row count");
+    if (nq == 0 || nt == 0) return ORBX_OK;                 // cv: empty query or train -> no matches, no throw
+    if (!query || !train || !out) return fail(c, ORBX_E_ARG, "null pointer");
+    CU(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = ensure(c, c->mq, (size_t)nq * 32))) return rc;
+    if ((rc = ensure(c, c->mt, (size_t)nt * 32))) return rc;
+    if ((rc = ensure(c, c->mbest, (size_t)nq * 16))) return rc;
+    if (knn2 && (rc = ensure(c, c->msecond, (size_t)nq * 16))) return rc;
+    CU(cudaMemcpyAsync(c->mq.p, query, (size_t)nq * 32, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->mt.p, train, (size_t)nt * 32, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = run_match(c, (const uint8_t*)c->mq.p, nq, (const uint8_t*)c->mt.p, nt, 1, (int4*)c->mbest.p, knn2 ? (int4*)c->msecond.p : nullptr))) return rc;
+    if (!knn2) {
+        CU(cudaMemcpyAsync(out, c->mbest.p, (size_t)nq * 16, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        CU(cudaMemcpy2DAsync(out, 32, c->mbest.p, 16, 16, (size_t)nq, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpy2DAsync(out + 1, 32, c->msecond.p, 16, 16, (size_t)nq, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaMemcpyAsync(c->h_small, c->mstatus.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->h_small[0]) return fail(c, ORBX_E_INTERNAL, "matcher pipeline timed out on an mbarrier (device status set)");
+    if (n_out) *n_out = nq;
+    return ORBX_OK;
+}
+
+}  // namespace
+
+// =================================================================================================== C-ABI
+extern "C" {
+
+const char* orbx_version(void) { return "orbx 0.1 (sm_100a; tcgen05 int8 matcher)"; }
+
+int orbx_create(orbx_ctx** out, int device, int nfeatures, float scale_factor, int nlevels, int max_w, int max_h, int max_batch)
+{
+    if (!out) return ORBX_E_ARG;
+    *out = nullptr;
+    if (nfeatures < 0 || nlevels < 1 || nlevels > ORBX_LEVELS_MAX || !(scale_factor > 1.0f) || max_w < 1 || max_h < 1 ||
+        max_w > 65535 || max_h > 65535 || max_batch < 1 || max_batch > 65535)
+        return ORBX_E_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return ORBX_E_CUDA;
+    orbx_ctx* c = new (std::nothrow) orbx_ctx();
+    if (!c) return ORBX_E_NOMEM;
+    c->device = device; c->nfeatures = nfeatures; c->scale_factor = scale_factor; c->nlevels = nlevels;
+    c->max_w = max_w; c->max_h = max_h; c->max_batch = max_batch;
+    auto bail = [&](int code) { orbx_destroy(c); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(ORBX_E_CUDA);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(ORBX_E_CUDA);
+    if (prop.major != 10) return bail(ORBX_E_CUDA);          // sm_100a only: no other code path exists
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(ORBX_E_CUDA);
+    for (int i = 0; i < N_STAGES + 2; ++i) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail(ORBX_E_CUDA);
+    build_geom(c, max_w, max_h, &c->geom_max, nullptr);
+    const Geom& g = c->geom_max;
+    const size_t B = (size_t)max_batch;
+    if (ensure(c, c->pyr, g.pyr_frame * B) || ensure(c, c->rowcnt, g.cnt_frame * 4 * B) || ensure(c, c->rowent, g.ent_frame * 4 * B) ||
+        ensure(c, c->work, g.ws_frame * sizeof(Elem) * B) || ensure(c, c->fincnt, sizeof(int) * ORBX_LEVELS_MAX * B) ||
+        ensure(c, c->status, sizeof(int) * B) || ensure(c, c->pattern, sizeof k_pattern_host))
+        return bail(ORBX_E_NOMEM);
+    if (cudaMemcpy(c->pattern.p, k_pattern_host, sizeof k_pattern_host, cudaMemcpyHostToDevice) != cudaSuccess) return bail(ORBX_E_CUDA);
+    if (cudaMemcpyToSymbol(c_umax, k_umax_host, sizeof k_umax_host) != cudaSuccess) return bail(ORBX_E_CUDA);
+    if (cudaMemset(c->status.p, 0, sizeof(int) * B) != cudaSuccess) return bail(ORBX_E_CUDA);
+    if (cudaMallocHost((void**)&c->h_small, sizeof(int) * (2 * B + 4)) != cudaSuccess) return bail(ORBX_E_NOMEM);
+    if (cudaFuncSetAttribute(k_hamming_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_hamming_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES) != cudaSuccess)
+        return bail(ORBX_E_CUDA);
+    *out = c;
+    return ORBX_OK;
+}
+
+void orbx_destroy(orbx_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    Buf* bufs[] = {&c->pyr, &c->rowcnt, &c->rowent, &c->work, &c->fincnt, &c->status, &c->tabs, &c->pattern, &c->in, &c->kps,
+                   &c->desc, &c->counts, &c->mq, &c->mt, &c->mbest, &c->msecond, &c->mkeys, &c->mstatus};
+    for (Buf* b : bufs) if (b->p) cudaFree(b->p);
+    if (c->h_small) cudaFreeHost(c->h_small);
+    for (int i = 0; i < N_STAGES + 2; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* orbx_last_error(const orbx_ctx* c) { return c ? c->err.c_str() : "null context"; }
+void* orbx_stream(orbx_ctx* c) { return c ? (void*)c->stream : nullptr; }
+uint64_t orbx_launch_count(const orbx_ctx* c) { return c ? c->launches : 0; }
+
+int orbx_synchronize(orbx_ctx* c)
+{
+    if (!c) return ORBX_E_ARG;
+    CU(cudaSetDevice(c->device));
+    const int b = c->last_batch;
+    if (b > 0) CU(cudaMemcpyAsync(c->h_small, c->status.p, sizeof(int) * (size_t)b, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < b; ++i)
+        if (c->h_small[i] & 1) return fail(c, ORBX_E_ORDER, "introselect depth limit hit: libstdc++ heap-select order not reproduced");
+    return ORBX_OK;
+}
+
+int orbx_detect_and_compute_device(orbx_ctx* c, const uint8_t* d_imgs, int batch, int w, int h, size_t step, size_t frame_stride,
+                                   int channels, orbx_keypoint* d_kps, uint8_t* d_desc, int cap, int* d_counts)
+{
+    int rc = check_args_extract(c, batch, w, h, channels, cap);
+    if (rc) return rc;
+    if (batch == 0) return ORBX_OK;
+    if (!d_imgs || !d_kps || !d_desc || !d_counts) return fail(c, ORBX_E_ARG, "null pointer");
+    if (w == 0 || h == 0) return fail(c, ORBX_E_ARG, "empty frames are only accepted by the host entry points");
+    if (step < (size_t)w * channels) return fail(c, ORBX_E_ARG, "step smaller than a row");
+    CU(cudaSetDevice(c->device));
+    return run_extract(c, d_imgs, batch, w, h, step, frame_stride, channels, (float*)d_kps, d_desc, cap, d_counts);
+}
+
+int orbx_detect_and_compute_batch(orbx_ctx* c, const uint8_t* const* imgs, int batch, int w, int h, size_t step, int channels,
+                                  orbx_keypoint* kps, uint8_t* desc, int cap, int* n_out)
+{
+    int rc = check_args_extract(c, batch, w, h, channels, cap);
+    if (rc) return rc;
+    if (n_out) for (int i = 0; i < batch; ++i) n_out[i] = 0;
+    if (batch == 0 || w == 0 || h == 0) return ORBX_OK;     // cv: empty image -> silent return, no keypoints
+    if (!imgs || !n_out || (cap > 0 && (!kps || !desc))) return fail(c, ORBX_E_ARG, "null pointer");
+    if (step < (size_t)w * channels) return fail(c, ORBX_E_ARG, "step smaller than a row");
+    CU(cudaSetDevice(c->device));
+    const size_t row = (size_t)w * channels, dstep = round_up(row, 4), fstride = dstep * h;
+    if ((rc = ensure(c, c->in, fstride * batch))) return rc;
+    if ((rc = ensure(c, c->kps, sizeof(orbx_keypoint) * (size_t)std::max(cap, 1) * batch))) return rc;
+    if ((rc = ensure(c, c->desc, (size_t)32 * std::max(cap, 1) * batch))) return rc;
+    if ((rc = ensure(c, c->counts, sizeof(int) * (size_t)batch))) return rc;
+    for (int i = 0; i < batch; ++i) {
+        if (!imgs[i]) return fail(c, ORBX_E_ARG, "null frame pointer");
+        CU(cudaMemcpy2DAsync((uint8_t*)c->in.p + fstride * i, dstep, imgs[i], step, row, (size_t)h, cudaMemcpyHostToDevice, c->stream));
+    }
+    if ((rc = run_extract(c, (const uint8_t*)c->in.p, batch, w, h, dstep, fstride, channels, (float*)c->kps.p, (uint8_t*)c->desc.p, cap,
+                          (int*)c->counts.p)))
+        return rc;
+    int* h_counts = c->h_small;
+    int* h_status = c->h_small + batch;
+    CU(cudaMemcpyAsync(h_counts, c->counts.p, sizeof(int) * (size_t)batch, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(h_status, c->status.p, sizeof(int) * (size_t)batch, cudaMemcpyDeviceToHost, c->stream));
+    if (cap > 0) {
+        // outputs are [batch][cap] on both sides: two bulk copies (records past n_out[i] are unspecified)
+        CU(cudaMemcpyAsync(kps, c->kps.p, sizeof(orbx_keypoint) * (size_t)cap * batch, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(desc, c->desc.p, (size_t)32 * cap * batch, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    bool over = false;
+    for (int i = 0; i < batch; ++i) {
+        if (h_status[i] & 1) return fail(c, ORBX_E_ORDER, "introselect depth limit hit: libstdc++ heap-select order not reproduced");
+        n_out[i] = h_counts[i];
+        if (h_counts[i] > cap) over = true;
+    }
+    if (over) return fail(c, ORBX_E_CAPACITY, "output capacity too small; n_out holds the needed counts");
+    return ORBX_OK;
+}
+
+int orbx_detect_and_compute(orbx_ctx* c, const uint8_t* img, int w, int h, size_t step, int channels, orbx_keypoint* kps,
+                            uint8_t* desc, int cap, int* n_out)
+{
+    if (!c) return ORBX_E_ARG;
+    if (!n_out) return fail(c, ORBX_E_ARG, "null n_out");
+    *n_out = 0;
+    if (w == 0 || h == 0 || !img) { if (!img && w > 0 && h > 0) return fail(c, ORBX_E_ARG, "null image"); return ORBX_OK; }
+    const uint8_t* one[1] = {img};
+    return orbx_detect_and_compute_batch(c, one, 1, w, h, step, channels, kps, desc, cap, n_out);
+}
+
+int orbx_match_hamming(orbx_ctx* c, const uint8_t* q, int nq, const uint8_t* t, int nt, orbx_match* out, int* n_out)
+{
+    return match_host(c, q, nq, t, nt, out, n_out, false);
+}
+int orbx_match_hamming_knn2(orbx_ctx* c, const uint8_t* q, int nq, const uint8_t* t, int nt, orbx_match* out, int* n_out)
+{
+    return match_host(c, q, nq, t, nt, out, n_out, true);
+}
+
+int orbx_match_hamming_device(orbx_ctx* c, const uint8_t* d_query, int nq, const uint8_t* d_train, int nt, int nsets,
+                              orbx_match* d_best, orbx_match* d_second)
+{
+    if (!c) return ORBX_E_ARG;
+    if (nq < 0 || nt < 0 || nsets < 0 || nsets > 65535) return fail(c, ORBX_E_ARG, "bad sizes");
+    if (nq == 0 || nt == 0 || nsets == 0) return ORBX_OK;
+    if (!d_query || !d_train || !d_best) return fail(c, ORBX_E_ARG, "null pointer");
+    CU(cudaSetDevice(c->device));
+    return run_match(c, d_query, nq, d_train, nt, nsets, (int4*)d_best, (int4*)d_second);
+}
+
+int orbx_filter_matches(orbx_match* m, int n, float ratio)
+{
+    if (!m || n <= 0) return 0;
+    float mn = m[0].distance;
+    for (int i = 1; i < n; ++i) mn = std::min(mn, m[i].distance);
+    const float mx = std::max(mn * ratio, 30.0f);
+    int k = 0;
+    for (int i = 0; i < n; ++i) if (m[i].distance <= mx) m[k++] = m[i];
+    return k;
+}
+
+int orbx_level_geometry(const orbx_ctx* c, int w, int h, int* ws, int* hs, float* scales, int* quotas)
+{
+    if (!c || w < 0 || h < 0) return ORBX_E_ARG;
+    int a[ORBX_LEVELS_MAX], b[ORBX_LEVELS_MAX], q[ORBX_LEVELS_MAX];
+    float s[ORBX_LEVELS_MAX];
+    level_sizes(w, h, c->nlevels, c->scale_factor, a, b, s);
+    level_quotas(c->nfeatures, c->scale_factor, c->nlevels, q);
+    for (int l = 0; l < c->nlevels; ++l) {
+        if (ws) ws[l] = a[l];
+        if (hs) hs[l] = b[l];
+        if (scales) scales[l] = s[l];
+        if (quotas) quotas[l] = q[l];
+    }
+    return ORBX_OK;
+}
+
+int orbx_debug_read_level(orbx_ctx* c, int frame, int level, uint8_t* out, size_t out_bytes)
+{
+    if (!c || !out) return ORBX_E_ARG;
+    if (frame < 0 || frame >= c->last_batch || level < 0 || level >= c->geom.nlevels) return fail(c, ORBX_E_ARG, "frame/level out of range");
+    const LevelGeom& L = c->geom.L[level];
+    if (out_bytes < (size_t)L.w * L.h) return fail(c, ORBX_E_CAPACITY, "buffer too small");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    if (L.w > 0 && L.h > 0)
+        CU(cudaMemcpy2D(out, (size_t)L.w, (const uint8_t*)c->pyr.p + (size_t)frame * c->geom.pyr_frame + L.img_off, (size_t)L.pitch,
+                        (size_t)L.w, (size_t)L.h, cudaMemcpyDeviceToHost));
+    return ORBX_OK;
+}
+
+int orbx_debug_read_fast(orbx_ctx* c, int frame, int level, int32_t* x, int32_t* y, int32_t* score, int cap, int* n_out)
+{
+    if (!c || !n_out) return ORBX_E_ARG;
+    *n_out = 0;
+    if (frame < 0 || frame >= c->last_batch || level < 0 || level >= c->geom.nlevels) return fail(c, ORBX_E_ARG, "frame/level out of range");
+    const Geom& g = c->geom;
+    const LevelGeom& L = g.L[level];
+    if (L.in_h <= 0) return ORBX_OK;
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    std::vector<uint32_t> cnt((size_t)L.in_h), ent((size_t)L.in_h * L.ent_pitch);
+    CU(cudaMemcpy(cnt.data(), (const uint32_t*)c->rowcnt.p + (size_t)frame * g.cnt_frame + L.cnt_off, cnt.size() * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(ent.data(), (const uint32_t*)c->rowent.p + (size_t)frame * g.ent_frame + L.ent_off, ent.size() * 4, cudaMemcpyDeviceToHost));
+    int n = 0;
+    for (int r = 0; r < L.in_h; ++r)
+        for (uint32_t i = 0; i < cnt[r]; ++i, ++n)
+            if (n < cap) {
+                const uint32_t e = ent[(size_t)r * L.ent_pitch + i];
+                if (x) x[n] = (int)(e & 0xffffu);
+                if (y) y[n] = r + ORBX_EDGE;
+                if (score) score[n] = (int)(e >> 16);
+            }
+    *n_out = n;
+    return n > cap ? ORBX_E_CAPACITY : ORBX_OK;
+}
+
+int orbx_set_profiling(orbx_ctx* c, int enable)
+{
+    if (!c) return ORBX_E_ARG;
+    c->profiling = enable != 0;
+    for (int i = 0; i < N_STAGES; ++i) c->stage_valid[i] = false;
+    return ORBX_OK;
+}
+
+int orbx_debug_stage_times(orbx_ctx* c, const char** names, float* ms, int cap)
+{
+    if (!c) return ORBX_E_ARG;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    int n = 0;
+    for (int i = 0; i < N_STAGES && n < cap; ++i) {
+        if (!c->stage_valid[i]) continue;
+        float t = 0.f;
+        const int e0 = i < 5 ? i : 6;
+        if (cudaEventElapsedTime(&t, c->ev[e0], c->ev[e0 + 1]) != cudaSuccess) continue;
+        if (names) names[n] = k_stage_names[i];
+        if (ms) ms[n] = t;
+        ++n;
+    }
+    return n;
+}
+
+}  // extern "C"

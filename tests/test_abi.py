@@ -1,0 +1,80 @@
+"""CPU-side checks of the drop-in boundary: liborbx.so builds/loads, exports every symbol include/orbx.h declares,
+record layouts equal cv::KeyPoint / cv::DMatch, and the library refuses to run without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "orbx.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(orbx_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    from rgbd_visualodometry_b200 import _lib
+    lib = _lib.load()
+    decl = _declared()
+    assert len(decl) >= 18
+    for name in decl:
+        assert hasattr(lib, name), f"{name} declared in include/orbx.h but not exported"
+    assert sorted(_lib.SYMBOLS) == decl, "python binding table and header disagree"
+    assert b"sm_100a" in lib.orbx_version()
+
+
+def test_record_layouts():
+    from rgbd_visualodometry_b200 import _lib, orb
+    assert C.sizeof(_lib.Keypoint) == 28 == orb.KP_DTYPE.itemsize          # cv::KeyPoint
+    assert C.sizeof(_lib.Match) == 16 == orb.DMATCH_DTYPE.itemsize         # cv::DMatch
+    assert [orb.KP_DTYPE.fields[n][1] for n in ("x", "y", "size", "angle", "response", "octave", "class_id")] == [0, 4, 8, 12, 16, 20, 24]
+    assert [orb.DMATCH_DTYPE.fields[n][1] for n in ("queryIdx", "trainIdx", "imgIdx", "distance")] == [0, 4, 8, 12]
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, never compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from rgbd_visualodometry_b200 import orb
+    with pytest.raises(orb.OrbxError) as e:
+        orb.Context()
+    assert e.value.code == orb.E_CUDA
+    with pytest.raises(orb.OrbxError):
+        orb.ORB_create(500).detectAndCompute(np.zeros((480, 640, 3), np.uint8))
+    with pytest.raises(orb.OrbxError):
+        orb.BFMatcher(orb.NORM_HAMMING)
+
+
+def test_create_rejects_bad_arguments():
+    from rgbd_visualodometry_b200 import _lib
+    lib = _lib.load()
+    h = C.c_void_p()
+    assert lib.orbx_create(C.byref(h), 0, 500, 1.2, 0, 640, 480, 1) == -1      # nlevels < 1
+    assert lib.orbx_create(C.byref(h), 0, 500, 1.0, 8, 640, 480, 1) == -1      # scale factor must exceed 1
+    assert lib.orbx_create(None, 0, 500, 1.2, 8, 640, 480, 1) == -1
+    assert lib.orbx_last_error(None) == b"null context"
+
+
+def test_filter_matches_host_glue(oracle):
+    """orbx_filter_matches == the reference's threshold loop (src/frontend.cpp:190-211) == oracle restatement."""
+    from rgbd_visualodometry_b200 import orb
+    from rgbd_visualodometry_b200.synth import synth_descriptors, synth_map_queries
+    t = synth_descriptors(400, 3)
+    m = oracle.match_hamming(synth_map_queries(t, 250, 4), t)
+    assert orb.filter_matches(m.astype(orb.DMATCH_DTYPE), 2.0).tobytes() == oracle.filter_matches(m, 2.0).tobytes()
+    assert len(orb.filter_matches(np.zeros(0, orb.DMATCH_DTYPE))) == 0
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under the package may reference it (or cv2)."""
+    pkg = os.path.join(ROOT, "rgbd_visualodometry_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                s = open(os.path.join(dp, f)).read()
+                assert "import cv2" not in s and "from oracle" not in s and "import oracle" not in s and "orb_oracle" not in s, f

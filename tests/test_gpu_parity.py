@@ -1,0 +1,244 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C-ABI of liborbx.so,
+against (a) the committed cv2 golden vectors, (b) the CPU oracle on the same seeded inputs, (c) cv2 itself when
+importable, and (d) size-independent properties at BASELINE.json's full sizes.
+
+Bar: bit-exact everywhere -- keypoint records (all 7 cv::KeyPoint fields, order included), descriptors, match
+indices and distances.  (north_star allows 1e-4 relative on Harris responses and angles; the restatement is in
+fact bit-exact, so the tests assert equality and report the tolerance only in the failure message.)"""
+import os
+
+import numpy as np
+import pytest
+
+from cases import MATCH_CASES, ORB_CASES, ORB_CASES_LARGE
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def orbmod():
+    from rgbd_visualodometry_b200 import orb
+    return orb
+
+
+def _assert_kp_equal(k, d, ko, do, what):
+    assert len(k) == len(ko), f"{what}: count {len(k)} vs {len(ko)}"
+    for f in ko.dtype.names:
+        bad = int((k[f] != ko[f]).sum())
+        assert bad == 0, f"{what}: field {f} differs on {bad} keypoints (tolerance allowed by north_star: 1e-4 rel on response/angle)"
+    assert np.array_equal(d, do), f"{what}: {int((d != do).any(axis=1).sum())} descriptors differ"
+
+
+@pytest.mark.parametrize("name", list(ORB_CASES))
+def test_orb_vs_golden(orbmod, name):
+    mk, n = ORB_CASES[name]
+    img = mk()
+    g = np.load(os.path.join(GOLD, f"orb_{name}.npz"))
+    k, d = orbmod.ORB_create(n, 1.2, 8).detectAndCompute(img, None)
+    gd = g["descriptors"]
+    if len(g["keypoints"]) == 0:
+        assert len(k) == 0 and d is None          # cv2 returns ((), None)
+        return
+    _assert_kp_equal(k, d, g["keypoints"], gd, f"golden {name}")
+
+
+@pytest.mark.parametrize("name", list(ORB_CASES_LARGE))
+def test_orb_vs_oracle_large(orbmod, oracle, name):
+    mk, n = ORB_CASES_LARGE[name]
+    img = mk()
+    k, d = orbmod.ORB_create(n, 1.2, 8).detectAndCompute(img, None)
+    ko, do = oracle.detect_and_compute(img, n)
+    _assert_kp_equal(k, d, ko, do, f"oracle {name}")
+
+
+def test_orb_stages_vs_oracle(orbmod, oracle):
+    """Each kernel in isolation: pyramid levels and the raster-ordered FAST+NMS lists."""
+    from rgbd_visualodometry_b200.synth import synth_frame
+    img = synth_frame(467, 701, 21)
+    ctx = orbmod.Context(700, 1.2, 8, 701, 467, 1)
+    ctx.detect_and_compute(img)
+    _, _, dump = oracle.detect_and_compute(img, 700, dump=True)
+    ws, hs, sc, q = ctx.level_geometry(701, 467)
+    ows, ohs, osc = oracle.level_geometry(701, 467)
+    assert ws.tolist() == ows and hs.tolist() == ohs and sc.tobytes() == osc.tobytes() and q.tolist() == oracle.quotas(700)
+    for l in range(8):
+        assert np.array_equal(ctx.debug_level(0, l, ows[l], ohs[l]), dump["levels"][l]), f"level {l}"
+        x, y, s = ctx.debug_fast(0, l)
+        fo = dump["fast"][l]
+        assert np.array_equal(x, fo["x"]) and np.array_equal(y, fo["y"]) and np.array_equal(s, fo["response"].astype(np.int32)), f"FAST level {l}"
+    ctx.close()
+
+
+def test_orb_batch_and_strided(orbmod, oracle):
+    """Batch of distinct frames == per-frame results; a padded row step (cv::Mat::step) is honoured."""
+    from rgbd_visualodometry_b200.synth import synth_frame
+    frames = [synth_frame(240, 320, 100 + i) for i in range(5)]
+    ctx = orbmod.Context(300, 1.2, 8, 320, 240, 8)
+    kps, desc, cnt = ctx.detect_and_compute_batch(frames)
+    for i, fr in enumerate(frames):
+        ko, do = oracle.detect_and_compute(fr, 300)
+        _assert_kp_equal(kps[i, :cnt[i]], desc[i, :cnt[i]], ko, do, f"batch frame {i}")
+    padded = np.zeros((240, 333, 3), np.uint8)
+    padded[:, :320] = frames[0]
+    view = padded[:, :320]                                   # non-contiguous rows: step = 999 bytes
+    import ctypes as C
+    k = np.zeros(600, orbmod.KP_DTYPE); d = np.zeros((600, 32), np.uint8); n = C.c_int(0)
+    rc = ctx.lib.orbx_detect_and_compute(ctx.h, view.ctypes.data, 320, 240, view.strides[0], 3, k.ctypes.data, d.ctypes.data, 600, C.byref(n))
+    assert rc == 0
+    ko, do = oracle.detect_and_compute(frames[0], 300)
+    _assert_kp_equal(k[:n.value], d[:n.value], ko, do, "strided")
+    ctx.close()
+
+
+def test_orb_capacity_and_empty(orbmod):
+    import ctypes as C
+    from rgbd_visualodometry_b200.synth import synth_frame
+    ctx = orbmod.Context(500, 1.2, 8, 640, 480, 1)
+    img = synth_frame(480, 640, 0)
+    k = np.zeros(100, orbmod.KP_DTYPE); d = np.zeros((100, 32), np.uint8); n = C.c_int(0)
+    rc = ctx.lib.orbx_detect_and_compute(ctx.h, img.ctypes.data, 640, 480, 1920, 3, k.ctypes.data, d.ctypes.data, 100, C.byref(n))
+    assert rc == orbmod.E_CAPACITY and n.value == 500            # never truncates silently: reports the need
+    rc = ctx.lib.orbx_detect_and_compute(ctx.h, img.ctypes.data, 0, 0, 0, 3, k.ctypes.data, d.ctypes.data, 100, C.byref(n))
+    assert rc == 0 and n.value == 0                              # empty image: silent, no keypoints
+    rc = ctx.lib.orbx_detect_and_compute(ctx.h, img.ctypes.data, 641, 480, 1923, 3, k.ctypes.data, d.ctypes.data, 100, C.byref(n))
+    assert rc == orbmod.E_ARG
+    rc = ctx.lib.orbx_detect_and_compute(ctx.h, img.ctypes.data, 640, 480, 1280, 2, k.ctypes.data, d.ctypes.data, 100, C.byref(n))
+    assert rc == orbmod.E_UNSUPPORTED
+    assert orbmod.ORB_create(500).detectAndCompute(np.zeros((0, 0, 3), np.uint8))[1] is None
+    ctx.close()
+
+
+def test_orb_gray_equals_bgr(orbmod):
+    """ORB(BGR) == ORB(gray(BGR)) (SURVEY probe E2) -- uses the library's own level 0 as the gray image."""
+    from rgbd_visualodometry_b200.synth import synth_frame
+    img = synth_frame(300, 400, 77)
+    ctx = orbmod.Context(400, 1.2, 8, 400, 300, 1)
+    k1, d1 = ctx.detect_and_compute(img)
+    g = ctx.debug_level(0, 0, 400, 300)
+    k2, d2 = ctx.detect_and_compute(g)
+    assert k1.tobytes() == k2.tobytes() and np.array_equal(d1, d2)
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", list(MATCH_CASES))
+def test_match_vs_golden(orbmod, name):
+    mq, mt = MATCH_CASES[name]
+    q, t = mq(), mt()
+    g = np.load(os.path.join(GOLD, f"match_{name}.npz"))
+    bf = orbmod.BFMatcher(orbmod.NORM_HAMMING)
+    assert bf.match(q, t).tobytes() == g["match"].tobytes()
+    k2 = bf.knnMatch(q, t, k=2)
+    if len(t) >= 2:
+        assert k2.tobytes() == g["knn2"].tobytes()
+    else:
+        assert np.array_equal(k2["trainIdx"][:, 0], g["knn2"]["trainIdx"][:, 0]) and (k2["trainIdx"][:, 1] == -1).all()
+
+
+def test_match_empty(orbmod):
+    bf = orbmod.BFMatcher(orbmod.NORM_HAMMING)
+    e = np.zeros((0, 32), np.uint8); t = np.zeros((4, 32), np.uint8)
+    assert len(bf.match(e, t)) == 0 and len(bf.match(t, e)) == 0
+
+
+@pytest.mark.parametrize("m", [1000, 5000, 20000, 100000])
+def test_match_sweep_vs_oracle(orbmod, oracle, m):
+    """BASELINE config 3: map size sweep vs 2k frame descriptors, 'realistic' distribution (true matches + ties)."""
+    from rgbd_visualodometry_b200.synth import synth_descriptors, synth_map_queries
+    t = synth_descriptors(2000, 40)
+    q = synth_map_queries(t, m, 41)
+    got = orbmod.BFMatcher(orbmod.NORM_HAMMING).match(q, t)
+    if m <= 20000:
+        assert got.tobytes() == oracle.match_hamming(q, t).tobytes()
+    else:
+        # full size: size-independent properties + an oracle check on a sample of rows
+        assert np.array_equal(got["queryIdx"], np.arange(m)) and (got["imgIdx"] == 0).all()
+        rows = np.random.default_rng(0).choice(m, 4000, replace=False)
+        ref = oracle.match_hamming(q[rows], t)
+        assert np.array_equal(got["trainIdx"][rows], ref["trainIdx"]) and np.array_equal(got["distance"][rows], ref["distance"])
+        x = np.bitwise_xor(q, t[got["trainIdx"]])
+        assert np.array_equal(np.unpackbits(x, axis=1).sum(1).astype(np.float32), got["distance"])   # distance is the true Hamming of the pair
+
+
+def test_match_properties(orbmod):
+    """Self-match: every row's nearest neighbour in its own set is itself at distance 0; duplicated rows tie to the first."""
+    from rgbd_visualodometry_b200.synth import synth_descriptors
+    t = synth_descriptors(777, 9)
+    t[500:600] = t[100:200]
+    m = orbmod.BFMatcher(orbmod.NORM_HAMMING).match(t, t)
+    exp = np.arange(777); exp[500:600] = np.arange(100, 200)
+    assert np.array_equal(m["trainIdx"], exp) and (m["distance"] == 0).all()
+
+
+def test_match_device_batched(orbmod, oracle):
+    """Device-resident, batched over several frames' train sets sharing one map (BASELINE config 3, batched variant)."""
+    import torch
+    from rgbd_visualodometry_b200.synth import synth_descriptors, synth_map_queries
+    nsets, nt, nq = 3, 700, 1300
+    trains = np.stack([synth_descriptors(nt, 60 + i) for i in range(nsets)])
+    q = synth_map_queries(trains[0], nq, 70)
+    ctx = orbmod.Context(1, 1.2, 1, 64, 64, 1)
+    dq = torch.from_numpy(q).cuda(); dt = torch.from_numpy(trains).cuda()
+    best = torch.zeros((nsets, nq, 4), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.match_device(dq.data_ptr(), nq, dt.data_ptr(), nt, nsets, best.data_ptr())
+    ctx.synchronize()
+    got = best.cpu().numpy().view(orbmod.DMATCH_DTYPE).reshape(nsets, nq)
+    for s in range(nsets):
+        assert got[s].tobytes() == oracle.match_hamming(q, trains[s]).tobytes(), f"set {s}"
+    ctx.close()
+
+
+def test_orb_device_resident_full_size(orbmod, oracle):
+    """BASELINE config 2 shape: a device-resident batch of 640x480 frames, 1000 features; every frame checked."""
+    import torch
+    from rgbd_visualodometry_b200.synth import synth_frame
+    b, cap = 8, 2048
+    frames = np.stack([synth_frame(480, 640, 300 + i) for i in range(b)])
+    ctx = orbmod.Context(1000, 1.2, 8, 640, 480, b)
+    d_in = torch.from_numpy(frames).cuda()
+    d_k = torch.zeros((b, cap, 7), dtype=torch.float32, device="cuda")
+    d_d = torch.zeros((b, cap, 32), dtype=torch.uint8, device="cuda")
+    d_n = torch.zeros(b, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.detect_and_compute_device(d_in.data_ptr(), b, 640, 480, 1920, 480 * 1920, 3, d_k.data_ptr(), d_d.data_ptr(), cap, d_n.data_ptr())
+    ctx.synchronize()
+    n = d_n.cpu().numpy(); k = d_k.cpu().numpy().view(orbmod.KP_DTYPE).reshape(b, cap); d = d_d.cpu().numpy()
+    for i in range(b):
+        ko, do = oracle.detect_and_compute(frames[i], 1000)
+        _assert_kp_equal(k[i, :n[i]], d[i, :n[i]], ko, do, f"device frame {i}")
+    ctx.close()
+
+
+def test_frontend_pattern(orbmod, oracle):
+    """BASELINE config 1: the front-end's per-frame call pattern (1 extraction + 2 matches, src/frontend.cpp:98-108)
+    on a synthetic TUM-shaped sequence; map = descriptors of every 5th frame."""
+    from rgbd_visualodometry_b200.synth import synth_sequence
+    orb_g = orbmod.ORB_create(500, 1.2, 8)
+    bf = orbmod.BFMatcher(orbmod.NORM_HAMMING)
+    map_desc = None
+    for i, (color, depth) in enumerate(synth_sequence(480, 640, 6, seed=3)):
+        k, d = orb_g.detectAndCompute(color, None)
+        ko, do = oracle.detect_and_compute(color, 500)
+        _assert_kp_equal(k, d, ko, do, f"sequence frame {i}")
+        if map_desc is not None:
+            for _ in range(2):
+                m = bf.match(map_desc, d)
+                mo = oracle.match_hamming(map_desc, do)
+                assert m.tobytes() == mo.tobytes()
+                assert orbmod.filter_matches(m, 2.0).tobytes() == oracle.filter_matches(mo, 2.0).tobytes()
+        if i % 5 == 0:
+            map_desc = d if map_desc is None else np.concatenate([map_desc, d])
+
+
+def test_cv2_live_if_available(orbmod):
+    cv2 = pytest.importorskip("cv2")
+    from oracle import oracle as O
+    from rgbd_visualodometry_b200.synth import synth_descriptors, synth_frame, synth_map_queries
+    img = synth_frame(480, 640, 555)
+    k, d = orbmod.ORB_create(1000, 1.2, 8).detectAndCompute(img, None)
+    kc, dc = cv2.ORB_create(1000, 1.2, 8).detectAndCompute(img, None)
+    _assert_kp_equal(k, d, O.cv2_keypoints_to_array(kc), dc, "cv2 live")
+    t = synth_descriptors(2000, 1); q = synth_map_queries(t, 3000, 2)
+    m = orbmod.BFMatcher(orbmod.NORM_HAMMING).match(q, t)
+    assert m.tobytes() == O.cv2_matches_to_array(cv2.BFMatcher(cv2.NORM_HAMMING).match(q, t)).tobytes()
