@@ -110,6 +110,16 @@ int orbx_match_hamming_knn2(orbx_ctx* ctx, const uint8_t* query, int nq, const u
  * query set (the map): d_train is [nsets][nt][32], d_best / d_second are [nsets][nq] (d_second may be NULL). */
 int orbx_match_hamming_device(orbx_ctx* ctx, const uint8_t* d_query, int nq, const uint8_t* d_train, int nt,
                               int nsets, orbx_match* d_best, orbx_match* d_second);
+/* Ragged variant: set s holds min(d_train_counts[s], train_stride_rows) valid rows at d_train + s*train_stride_rows*32
+ * (exactly the [batch][cap][32] / d_counts layout orbx_detect_and_compute_device writes, so extraction feeds matching
+ * without a host round trip).  A query matched against an empty set gets trainIdx = -1, distance = 0. */
+int orbx_match_hamming_device_ragged(orbx_ctx* ctx, const uint8_t* d_query, int nq, const uint8_t* d_train,
+                                     int train_stride_rows, const int* d_train_counts, int nsets,
+                                     orbx_match* d_best, orbx_match* d_second);
+/* HOST-buffer form of the ragged batched match: one map (query) against `nsets` frames' descriptor sets
+ * ([nsets][train_stride_rows][32] with train_counts[nsets]); best / second are [nsets][nq] (second may be NULL). */
+int orbx_match_hamming_sets(orbx_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int train_stride_rows,
+                            const int* train_counts, int nsets, orbx_match* best, orbx_match* second);
 /* The reference's host-side post-filter (src/frontend.cpp:190-211): keep distance <= max(min*ratio, 30).
  * Pure host helper for the shim; in place compaction, returns the kept count. */
 int orbx_filter_matches(orbx_match* matches, int n, float match_ratio);

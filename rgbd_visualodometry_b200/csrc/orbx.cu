@@ -56,7 +56,7 @@ struct orbx_ctx {
     Buf pyr, rowcnt, rowent, work, fincnt, status, tabs, pattern;
     Buf in, kps, desc, counts;               // host-path staging on the device
     int out_cap = 0;
-    Buf mq, mt, mbest, msecond, mkeys, mstatus;
+    Buf mq, mt, mbest, msecond, mkeys, mstatus, mcounts;
     int* h_small = nullptr;                  // pinned: counts[max_batch] + status[max_batch] + 1
     int last_batch = 0;
 
@@ -255,7 +255,8 @@ int check_args_extract(orbx_ctx* c, int batch, int w, int h, int channels, int c
     return ORBX_OK;
 }
 
-int run_match(orbx_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int nsets, int4* d_best, int4* d_second)
+int run_match(orbx_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int stride_rows, const int* d_counts, int nsets,
+              int4* d_best, int4* d_second)
 {
     if (nt >= MT_MAX_TRAIN) return fail(c, ORBX_E_UNSUPPORTED, "train set larger than 2^20 - 1 rows");
     const bool knn2 = d_second != nullptr;
@@ -282,8 +283,8 @@ int run_match(orbx_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int n
         ++c->launches;
     }
     const dim3 grd((unsigned)tiles_m, (unsigned)nsplit, (unsigned)nsets);
-    if (knn2) k_hamming_umma<true><<<grd, MT_THREADS, MT_SMEM_BYTES, c->stream>>>(d_q, nq, d_t, nt, nsplit, rows_per_split, d_best, d_second, keys, (int*)c->mstatus.p);
-    else      k_hamming_umma<false><<<grd, MT_THREADS, MT_SMEM_BYTES, c->stream>>>(d_q, nq, d_t, nt, nsplit, rows_per_split, d_best, d_second, keys, (int*)c->mstatus.p);
+    if (knn2) k_hamming_umma<true><<<grd, MT_THREADS, MT_SMEM_BYTES, c->stream>>>(d_q, nq, d_t, nt, stride_rows, d_counts, rows_per_split, d_best, d_second, keys, (int*)c->mstatus.p);
+    else      k_hamming_umma<false><<<grd, MT_THREADS, MT_SMEM_BYTES, c->stream>>>(d_q, nq, d_t, nt, stride_rows, d_counts, rows_per_split, d_best, d_second, keys, (int*)c->mstatus.p);
     ++c->launches;
     if (nsplit > 1) {
         k_match_finalize<<<(unsigned)((nout + 255) / 256), 256, 0, c->stream>>>(keys, nq, nout, d_best);
@@ -310,7 +311,7 @@ int match_host(orbx_ctx* c, const uint8_t* query, int nq, const uint8_t* train, 
     if (knn2 && (rc = ensure(c, c->msecond, (size_t)nq * 16))) return rc;
     CU(cudaMemcpyAsync(c->mq.p, query, (size_t)nq * 32, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->mt.p, train, (size_t)nt * 32, cudaMemcpyHostToDevice, c->stream));
-    if ((rc = run_match(c, (const uint8_t*)c->mq.p, nq, (const uint8_t*)c->mt.p, nt, 1, (int4*)c->mbest.p, knn2 ? (int4*)c->msecond.p : nullptr))) return rc;
+    if ((rc = run_match(c, (const uint8_t*)c->mq.p, nq, (const uint8_t*)c->mt.p, nt, nt, nullptr, 1, (int4*)c->mbest.p, knn2 ? (int4*)c->msecond.p : nullptr))) return rc;
     if (!knn2) {
         CU(cudaMemcpyAsync(out, c->mbest.p, (size_t)nq * 16, cudaMemcpyDeviceToHost, c->stream));
     } else {
@@ -375,7 +376,7 @@ void orbx_destroy(orbx_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     Buf* bufs[] = {&c->pyr, &c->rowcnt, &c->rowent, &c->work, &c->fincnt, &c->status, &c->tabs, &c->pattern, &c->in, &c->kps,
-                   &c->desc, &c->counts, &c->mq, &c->mt, &c->mbest, &c->msecond, &c->mkeys, &c->mstatus};
+                   &c->desc, &c->counts, &c->mq, &c->mt, &c->mbest, &c->msecond, &c->mkeys, &c->mstatus, &c->mcounts};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     if (c->h_small) cudaFreeHost(c->h_small);
     for (int i = 0; i < N_STAGES + 2; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -482,7 +483,45 @@ int orbx_match_hamming_device(orbx_ctx* c, const uint8_t* d_query, int nq, const
     if (nq == 0 || nt == 0 || nsets == 0) return ORBX_OK;
     if (!d_query || !d_train || !d_best) return fail(c, ORBX_E_ARG, "null pointer");
     CU(cudaSetDevice(c->device));
-    return run_match(c, d_query, nq, d_train, nt, nsets, (int4*)d_best, (int4*)d_second);
+    return run_match(c, d_query, nq, d_train, nt, nt, nullptr, nsets, (int4*)d_best, (int4*)d_second);
+}
+
+int orbx_match_hamming_device_ragged(orbx_ctx* c, const uint8_t* d_query, int nq, const uint8_t* d_train, int train_stride_rows,
+                                     const int* d_train_counts, int nsets, orbx_match* d_best, orbx_match* d_second)
+{
+    if (!c) return ORBX_E_ARG;
+    if (nq < 0 || train_stride_rows < 0 || nsets < 0 || nsets > 65535) return fail(c, ORBX_E_ARG, "bad sizes");
+    if (nq == 0 || train_stride_rows == 0 || nsets == 0) return ORBX_OK;
+    if (!d_query || !d_train || !d_best || !d_train_counts) return fail(c, ORBX_E_ARG, "null pointer");
+    CU(cudaSetDevice(c->device));
+    return run_match(c, d_query, nq, d_train, train_stride_rows, train_stride_rows, d_train_counts, nsets, (int4*)d_best, (int4*)d_second);
+}
+
+int orbx_match_hamming_sets(orbx_ctx* c, const uint8_t* query, int nq, const uint8_t* train, int train_stride_rows,
+                            const int* train_counts, int nsets, orbx_match* best, orbx_match* second)
+{
+    if (!c) return ORBX_E_ARG;
+    if (nq < 0 || train_stride_rows < 0 || nsets < 0 || nsets > 65535) return fail(c, ORBX_E_ARG, "bad sizes");
+    if (nq == 0 || train_stride_rows == 0 || nsets == 0) return ORBX_OK;
+    if (!query || !train || !best || !train_counts) return fail(c, ORBX_E_ARG, "null pointer");
+    CU(cudaSetDevice(c->device));
+    const size_t tbytes = (size_t)nsets * train_stride_rows * 32, obytes = (size_t)nsets * nq * 16;
+    int rc;
+    if ((rc = ensure(c, c->mq, (size_t)nq * 32)) || (rc = ensure(c, c->mt, tbytes)) || (rc = ensure(c, c->mbest, obytes)) ||
+        (rc = ensure(c, c->mcounts, sizeof(int) * (size_t)nsets)) || (second && (rc = ensure(c, c->msecond, obytes))))
+        return rc;
+    CU(cudaMemcpyAsync(c->mq.p, query, (size_t)nq * 32, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->mt.p, train, tbytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->mcounts.p, train_counts, sizeof(int) * (size_t)nsets, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = run_match(c, (const uint8_t*)c->mq.p, nq, (const uint8_t*)c->mt.p, train_stride_rows, train_stride_rows, (const int*)c->mcounts.p,
+                        nsets, (int4*)c->mbest.p, second ? (int4*)c->msecond.p : nullptr)))
+        return rc;
+    CU(cudaMemcpyAsync(best, c->mbest.p, obytes, cudaMemcpyDeviceToHost, c->stream));
+    if (second) CU(cudaMemcpyAsync(second, c->msecond.p, obytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_small, c->mstatus.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->h_small[0]) return fail(c, ORBX_E_INTERNAL, "matcher pipeline timed out on an mbarrier (device status set)");
+    return ORBX_OK;
 }
 
 int orbx_filter_matches(orbx_match* m, int n, float ratio)

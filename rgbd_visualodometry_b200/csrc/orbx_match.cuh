@@ -114,9 +114,9 @@ __device__ __forceinline__ void expand_row(uint8_t* tile, int rows, int r, const
 //          else DMatch records are written directly.
 template <bool KNN2>
 __global__ void __launch_bounds__(MT_THREADS, 1)
-k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restrict__ train, int nt, int nsplit,
-               int rows_per_split, int4* __restrict__ best, int4* __restrict__ second, int* __restrict__ keys,
-               int* __restrict__ status)
+k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restrict__ train, int nt, int train_stride_rows,
+               const int* __restrict__ train_counts, int rows_per_split, int4* __restrict__ best, int4* __restrict__ second,
+               int* __restrict__ keys, int* __restrict__ status)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -129,9 +129,10 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int set = blockIdx.z, split = blockIdx.y;
     const int q0 = blockIdx.x * MT_QROWS;
-    const int n0 = split * rows_per_split, n1 = min(nt, n0 + rows_per_split);
-    const int ntiles = (n1 - n0 + MT_BN - 1) / MT_BN;
-    const uint8_t* tr = train + (size_t)set * nt * 32;
+    const int nvalid = train_counts ? max(0, min(__ldg(train_counts + set), nt)) : nt;   // ragged sets: rows actually present
+    const int n0 = split * rows_per_split, n1 = min(nvalid, n0 + rows_per_split);
+    const int ntiles = n1 > n0 ? (n1 - n0 + MT_BN - 1) / MT_BN : 0;
+    const uint8_t* tr = train + (size_t)set * train_stride_rows * 32;
 
     // ---- setup: LUT, barriers, TMEM, A tiles
     if (tid < 256) {
@@ -262,7 +263,10 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
         if (ok && qrow < nq) {
             const size_t o = (size_t)set * nq + qrow;
             if (keys) {
-                atomicMax(&keys[o], m1);
+                if (m1 != INT_MIN) atomicMax(&keys[o], m1);
+            } else if (m1 == INT_MIN) {                       // empty train set: no match (trainIdx -1)
+                best[o] = make_int4(qrow, -1, 0, 0);
+                if (KNN2) second[o] = make_int4(qrow, -1, 0, 0);
             } else {
                 const int dot = m1 >> MT_KEY_SHIFT, j = (MT_MAX_TRAIN - 1) - (m1 & (MT_MAX_TRAIN - 1));
                 best[o] = make_int4(qrow, j, 0, __float_as_int((float)((256 - dot) >> 1)));
@@ -297,6 +301,7 @@ __global__ void k_match_finalize(const int* __restrict__ keys, int nq, size_t n,
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int k = keys[i];
+    if (k == INT_MIN) { best[i] = make_int4((int)(i % (size_t)nq), -1, 0, 0); return; }
     const int dot = k >> MT_KEY_SHIFT, j = (MT_MAX_TRAIN - 1) - (k & (MT_MAX_TRAIN - 1));
     best[i] = make_int4((int)(i % (size_t)nq), j, 0, __float_as_int((float)((256 - dot) >> 1)));
 }

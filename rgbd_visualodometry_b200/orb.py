@@ -121,6 +121,22 @@ class Context:
         self._check(self.lib.orbx_match_hamming_device(self.h, d_query_ptr, nq, d_train_ptr, nt, nsets, d_best_ptr,
                                                        d_second_ptr or None))
 
+    def match_device_ragged(self, d_query_ptr: int, nq: int, d_train_ptr: int, stride_rows: int, d_counts_ptr: int, nsets: int,
+                            d_best_ptr: int, d_second_ptr: int = 0):
+        self._check(self.lib.orbx_match_hamming_device_ragged(self.h, d_query_ptr, nq, d_train_ptr, stride_rows, d_counts_ptr, nsets,
+                                                              d_best_ptr, d_second_ptr or None))
+
+    def match_sets(self, query: np.ndarray, train: np.ndarray, counts: np.ndarray, knn2: bool = False):
+        """One map (query [M,32]) against nsets frames' descriptor sets (train [S,cap,32], counts [S]); host buffers."""
+        q = np.ascontiguousarray(query, np.uint8).reshape(-1, 32)
+        t = np.ascontiguousarray(train, np.uint8)
+        cnt = np.ascontiguousarray(counts, np.int32)
+        s, cap = t.shape[0], t.shape[1]
+        best = np.zeros((s, len(q)), DMATCH_DTYPE)
+        second = np.zeros((s, len(q)), DMATCH_DTYPE) if knn2 else None
+        self._check(self.lib.orbx_match_hamming_sets(self.h, _ptr(q), len(q), _ptr(t), cap, _ptr(cnt), s, _ptr(best), _ptr(second)))
+        return (best, second) if knn2 else best
+
     # ---- misc -----------------------------------------------------------------------------------------------
     def synchronize(self):
         self._check(self.lib.orbx_synchronize(self.h))
