@@ -28,9 +28,9 @@ const int8_t k_pattern_host[256 * 4] = {
 };
 const int k_umax_host[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
-constexpr int FAST_R = 16, FAST_CW = 256, FAST_NT = 256;
+constexpr int FAST_R = 16, FAST_NT = 256;
 constexpr int N_STAGES = 6;
-const char* const k_stage_names[N_STAGES] = {"gray", "pyramid", "fast_nms", "select_harris", "describe", "match"};
+const char* const k_stage_names[N_STAGES] = {"gray", "pyramid", "fast_nms", "select_harris", "blur_describe", "match"};
 
 size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -53,7 +53,7 @@ struct orbx_ctx {
     int geom_w = 0, geom_h = 0;
     size_t tabs_len = 0;
 
-    Buf pyr, rowcnt, rowent, work, fincnt, status, tabs, pattern;
+    Buf pyr, blur, rowcnt, rowent, work, selpos, fincnt, status, tabs, pattern;
     Buf in, kps, desc, counts;               // host-path staging on the device
     int out_cap = 0;
     Buf mq, mt, mbest, msecond, mkeys, mstatus, mcounts;
@@ -148,7 +148,7 @@ void build_geom(const orbx_ctx* c, int w, int h, Geom* g, std::vector<uint32_t>*
     level_quotas(c->nfeatures, c->scale_factor, c->nlevels, q);
     g->nlevels = c->nlevels; g->w = w; g->h = h; g->band_rows = FAST_R;
     size_t pyr = 0, cnt = 0, ent = 0, wsz = 0, tab = 0;
-    int bands = 0;
+    int bands = 0, blurs = 0;
     for (int l = 0; l < c->nlevels; ++l) {
         LevelGeom& L = g->L[l];
         L.w = std::max(ws[l], 0); L.h = std::max(hs[l], 0);
@@ -159,13 +159,18 @@ void build_geom(const orbx_ctx* c, int w, int h, Geom* g, std::vector<uint32_t>*
         L.ent_pitch = (int)round_up((size_t)(L.in_w + 1) / 2 + 1, 8);
         L.ws_cap = std::max(((L.in_w + 1) / 2) * ((L.in_h + 1) / 2), 1);
         L.band0 = bands; L.nbands = (L.in_h + FAST_R - 1) / FAST_R; bands += L.nbands;
+        if (L.in_w > 0) {                                    // blur tiles: 128-column groups x (4 strips of BLUR_RH rows)
+            L.blur_cgs = (L.w - 13 - BLUR_LO + 127) / 128;
+            L.nblur = L.blur_cgs * ((L.h - 26 + 4 * BLUR_RH - 1) / (4 * BLUR_RH));
+        }
+        L.blur0 = blurs; blurs += L.nblur;
         L.img_off = pyr; pyr += round_up((size_t)L.pitch * std::max(L.h, 1), 256);
         L.cnt_off = cnt; cnt += round_up((size_t)std::max(L.in_h, 1), 8);
         L.ent_off = ent; ent += (size_t)L.ent_pitch * std::max(L.in_h, 1);
         L.ws_off = wsz; wsz += round_up((size_t)L.ws_cap, 4);
         if (l > 0) { L.xtab = (uint32_t)tab; tab += L.w; L.ytab = (uint32_t)tab; tab += L.h; }
     }
-    g->total_bands = bands;
+    g->total_bands = bands; g->total_blur = blurs;
     g->pyr_frame = round_up(pyr, 256); g->cnt_frame = cnt; g->ent_frame = ent; g->ws_frame = wsz;
     if (tabs) {
         tabs->assign(std::max<size_t>(tab, 1), 0);
@@ -226,17 +231,21 @@ int run_extract(orbx_ctx* c, const uint8_t* d_imgs, int batch, int w, int h, siz
     }
     stage_mark(c, 2);
     if (g.total_bands > 0) {
-        k_fast_bands<FAST_R, FAST_CW, FAST_NT><<<dim3((unsigned)g.total_bands, (unsigned)batch), FAST_NT, 0, c->stream>>>(
+        k_fast_bands<FAST_R, FAST_NT><<<dim3((unsigned)g.total_bands, (unsigned)batch), FAST_NT, 0, c->stream>>>(
             g, pyr, (uint32_t*)c->rowcnt.p, (uint32_t*)c->rowent.p);
         ++c->launches;
     }
     stage_mark(c, 3);
     k_select<<<dim3((unsigned)g.nlevels, (unsigned)batch), SEL_NT, 0, c->stream>>>(
-        g, pyr, (const uint32_t*)c->rowcnt.p, (const uint32_t*)c->rowent.p, (Elem*)c->work.p, (int*)c->fincnt.p, (int*)c->status.p);
+        g, pyr, (const uint32_t*)c->rowcnt.p, (const uint32_t*)c->rowent.p, (Elem*)c->work.p, (uint32_t*)c->selpos.p, (int*)c->fincnt.p, (int*)c->status.p);
     ++c->launches;
     stage_mark(c, 4);
+    if (g.total_blur > 0) {
+        k_blur<<<dim3((unsigned)g.total_blur, (unsigned)batch), BLUR_NT, 0, c->stream>>>(g, pyr, (uint8_t*)c->blur.p);
+        ++c->launches;
+    }
     k_describe<<<dim3((unsigned)((std::max(cap, 1) + DESC_KPB - 1) / DESC_KPB), (unsigned)batch), DESC_NT, 0, c->stream>>>(
-        g, pyr, (const Elem*)c->work.p, (const int*)c->fincnt.p, (const int8_t*)c->pattern.p, d_kps, d_desc, d_counts, cap);
+        g, pyr, (const uint8_t*)c->blur.p, (const Elem*)c->work.p, (const int*)c->fincnt.p, (const int8_t*)c->pattern.p, d_kps, d_desc, d_counts, cap);
     ++c->launches;
     stage_mark(c, 5);
     CU(cudaGetLastError());
@@ -355,8 +364,8 @@ int orbx_create(orbx_ctx** out, int device, int nfeatures, float scale_factor, i
     build_geom(c, max_w, max_h, &c->geom_max, nullptr);
     const Geom& g = c->geom_max;
     const size_t B = (size_t)max_batch;
-    if (ensure(c, c->pyr, g.pyr_frame * B) || ensure(c, c->rowcnt, g.cnt_frame * 4 * B) || ensure(c, c->rowent, g.ent_frame * 4 * B) ||
-        ensure(c, c->work, g.ws_frame * sizeof(Elem) * B) || ensure(c, c->fincnt, sizeof(int) * ORBX_LEVELS_MAX * B) ||
+    if (ensure(c, c->pyr, g.pyr_frame * B) || ensure(c, c->blur, g.pyr_frame * B) || ensure(c, c->rowcnt, g.cnt_frame * 4 * B) || ensure(c, c->rowent, g.ent_frame * 4 * B) ||
+        ensure(c, c->work, g.ws_frame * sizeof(Elem) * B) || ensure(c, c->selpos, g.ws_frame * 8 * B) || ensure(c, c->fincnt, sizeof(int) * ORBX_LEVELS_MAX * B) ||
         ensure(c, c->status, sizeof(int) * B) || ensure(c, c->pattern, sizeof k_pattern_host))
         return bail(ORBX_E_NOMEM);
     if (cudaMemcpy(c->pattern.p, k_pattern_host, sizeof k_pattern_host, cudaMemcpyHostToDevice) != cudaSuccess) return bail(ORBX_E_CUDA);
@@ -375,7 +384,7 @@ void orbx_destroy(orbx_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    Buf* bufs[] = {&c->pyr, &c->rowcnt, &c->rowent, &c->work, &c->fincnt, &c->status, &c->tabs, &c->pattern, &c->in, &c->kps,
+    Buf* bufs[] = {&c->pyr, &c->blur, &c->rowcnt, &c->rowent, &c->work, &c->selpos, &c->fincnt, &c->status, &c->tabs, &c->pattern, &c->in, &c->kps,
                    &c->desc, &c->counts, &c->mq, &c->mt, &c->mbest, &c->msecond, &c->mkeys, &c->mstatus, &c->mcounts};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     if (c->h_small) cudaFreeHost(c->h_small);

@@ -5,6 +5,7 @@
 // sits at a fixed offset, so one frame's working set stays together in L2 across the pipeline.
 //
 //   pyr     u8    [frame][level: h_l rows x pitch_l]            the unblurred pyramid (level 0 = gray)
+//   blur    u8    same layout as pyr                            7x7 Gaussian of each level (only where descriptors sample)
 //   rowcnt  u32   [frame][level: inner row r = y-31]            FAST+NMS survivors per inner row
 //   rowent  u32   [frame][level: inner row r][ent_pitch_l]      survivors of that row in x order: x | score<<16
 //   work    Elem  [frame][level: ws_cap_l]                      selection workspace; its prefix is the final list
@@ -31,6 +32,7 @@ struct LevelGeom {
     int ws_cap;               // workspace capacity (entries): ceil(in_w/2)*ceil(in_h/2)
     int band0;                // index of this level's first band in the per-frame band list
     int nbands;
+    int blur0, nblur, blur_cgs;  // blur tiles: first tile index, tile count (= column groups x strip groups), column groups
     uint32_t xtab, ytab;      // offsets (u32 units) of the INTER_LINEAR_EXACT tap tables: i0 | c1 << 16
     unsigned long long img_off;   // bytes, inside the frame's pyr block
     unsigned long long cnt_off;   // u32 units, inside the frame's rowcnt block
@@ -41,6 +43,7 @@ struct LevelGeom {
 struct Geom {
     int nlevels, w, h;
     int total_bands;          // per frame
+    int total_blur;           // blur tiles per frame
     int band_rows;            // rows per FAST band
     unsigned long long pyr_frame, cnt_frame, ent_frame, ws_frame;   // per-frame strides (bytes / u32 / u32 / Elem)
     LevelGeom L[ORBX_LEVELS_MAX];

@@ -8,7 +8,8 @@
 //   k_fast_bands    A.3   FAST-9/16 score + 3x3 NMS -> per-row lists    smem tiles with halos, u16x2 SIMD min/max,
 //                                                                       ballot compaction, raster order kept
 //   k_select        A.4-6 retainBest(2n) -> Harris -> retainBest(n)     libstdc++ introselect order reproduced
-//   k_describe      A.7-10 IC angle, 7x7 blur of the sampled patch, steered rBRIEF-256, cv::KeyPoint records
+//   k_blur          A.8   7x7 float-FMA Gaussian of the samplable region of every level (register sliding window)
+//   k_describe      A.7-10 IC angle, steered rBRIEF-256 sampled from the blurred level, cv::KeyPoint records (warp / keypoint)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -102,41 +103,48 @@ __global__ void __launch_bounds__(256) k_pyr_down(const __grid_constant__ Geom g
 }
 
 // ------------------------------------------------------------------------------------------------ A.3 FAST + NMS
-// One CTA = one band of R inner rows of one level of one frame, walked left to right in chunks of CW columns, so
-// every row's survivors come out in x order and the per-row lists concatenate to OpenCV's raster order.
+// One CTA = one band of R inner rows of one level of one frame, walked left to right in chunks of CWO = 252 output
+// columns, so every row's survivors come out in x order and the per-row lists concatenate to OpenCV's raster order.
 // Only the region that can survive the 31-px border filter is evaluated.
 //
-// Per chunk:  load (R+8) x (CW+16) pixels widened to u16 into smem
-//   phase A   every pixel pair: 4-compass-point rejection test in u16x2 SIMD (native VIMNMX.U16x2) -> pass queue
+// Per chunk (score tile = (R+2) rows x 256 columns, x = ox0-2 .. ox0+253):
+//   load      (R+8) x 272 pixels widened to u16 into smem (one warp per row, aligned 32-bit loads)
+//   phase A   every pixel pair: 4-compass-point rejection test in u16x2 SIMD (native VIMNMX.U16x2); the pass bits
+//             leave as warp ballots (one word per 32 pairs and parity); a block scan turns them into a queue
 //   phase B   queued pixels: full 16-point test.  Each circle pixel is packed (p | (255-p) << 16) so ONE sliding
 //             max over the 16 nine-long arcs (VIMNMX3.U16x2) yields both min-of-max(p) and max-of-min(p):
 //             A = v - min_arcs max p,  -B = max_arcs min p - v,  score = max(A, -B) - 1  (corner iff > t)
-//   phase C   3x3 NMS of the corners on the smem score tile -> per-row bit masks
+//   phase C   3x3 NMS (strict >) of the corners on the smem score tile -> per-row bit masks
 //   phase D   ordered extraction of the bit masks (popc prefix) -> global per-row lists
-template <int R, int CW, int NT>
+template <int R, int NT>
 __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr,
                                                    uint32_t* __restrict__ rowcnt, uint32_t* __restrict__ rowent)
 {
-    constexpr int TP = CW + 16;            // image tile pitch (pixels, u16 each)
+    constexpr int CWO = 252;               // output columns per chunk
+    constexpr int SP = 256;                // score tile pitch (bytes) = pixels evaluated per row
+    constexpr int SR = R + 2;              // score tile rows
+    constexpr int TP = SP + 16;            // image tile pitch (pixels, u16 each): x = ox0-8 .. ox0+263
     constexpr int TPW = TP / 2;            // ... in 32-bit words
     constexpr int TR = R + 8;              // image tile rows
-    constexpr int SP = CW + 4;             // score tile pitch (bytes)
-    constexpr int SR = R + 2;              // score tile rows
-    constexpr int MW = CW / 32;            // mask words per row
+    constexpr int MW = 8;                  // mask words per row (252 bits used)
+    constexpr int NPW = SR * 8;            // pass-bit words: [row][pair-column block of 32][parity]
     constexpr int T = ORBX_FAST_T;
-    static_assert(R * MW <= NT, "phase D needs one thread per mask word");
-    static_assert(CW % 32 == 0 && TP % 4 == 0, "tile shape");
+    constexpr int NWARP = NT / 32;
+    static_assert(NT == 256, "phase A maps 128 pair columns x 2 row groups onto 256 threads");
+    static_assert(R * MW <= NT && NPW <= NT, "one thread per mask / pass word");
 
     __shared__ __align__(16) uint16_t s_img[TR * TP];
-    __shared__ __align__(4) uint8_t s_score[SR * SP];
-    __shared__ uint16_t s_q[SR * SP];
+    __shared__ __align__(16) uint8_t s_score[SR * SP];
+    __shared__ uint16_t s_q[SR * SP];      // pass queue: sy << 8 | sx
+    __shared__ uint16_t s_cq[R * SP];      // corner queue (NMS candidates inside the output region; <= R x 252)
+    __shared__ uint32_t s_pass[NPW];
     __shared__ uint32_t s_mask[R * MW];
     __shared__ uint32_t s_rowcnt[R];
-    __shared__ int s_qn;
+    __shared__ int s_wsum[NWARP];
+    __shared__ int s_qn, s_cn;
 
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int f = blockIdx.y;
-    // which level / band
     int l = 0;
 #pragma unroll 1
     for (int i = 1; i < g.nlevels; ++i) if ((int)blockIdx.x >= g.L[i].band0) l = i;
@@ -145,6 +153,7 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
     if (band >= L.nbands) return;
     const int y0 = ORBX_EDGE + band * R;
     const int y1 = min(y0 + R, L.h - ORBX_EDGE);           // output rows [y0, y1)
+    const int nsr = y1 - y0 + 2;                            // score rows in use
     const int xend = L.w - ORBX_EDGE;                       // output cols [31, xend)
     const uint8_t* img = pyr + (size_t)f * g.pyr_frame + L.img_off;
     uint32_t* cnt_out = rowcnt + (size_t)f * g.cnt_frame + L.cnt_off;
@@ -153,63 +162,85 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
     if (tid < R) s_rowcnt[tid] = 0;
 
     const uint32_t* W = reinterpret_cast<const uint32_t*>(s_img);
-    for (int ox0 = 28; ox0 < xend; ox0 += CW) {
-        const int ox1 = min(ox0 + CW, xend);
+    for (int ox0 = 28; ox0 < xend; ox0 += CWO) {
+        const int ox1 = min(ox0 + CWO, xend);
         const int ix0 = ox0 - 8;
+        const int need = min(ox1 + 2 - (ox0 - 2), SP);      // pixels per score row that matter: x = ox0-2 .. ox1+1
         __syncthreads();                                     // previous chunk fully consumed
-        // ---- load tile rows [y0-4, y1+4), cols [ix0, ix0+TP) as u16
+        // ---- load tile rows [y0-4, y1+4), one warp per row, 4 pixels per lane and step
         {
             const int rows = y1 - y0 + 8;
-            constexpr int QPR = TP / 4;                      // 4-pixel groups per tile row
-            for (int i = tid; i < rows * QPR; i += NT) {
-                const int ty = i / QPR, q = i - ty * QPR;
-                const int gx = ix0 + q * 4;
-                uint32_t w = 0;
-                if (gx < L.pitch) w = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)(y0 - 4 + ty) * L.pitch + gx));
-                uint2 o;
-                o.x = __byte_perm(w, 0, 0x4140);
-                o.y = __byte_perm(w, 0, 0x4342);
-                *reinterpret_cast<uint2*>(&s_img[ty * TP + q * 4]) = o;
+            const int nq = min((need + 16 + 3) >> 2, TP / 4);
+            for (int ty = wid; ty < rows; ty += NWARP) {
+                const uint8_t* src = img + (size_t)(y0 - 4 + ty) * L.pitch + ix0;
+                for (int q = lane; q < nq; q += 32) {
+                    uint32_t w = 0;
+                    if (ix0 + q * 4 < L.pitch) w = __ldg(reinterpret_cast<const uint32_t*>(src) + q);
+                    uint2 o;
+                    o.x = __byte_perm(w, 0, 0x4140);
+                    o.y = __byte_perm(w, 0, 0x4342);
+                    *reinterpret_cast<uint2*>(&s_img[ty * TP + q * 4]) = o;
+                }
             }
-            for (int i = tid; i < SR * SP / 4; i += NT) reinterpret_cast<uint32_t*>(s_score)[i] = 0;
+            for (int i = tid; i < SR * SP / 16; i += NT) reinterpret_cast<uint4*>(s_score)[i] = make_uint4(0, 0, 0, 0);
             if (tid < R * MW) s_mask[tid] = 0;
-            if (tid == 0) s_qn = 0;
+            if (tid == 0) s_cn = 0;
         }
         __syncthreads();
-        // ---- phase A: compass rejection on pixel pairs
+        // ---- phase A: compass rejection; thread = pair column (tid & 127), rows tid >> 7, +2, ...
         {
-            constexpr int NP = SP / 2;
             constexpr unsigned K = ((511u - T) << 16) | (511u - T);
-            for (int i0 = 0; i0 < SR * NP; i0 += NT) {
-                const int i = i0 + tid;
-                const int sy = i / NP, sx = (i - sy * NP) * 2;
-                const int x = ox0 - 2 + sx, y = y0 - 1 + sy;
+            const int p = tid & 127, wc = (tid >> 5) & 3;
+            const bool warp_on = wc * 64 < need;            // warp-uniform: this 64-pixel block holds needed pixels
+            const bool col_on = 2 * p < need;
+            for (int sy = tid >> 7; sy < nsr; sy += 2) {
                 unsigned m = 0;
-                if (i < SR * NP && x <= ox1 && y <= y1) {
-                    const int b = (sy + 3) * TPW + (sx + 6) / 2;
-                    const unsigned c = W[b], n = W[b - 3 * TPW], s = W[b + 3 * TPW];
-                    const unsigned e = __byte_perm(W[b + 1], W[b + 2], 0x5432);
-                    const unsigned w = __byte_perm(W[b - 2], W[b - 1], 0x5432);
-                    const unsigned D = vmax2(vmin2(n, s), vmin2(e, w));
-                    const unsigned B = vmin2(vmax2(n, s), vmax2(e, w));
-                    m = ((c + K - D) | (B + K - c)) & 0x02000200u;
+                if (warp_on) {
+                    if (col_on) {
+                        const int b = (sy + 3) * TPW + p + 3;
+                        const unsigned c = W[b], n = W[b - 3 * TPW], s = W[b + 3 * TPW];
+                        const unsigned e = __byte_perm(W[b + 1], W[b + 2], 0x5432);
+                        const unsigned w = __byte_perm(W[b - 2], W[b - 1], 0x5432);
+                        const unsigned D = vmax2(vmin2(n, s), vmin2(e, w));
+                        const unsigned B = vmin2(vmax2(n, s), vmax2(e, w));
+                        m = ((c + K - D) | (B + K - c)) & 0x02000200u;
+                    }
+                    const unsigned blo = __ballot_sync(0xffffffffu, m & 0x200u);
+                    const unsigned bhi = __ballot_sync(0xffffffffu, m & 0x02000000u);
+                    if (lane == 0) { s_pass[(sy * 4 + wc) * 2] = blo; s_pass[(sy * 4 + wc) * 2 + 1] = bhi; }
+                } else if (lane == 0) {
+                    s_pass[(sy * 4 + wc) * 2] = 0; s_pass[(sy * 4 + wc) * 2 + 1] = 0;
                 }
-                const unsigned blo = __ballot_sync(0xffffffffu, m & 0x200u);
-                const unsigned bhi = __ballot_sync(0xffffffffu, m & 0x02000000u);
-                const int nlo = __popc(blo), tot = nlo + __popc(bhi);
-                int base = 0;
-                if (lane == 0 && tot) base = atomicAdd(&s_qn, tot);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (m & 0x200u) s_q[base + __popc(blo & lanemask_lt())] = (uint16_t)((sy << 9) | sx);
-                if (m & 0x02000000u) s_q[base + nlo + __popc(bhi & lanemask_lt())] = (uint16_t)((sy << 9) | (sx + 1));
+            }
+        }
+        __syncthreads();
+        // ---- pass bits -> queue (block scan of the popcounts, then every word owner expands its bits)
+        {
+            const int nw = nsr * 8;
+            unsigned bits = tid < nw ? s_pass[tid] : 0u;
+            const int cnt = __popc(bits);
+            int inc = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+            if (lane == 31) s_wsum[wid] = inc;
+            __syncthreads();
+            int off = inc - cnt, tot = 0;
+#pragma unroll
+            for (int i = 0; i < NWARP; ++i) { const int s = s_wsum[i]; if (i < wid) off += s; tot += s; }
+            if (tid == 0) s_qn = tot;
+            const int sy = tid >> 3, wc = (tid >> 1) & 3, par = tid & 1;
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                s_q[off++] = (uint16_t)((sy << 8) | ((wc * 32 + b) * 2 + par));
             }
         }
         __syncthreads();
         const int qn = s_qn;
-        // ---- phase B: full segment test + score on the queued pixels
+        // ---- phase B: full segment test + score on the queued pixels; corners inside the output region are queued for NMS
         for (int i = tid; i < qn; i += NT) {
             const int e = s_q[i];
-            const int sy = e >> 9, sx = e & 511;
+            const int sy = e >> 8, sx = e & 255;
             const uint16_t* c = &s_img[(sy + 3) * TP + sx + 6];
             const int v = c[0];
             unsigned q[16];
@@ -230,21 +261,23 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
             const int A = v - (int)(mm & 0xffffu);
             const int nB = 255 - (int)(mm >> 16) - v;
             const int sc = max(A, nB);
-            if (sc > T) s_score[sy * SP + sx] = (uint8_t)(sc - 1);
+            if (sc > T) {
+                s_score[sy * SP + sx] = (uint8_t)(sc - 1);
+                const int x = ox0 - 2 + sx;
+                if (x >= max(ox0, ORBX_EDGE) && x < ox1 && sy >= 1 && sy <= y1 - y0) s_cq[atomicAdd(&s_cn, 1)] = (uint16_t)e;
+            }
         }
         __syncthreads();
-        // ---- phase C: 3x3 NMS (strict >) of corners inside the output region
-        for (int i = tid; i < qn; i += NT) {
-            const int e = s_q[i];
-            const int sy = e >> 9, sx = e & 511;
+        // ---- phase C: 3x3 NMS of the queued corners
+        const int cn = s_cn;
+        for (int i = tid; i < cn; i += NT) {
+            const int e = s_cq[i];
+            const int sy = e >> 8, sx = e & 255;
             const uint8_t* p = &s_score[sy * SP + sx];
             const int s = p[0];
-            if (!s) continue;
-            const int x = ox0 - 2 + sx, y = y0 - 1 + sy;
-            if (x < max(ox0, ORBX_EDGE) || x >= ox1 || y < y0 || y >= y1) continue;
             if (s > p[-1] && s > p[1] && s > p[-SP - 1] && s > p[-SP] && s > p[-SP + 1] && s > p[SP - 1] && s > p[SP] && s > p[SP + 1]) {
-                const int bit = x - ox0;
-                atomicOr(&s_mask[(y - y0) * MW + (bit >> 5)], 1u << (bit & 31));
+                const int bit = sx - 2;
+                atomicOr(&s_mask[(sy - 1) * MW + (bit >> 5)], 1u << (bit & 31));
             }
         }
         __syncthreads();
@@ -266,9 +299,9 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
             while (m) {
                 const int b = __ffs(m) - 1;
                 m &= m - 1;
-                const int x = ox0 + wi * 32 + b;
-                const uint32_t sc = s_score[(row + 1) * SP + (x - ox0 + 2)];
-                dst[slot++] = (uint32_t)x | (sc << 16);
+                const int bit = wi * 32 + b;
+                const uint32_t sc = s_score[(row + 1) * SP + bit + 2];
+                dst[slot++] = (uint32_t)(ox0 + bit) | (sc << 16);
             }
             if (wi == MW - 1) s_rowcnt[row] = base + pre;
         }
@@ -277,11 +310,17 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
     if (tid < y1 - y0) cnt_out[y0 - ORBX_EDGE + tid] = s_rowcnt[tid];
 }
 
+
 // ------------------------------------------------------------------------------------------------ A.6 retainBest
-// Warp-cooperative, exact emulation of KeyPointsFilter::retainBest = libstdc++ std::nth_element (__introselect:
-// median-of-3 to first, Hoare __unguarded_partition, insertion sort of <= 3) + bidirectional std::partition.
-// The pointer scans are vectorised 32 wide with ballots; every swap is the sequential algorithm's swap, so the
-// resulting ORDER is libstdc++'s.  `v` may live in shared or global memory.
+// Exact emulation of KeyPointsFilter::retainBest = libstdc++ std::nth_element (__introselect: median-of-3 to
+// first, Hoare __unguarded_partition, insertion sort of <= 3) + bidirectional std::partition.  The resulting ORDER
+// is libstdc++'s, which OpenCV's output order (and, through index tie-breaks, the matcher) depends on.
+//   - ranges longer than SEL_PAR_MIN: one whole-CTA data-parallel Hoare pass (SURVEY A.6 / probe E21): with
+//     L = ascending positions of !(a > piv) and R = descending positions of !(piv > a) (original contents), the
+//     sequential loop swaps a[L[k]] <-> a[R[k]] for k < K, K = #{k : L[k] < R[k]}, and returns
+//     cut = min(L[K], R[K-1]).  Ranks come from a block scan, K from a block reduction, swaps run in parallel.
+//   - short ranges and the std::partition tail: warp-cooperative sequential emulation, scans vectorised with ballots.
+// `v` may live in shared or global memory.
 __device__ __forceinline__ void elem_swap(Elem* v, int a, int b) { const Elem t = v[a]; v[a] = v[b]; v[b] = t; }
 
 // first i in [start, end) with stopper(v[i]); `end` if none.  MODE 0: !(r > piv)   1: !(r >= piv)
@@ -311,54 +350,52 @@ __device__ __forceinline__ int scan_down(const Elem* v, int start, int stop, flo
     return stop;
 }
 
-// returns the new length; sets *flag |= 1 if the depth limit (heap-select fallback) would have been hit
-__device__ int retain_best_warp(Elem* v, int len, int m, int lane, int* flag)
+__device__ __forceinline__ int median3_pick(const Elem* v, int a, int b, int c)
 {
-    if (m < 0 || len <= m) return len;
-    if (m == 0) return 0;
-    // ---- std::nth_element(v, v + m - 1, v + len, response-greater)
-    {
-        const int nth = m - 1;
-        int first = 0, last = len;
-        int depth = 2 * (31 - __clz(len));
-        while (last - first > 3) {
-            if (depth == 0) { *flag |= 1; return m; }   // heap-select fallback: flagged, order not reproduced
-            --depth;
-            const int mid = first + (last - first) / 2;
-            const int a = first + 1, b = mid, c = last - 1;
-            const float ra = v[a].response, rb = v[b].response, rc = v[c].response;
-            int pick;
-            if (ra > rb) pick = (rb > rc) ? b : ((ra > rc) ? c : a);
-            else         pick = (ra > rc) ? a : ((rb > rc) ? c : b);
-            __syncwarp();
-            if (lane == 0) elem_swap(v, first, pick);
-            __syncwarp();
-            const float piv = v[first].response;
-            int f = first + 1, l = last;
-            for (;;) {
-                f = scan_up<0>(v, f, last, piv, lane);
-                --l;
-                l = scan_down<0>(v, l, first, piv, lane);
-                if (!(f < l)) break;
-                if (lane == 0) elem_swap(v, f, l);
-                __syncwarp();
-                ++f;
-            }
-            if (f <= nth) first = f; else last = f;
-        }
+    const float ra = v[a].response, rb = v[b].response, rc = v[c].response;
+    if (ra > rb) return (rb > rc) ? b : ((ra > rc) ? c : a);
+    return (ra > rc) ? a : ((rb > rc) ? c : b);
+}
+
+// warp-cooperative __introselect on [first, last) with the remaining depth budget; false = depth limit hit
+__device__ bool introselect_warp(Elem* v, int first, int last, int nth, int depth, int lane)
+{
+    while (last - first > 3) {
+        if (depth == 0) return false;
+        --depth;
+        const int pick = median3_pick(v, first + 1, first + (last - first) / 2, last - 1);
         __syncwarp();
-        if (lane == 0) {                                     // __insertion_sort, descending, <= 3 elements
-            for (int i = first + 1; i < last; ++i) {
-                const Elem val = v[i];
-                int j = i;
-                while (j > first && val.response > v[j - 1].response) { v[j] = v[j - 1]; --j; }
-                v[j] = val;
-            }
-        }
+        if (lane == 0) elem_swap(v, first, pick);
         __syncwarp();
+        const float piv = v[first].response;
+        int f = first + 1, l = last;
+        for (;;) {
+            f = scan_up<0>(v, f, last, piv, lane);
+            --l;
+            l = scan_down<0>(v, l, first, piv, lane);
+            if (!(f < l)) break;
+            if (lane == 0) elem_swap(v, f, l);
+            __syncwarp();
+            ++f;
+        }
+        if (f <= nth) first = f; else last = f;
     }
-    // ---- std::partition(v + m, v + len, response >= thr), bidirectional version
-    const float thr = v[m - 1].response;
+    __syncwarp();
+    if (lane == 0) {                                         // __insertion_sort, descending, <= 3 elements
+        for (int i = first + 1; i < last; ++i) {
+            const Elem val = v[i];
+            int j = i;
+            while (j > first && val.response > v[j - 1].response) { v[j] = v[j - 1]; --j; }
+            v[j] = val;
+        }
+    }
+    __syncwarp();
+    return true;
+}
+
+// warp-cooperative bidirectional std::partition(v + m, v + len, response >= thr); returns the partition point
+__device__ int partition_tail_warp(Elem* v, int m, int len, float thr, int lane)
+{
     int f = m, l = len;
     for (;;) {
         f = scan_up<1>(v, f, l, thr, lane);                  // first !pred in [f, l)
@@ -371,6 +408,94 @@ __device__ int retain_best_warp(Elem* v, int len, int m, int lane, int* flag)
         ++f;
     }
 }
+
+constexpr int SEL_NT = 128;
+constexpr int SEL_SMEM_ELEMS = 3072;
+constexpr int SEL_PAR_MIN = 96;        // ranges up to this length are finished by one warp
+
+struct SelShared {
+    int warp_a[SEL_NT / 32], warp_b[SEL_NT / 32];
+    int n, first, last, depth, ok;
+};
+
+// Whole-CTA KeyPointsFilter::retainBest(v, m).  All SEL_NT threads must call it.  PosT scratch lists Lp / Rp hold
+// `len` positions each.  Returns the new length (valid on every thread); *flag |= 1 on the heap-select fallback.
+template <typename PosT>
+__device__ int retain_best_block(Elem* v, int len, int m, PosT* Lp, PosT* Rp, SelShared* sh, int* flag)
+{
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (m < 0 || len <= m) return len;
+    if (m == 0) return 0;
+    const int nth = m - 1;
+    int first = 0, last = len, depth = 2 * (31 - __clz(len));
+    bool ok = true;
+    // ---- data-parallel Hoare passes while the range is long
+    while (last - first > SEL_PAR_MIN) {
+        if (depth == 0) { ok = false; break; }
+        --depth;
+        if (tid == 0) elem_swap(v, first, median3_pick(v, first + 1, first + (last - first) / 2, last - 1));
+        __syncthreads();
+        const float piv = v[first].response;
+        const int lo = first + 1, n = last - lo;
+        const int cs = (n + SEL_NT - 1) / SEL_NT;
+        const int b = min(lo + tid * cs, last), e = min(b + cs, last);
+        int cL = 0, cR = 0;
+        for (int i = b; i < e; ++i) { const float r = v[i].response; cL += !(r > piv); cR += !(piv > r); }
+        int iL = cL, iR = cR;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int oL = __shfl_up_sync(0xffffffffu, iL, d), oR = __shfl_up_sync(0xffffffffu, iR, d);
+            if (lane >= d) { iL += oL; iR += oR; }
+        }
+        if (lane == 31) { sh->warp_a[wid] = iL; sh->warp_b[wid] = iR; }
+        __syncthreads();
+        int totL = 0, totR = 0, exL = iL - cL, exR = iR - cR;
+#pragma unroll
+        for (int i = 0; i < SEL_NT / 32; ++i) {
+            const int a = sh->warp_a[i], c = sh->warp_b[i];
+            if (i < wid) { exL += a; exR += c; }
+            totL += a; totR += c;
+        }
+        {
+            int kL = exL, kR = totR - 1 - exR;               // L: ascending rank;  R: rank counted from the right end
+            for (int i = b; i < e; ++i) {
+                const float r = v[i].response;
+                if (!(r > piv)) Lp[kL++] = (PosT)i;
+                if (!(piv > r)) Rp[kR--] = (PosT)i;
+            }
+        }
+        __syncthreads();
+        const int mm = min(totL, totR);
+        int cnt = 0;
+        for (int k = tid; k < mm; k += SEL_NT) cnt += ((int)Lp[k] < (int)Rp[k]);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+        if (lane == 0) sh->warp_a[wid] = cnt;                // safe: all reads of warp_a finished before the last barrier
+        __syncthreads();
+        int K = 0;
+#pragma unroll
+        for (int i = 0; i < SEL_NT / 32; ++i) K += sh->warp_a[i];
+        for (int k = tid; k < K; k += SEL_NT) elem_swap(v, (int)Lp[k], (int)Rp[k]);
+        int cut = 0x7fffffff;
+        if (K < totL) cut = (int)Lp[K];
+        if (K > 0) cut = min(cut, (int)Rp[K - 1]);
+        __syncthreads();
+        if (cut <= nth) first = cut; else last = cut;
+    }
+    // ---- finish with one warp: short-range introselect + insertion sort, then the std::partition tail
+    if (wid == 0) {
+        int res = m;
+        if (ok) ok = introselect_warp(v, first, last, nth, depth, lane);
+        if (ok) res = partition_tail_warp(v, m, len, v[m - 1].response, lane);
+        if (lane == 0) { sh->n = res; sh->ok = ok ? 1 : 0; }
+    }
+    __syncthreads();
+    const int res = sh->n;
+    if (!sh->ok) *flag |= 1;
+    __syncthreads();
+    return res;
+}
+
 
 // ------------------------------------------------------------------------------------------------ A.5 Harris
 __device__ __forceinline__ float harris_response(const uint8_t* __restrict__ img, int pitch, int x, int y)
@@ -405,17 +530,16 @@ __device__ __forceinline__ float harris_response(const uint8_t* __restrict__ img
 // ------------------------------------------------------------------------------------------------ selection kernel
 // One CTA per (level, frame): gather the per-row FAST lists (raster order) -> retainBest(2 n_l) on the FAST score
 // -> Harris on the survivors -> retainBest(n_l) on Harris.  The final list is left as the prefix of the level's
-// global workspace; its length goes to fincnt.  The working array lives in shared memory when it fits.
-constexpr int SEL_NT = 128;
-constexpr int SEL_SMEM_ELEMS = 4096;
-
+// global workspace; its length goes to fincnt.  The working array (and the partition scratch) lives in shared
+// memory when the level's candidate count fits, else in global memory.
 __global__ void __launch_bounds__(SEL_NT) k_select(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr,
                                                    const uint32_t* __restrict__ rowcnt, const uint32_t* __restrict__ rowent,
-                                                   Elem* __restrict__ work, int* __restrict__ fincnt, int* __restrict__ status)
+                                                   Elem* __restrict__ work, uint32_t* __restrict__ selpos, int* __restrict__ fincnt,
+                                                   int* __restrict__ status)
 {
     __shared__ Elem s_v[SEL_SMEM_ELEMS];
-    __shared__ int s_warp[SEL_NT / 32];
-    __shared__ int s_n;
+    __shared__ uint16_t s_pos[2 * SEL_SMEM_ELEMS];
+    __shared__ SelShared sh;
     const int l = blockIdx.x, f = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const LevelGeom& L = g.L[l];
@@ -432,13 +556,14 @@ __global__ void __launch_bounds__(SEL_NT) k_select(const __grid_constant__ Geom 
     int inc = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
-    if (lane == 31) s_warp[wid] = inc;
+    if (lane == 31) sh.warp_a[wid] = inc;
     __syncthreads();
     int woff = 0, total = 0;
 #pragma unroll
-    for (int i = 0; i < SEL_NT / 32; ++i) { const int s = s_warp[i]; if (i < wid) woff += s; total += s; }
+    for (int i = 0; i < SEL_NT / 32; ++i) { const int s = sh.warp_a[i]; if (i < wid) woff += s; total += s; }
     const int N = total;
-    Elem* v = (N <= SEL_SMEM_ELEMS) ? s_v : gv;
+    const bool in_smem = N <= SEL_SMEM_ELEMS;
+    Elem* v = in_smem ? s_v : gv;
     {
         int o = woff + inc - mine;
         for (int r = rb; r < re; ++r) {
@@ -455,13 +580,10 @@ __global__ void __launch_bounds__(SEL_NT) k_select(const __grid_constant__ Geom 
     }
     __syncthreads();
     int flag = 0;
-    // ---- retainBest(2 n_l) on the FAST score (warp 0)
-    if (wid == 0) {
-        const int n1 = retain_best_warp(v, N, 2 * L.quota, lane, &flag);
-        if (lane == 0) s_n = n1;
-    }
-    __syncthreads();
-    const int n1 = s_n;
+    uint32_t* gpos = selpos + 2 * ((size_t)f * g.ws_frame + L.ws_off);
+    // ---- retainBest(2 n_l) on the FAST score
+    const int n1 = in_smem ? retain_best_block<uint16_t>(v, N, 2 * L.quota, s_pos, s_pos + SEL_SMEM_ELEMS, &sh, &flag)
+                           : retain_best_block<uint32_t>(v, N, 2 * L.quota, gpos, gpos + N, &sh, &flag);
     // ---- Harris on the unblurred level
     const uint8_t* img = pyr + (size_t)f * g.pyr_frame + L.img_off;
     for (int i = tid; i < n1; i += SEL_NT) {
@@ -469,15 +591,13 @@ __global__ void __launch_bounds__(SEL_NT) k_select(const __grid_constant__ Geom 
         v[i].response = harris_response(img, L.pitch, (int)(pos & 0xffffu), (int)(pos >> 16));
     }
     __syncthreads();
-    // ---- retainBest(n_l) on Harris (warp 0)
-    if (wid == 0) {
-        const int n2 = retain_best_warp(v, n1, L.quota, lane, &flag);
-        if (lane == 0) { s_n = n2; fincnt[f * g.nlevels + l] = n2; if (flag) atomicOr(&status[f], flag); }
-    }
-    __syncthreads();
-    const int n2 = s_n;
+    // ---- retainBest(n_l) on Harris
+    const int n2 = in_smem ? retain_best_block<uint16_t>(v, n1, L.quota, s_pos, s_pos + SEL_SMEM_ELEMS, &sh, &flag)
+                           : retain_best_block<uint32_t>(v, n1, L.quota, gpos, gpos + N, &sh, &flag);
+    if (tid == 0) { fincnt[f * g.nlevels + l] = n2; if (flag) atomicOr(&status[f], flag); }
     if (v != gv) for (int i = tid; i < n2; i += SEL_NT) gv[i] = v[i];
 }
+
 
 // ------------------------------------------------------------------------------------------------ A.7 / A.9 scalar math
 __device__ __forceinline__ float fast_atan2_deg(float y, float x)
@@ -540,136 +660,167 @@ __device__ __forceinline__ void glibc_sincosf(float ang, float* sn, float* cs)
     else       { *sn = sin_poly_d(x * s, x2); *cs = cos_poly_d(x2, tsg); }
 }
 
-// ------------------------------------------------------------------------------------------------ A.7-A.10 describe
-// One CTA = up to DESC_KPB keypoints of one frame.  Per keypoint: stage the 43x43 unblurred patch as f32 in smem;
-// IC moments over the radius-15 disc; fastAtan2; blur the 37x37 core with OpenCV's float sepFilter2D arithmetic
-// (row pass: general FMA chain, column pass: symmetric FMA chain, rint to u8); sample the 256 steered tests.
-constexpr int DESC_KPB = 4;
-constexpr int DESC_NT = 160;
-constexpr int PATCH = 43, PPITCH = 44, CORE = 37, CPITCH = 40;
+// ------------------------------------------------------------------------------------------------ A.8 blur
+// 7x7 sigma-2 Gaussian of every level in OpenCV's float sepFilter2D arithmetic:
+//   row pass   acc = F(k0*p[x-3]); acc = fma(p[x-3+i], k_i, acc), i = 1..6
+//   col pass   acc = F(k3*r[y]);   acc = fma(F(r[y+j] + r[y-j]), k_{3+j}, acc), j = 1..3;  out = rint(acc)
+// Only the region a descriptor can sample is produced: [13, w-13) x [13, h-13) (keypoints keep 31 px from the
+// border, rBRIEF reaches 18).  One thread = 4 adjacent columns walked down BLUR_RH rows with a 7-deep register
+// window of row-pass values, so every input byte is loaded once per thread and converted to float once
+// (exactly: PRMT into the mantissa of 2^23, one FADD).  No clamp is needed: the taps sum to < 1.
+constexpr int BLUR_RH = 32;            // output rows per thread
+constexpr int BLUR_NT = 128;           // 4 warps = 4 vertically stacked strips of a 128-column group
+constexpr int BLUR_LO = 12;            // first produced row / column is BLUR_LO rounded to the quad grid (x) / 13 (y)
+
+__device__ __forceinline__ float u8f(uint32_t w, uint32_t sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f; }
+
+__global__ void __launch_bounds__(BLUR_NT) k_blur(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur)
+{
+    const int f = blockIdx.y;
+    int l = 0;
+#pragma unroll 1
+    for (int i = 1; i < g.nlevels; ++i) if ((int)blockIdx.x >= g.L[i].blur0) l = i;
+    const LevelGeom& L = g.L[l];
+    const int tile = blockIdx.x - L.blur0;
+    if (tile >= L.nblur) return;
+    const int cg = tile % L.blur_cgs, sg = tile / L.blur_cgs;
+    const int x0 = BLUR_LO + (cg * 32 + (threadIdx.x & 31)) * 4;                 // first of this thread's 4 columns (multiple of 4)
+    const int ys = 13 + (sg * 4 + (threadIdx.x >> 5)) * BLUR_RH;                  // first output row of this warp's strip
+    const int ye = min(ys + BLUR_RH, L.h - 13);
+    if (x0 >= L.w - 13 || ys >= ye) return;
+    const float k0 = __int_as_float(0x3d8fafb1), k1 = __int_as_float(0x3e06387e), k2 = __int_as_float(0x3e434a39), k3 = __int_as_float(0x3e5d4ae0);
+    const uint8_t* src = pyr + (size_t)f * g.pyr_frame + L.img_off + (size_t)(ys - 3) * L.pitch + (x0 - 4);
+    uint8_t* dst = blur + (size_t)f * g.pyr_frame + L.img_off + (size_t)ys * L.pitch + x0;
+    float w[4][7];
+#pragma unroll 1
+    for (int r = 0; r < (ye - ys) + 6; ++r, src += L.pitch) {
+        const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(src));
+        const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(src) + 1);
+        const uint32_t c = (x0 + 4 < L.pitch) ? __ldg(reinterpret_cast<const uint32_t*>(src) + 2) : 0u;
+        float p[10];                                                              // pixels x0-3 .. x0+6
+        p[0] = u8f(a, 0x7651); p[1] = u8f(a, 0x7652); p[2] = u8f(a, 0x7653);
+        p[3] = u8f(b, 0x7650); p[4] = u8f(b, 0x7651); p[5] = u8f(b, 0x7652); p[6] = u8f(b, 0x7653);
+        p[7] = u8f(c, 0x7650); p[8] = u8f(c, 0x7651); p[9] = u8f(c, 0x7652);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float acc = __fmul_rn(k0, p[j]);
+            acc = __fmaf_rn(p[j + 1], k1, acc); acc = __fmaf_rn(p[j + 2], k2, acc); acc = __fmaf_rn(p[j + 3], k3, acc);
+            acc = __fmaf_rn(p[j + 4], k2, acc); acc = __fmaf_rn(p[j + 5], k1, acc); acc = __fmaf_rn(p[j + 6], k0, acc);
+#pragma unroll
+            for (int i = 0; i < 6; ++i) w[j][i] = w[j][i + 1];
+            w[j][6] = acc;
+        }
+        if (r >= 6) {
+            uint32_t out = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float o = __fmul_rn(k3, w[j][3]);
+                o = __fmaf_rn(__fadd_rn(w[j][4], w[j][2]), k2, o);
+                o = __fmaf_rn(__fadd_rn(w[j][5], w[j][1]), k1, o);
+                o = __fmaf_rn(__fadd_rn(w[j][6], w[j][0]), k0, o);
+                out |= (uint32_t)__float2int_rn(o) << (8 * j);
+            }
+            *reinterpret_cast<uint32_t*>(dst) = out;
+            dst += L.pitch;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ A.7 / A.9 / A.10 describe
+// One warp = one final keypoint (no block-level sync): IC moments over the radius-15 disc of the unblurred level
+// (lane = column, shuffle reduction), fastAtan2, glibc-exact sin/cos, then the 37x37 window of the blurred level is
+// staged in shared memory with aligned word loads and the 256 steered tests are sampled from it
+// (lane = descriptor byte).  Keypoint records and descriptors leave as coalesced stores.
+constexpr int DESC_KPB = 4;            // keypoints (warps) per CTA
+constexpr int DESC_NT = DESC_KPB * 32;
+constexpr int DWIN = 37, DWORDS = 12;  // staged window: 37 rows x 12 words (48 bytes >= 37 + 3 alignment slack)
 
 __constant__ int c_umax[16];
 
 __global__ void __launch_bounds__(DESC_NT) k_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr,
-                                                      const Elem* __restrict__ work, const int* __restrict__ fincnt,
-                                                      const int8_t* __restrict__ pattern, float* __restrict__ kps_out,
-                                                      uint8_t* __restrict__ desc_out, int* __restrict__ counts_out, int cap)
+                                                      const uint8_t* __restrict__ blur, const Elem* __restrict__ work,
+                                                      const int* __restrict__ fincnt, const int8_t* __restrict__ pattern,
+                                                      float* __restrict__ kps_out, uint8_t* __restrict__ desc_out,
+                                                      int* __restrict__ counts_out, int cap)
 {
-    __shared__ float s_patch[DESC_KPB][PATCH * PPITCH];
-    __shared__ uint8_t s_blur[DESC_KPB][CORE * CPITCH];
-    __shared__ int s_mom[DESC_KPB][2];
-    __shared__ int s_lvl[DESC_KPB], s_x[DESC_KPB], s_y[DESC_KPB];
-    __shared__ float s_resp[DESC_KPB], s_ang[DESC_KPB], s_cos[DESC_KPB], s_sin[DESC_KPB];
-
-    const int tid = threadIdx.x, f = blockIdx.y;
-    const int slot0 = blockIdx.x * DESC_KPB;
-    int total = 0;
-    for (int l = 0; l < g.nlevels; ++l) total += fincnt[f * g.nlevels + l];
-    if (blockIdx.x == 0 && tid == 0) counts_out[f] = total;
-    const int lim = min(total, cap);
-    if (slot0 >= lim) return;
-    const int nk = min(DESC_KPB, lim - slot0);
-
-    if (tid < nk) {
-        int s = slot0 + tid, l = 0;
-        for (; l < g.nlevels; ++l) { const int c = fincnt[f * g.nlevels + l]; if (s < c) break; s -= c; }
-        const Elem e = work[(size_t)f * g.ws_frame + g.L[l].ws_off + s];
-        s_lvl[tid] = l; s_x[tid] = (int)(e.pos & 0xffffu); s_y[tid] = (int)(e.pos >> 16); s_resp[tid] = e.response;
-        s_mom[tid][0] = 0; s_mom[tid][1] = 0;
+    __shared__ uint32_t s_win[DESC_KPB][DWIN * DWORDS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, f = blockIdx.y;
+    const int slot = blockIdx.x * DESC_KPB + wid;
+    int total = 0, lvl = -1, idx = 0;
+    {
+        int s = slot;
+        for (int l = 0; l < g.nlevels; ++l) {
+            const int c = __ldg(fincnt + f * g.nlevels + l);
+            total += c;
+            if (lvl < 0) { if (s < c) { lvl = l; idx = s; } else s -= c; }
+        }
     }
-    __syncthreads();
-    // ---- stage patches (u8 -> f32, exact)
-    for (int i = tid; i < nk * PATCH * PATCH; i += DESC_NT) {
-        const int j = i / (PATCH * PATCH), r = (i - j * PATCH * PATCH) / PATCH, c = i - j * PATCH * PATCH - r * PATCH;
-        const LevelGeom& L = g.L[s_lvl[j]];
-        const uint8_t* img = pyr + (size_t)f * g.pyr_frame + L.img_off;
-        s_patch[j][r * PPITCH + c] = (float)__ldg(img + (size_t)(s_y[j] - 21 + r) * L.pitch + (s_x[j] - 21 + c));
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts_out[f] = total;
+    if (slot >= min(total, cap) || lvl < 0) return;          // warp-uniform
+    const LevelGeom& L = g.L[lvl];
+    const Elem e = work[(size_t)f * g.ws_frame + L.ws_off + idx];
+    const int x = (int)(e.pos & 0xffffu), y = (int)(e.pos >> 16);
+    const uint8_t* img = pyr + (size_t)f * g.pyr_frame + L.img_off;
+    const uint8_t* bimg = blur + (size_t)f * g.pyr_frame + L.img_off;
+
+    // ---- stage the blurred window rows y-18 .. y+18, bytes (x-18) .. (x+18), as aligned words
+    const int xa = (x - 18) & ~3, sh = (x - 18) & 3;
+    uint32_t* win = s_win[wid];
+    for (int i = lane; i < DWIN * DWORDS; i += 32) {
+        const int r = i / DWORDS, c = i - r * DWORDS;
+        uint32_t v = 0;
+        if (xa + c * 4 < L.pitch) v = __ldg(reinterpret_cast<const uint32_t*>(bimg + (size_t)(y - 18 + r) * L.pitch + xa) + c);
+        win[i] = v;
     }
-    __syncthreads();
-    // ---- IC moments: thread (j, u) walks its column of the disc
-    if (tid < nk * 31) {
-        const int j = tid / 31, u = tid - j * 31 - 15;
-        const int au = u < 0 ? -u : u;
-        int m10 = 0, m01 = 0;
+    // ---- IC moments on the unblurred level: lane <-> column u = lane - 15
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+        const int u = lane - 15, au = u < 0 ? -u : u;
+        const uint8_t* p = img + (size_t)(y - 15) * L.pitch + (x + u);
 #pragma unroll 1
-        for (int vv = -15; vv <= 15; ++vv) {
+        for (int vv = -15; vv <= 15; ++vv, p += L.pitch) {
             const int av = vv < 0 ? -vv : vv;
-            if (au <= c_umax[av]) {
-                const int I = (int)s_patch[j][(21 + vv) * PPITCH + 21 + u];
-                m10 += u * I; m01 += vv * I;
-            }
-        }
-        atomicAdd(&s_mom[j][0], m10);
-        atomicAdd(&s_mom[j][1], m01);
-    }
-    __syncthreads();
-    if (tid < nk) {
-        const float ang = fast_atan2_deg((float)s_mom[tid][1], (float)s_mom[tid][0]);
-        s_ang[tid] = ang;
-        float sn, cs;
-        glibc_sincosf(__fmul_rn(ang, __int_as_float(0x3c8efa35)), &sn, &cs);
-        s_cos[tid] = cs; s_sin[tid] = sn;
-    }
-    // ---- blur: thread (j, c) produces column c of the 37x37 core with a 7-deep register window of row-pass values
-    if (tid < nk * CORE) {
-        const int j = tid / CORE, c = tid - j * CORE;
-        const float k0 = __int_as_float(0x3d8fafb1), k1 = __int_as_float(0x3e06387e), k2 = __int_as_float(0x3e434a39), k3 = __int_as_float(0x3e5d4ae0);
-        const float* P = &s_patch[j][c];
-        float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f, w4 = 0.f, w5 = 0.f, w6;
-#pragma unroll 1
-        for (int r = 0; r < PATCH; ++r) {
-            const float* p = P + r * PPITCH;
-            float acc = __fmul_rn(k0, p[0]);
-            acc = __fmaf_rn(p[1], k1, acc); acc = __fmaf_rn(p[2], k2, acc); acc = __fmaf_rn(p[3], k3, acc);
-            acc = __fmaf_rn(p[4], k2, acc); acc = __fmaf_rn(p[5], k1, acc); acc = __fmaf_rn(p[6], k0, acc);
-            w6 = acc;
-            if (r >= 6) {
-                float o = __fmul_rn(k3, w3);
-                o = __fmaf_rn(__fadd_rn(w4, w2), k2, o);
-                o = __fmaf_rn(__fadd_rn(w5, w1), k1, o);
-                o = __fmaf_rn(__fadd_rn(w6, w0), k0, o);
-                int q = __float2int_rn(o);
-                q = max(0, min(255, q));
-                s_blur[j][(r - 6) * CPITCH + c] = (uint8_t)q;
-            }
-            w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; w5 = w6;
+            if (au <= c_umax[av]) { const int I = __ldg(p); m10 += u * I; m01 += vv * I; }
         }
     }
-    __syncthreads();
-    // ---- steered rBRIEF: thread (j, byte)
-    if (tid < nk * 32) {
-        const int j = tid >> 5, bi = tid & 31;
-        const float a = s_cos[j], b = s_sin[j];
-        const uint8_t* B = &s_blur[j][18 * CPITCH + 18];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, d); m01 += __shfl_xor_sync(0xffffffffu, m01, d); }
+    const float ang = fast_atan2_deg((float)m01, (float)m10);
+    float sn, cs;
+    glibc_sincosf(__fmul_rn(ang, __int_as_float(0x3c8efa35)), &sn, &cs);
+    __syncwarp();
+    // ---- steered rBRIEF: lane <-> descriptor byte
+    {
+        const uint8_t* B = reinterpret_cast<const uint8_t*>(win) + 18 * (DWORDS * 4) + 18 + sh;
         unsigned byte = 0;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-            const char4 pt = *reinterpret_cast<const char4*>(pattern + (bi * 8 + t) * 4);
+            const char4 pt = *reinterpret_cast<const char4*>(pattern + (lane * 8 + t) * 4);
             const float x0 = (float)pt.x, y0 = (float)pt.y, x1 = (float)pt.z, y1 = (float)pt.w;
-            const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-            const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-            const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-            const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-            const int t0 = B[iy0 * CPITCH + ix0], t1 = B[iy1 * CPITCH + ix1];
+            const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, cs), __fmul_rn(y0, sn)));
+            const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sn), __fmul_rn(y0, cs)));
+            const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, cs), __fmul_rn(y1, sn)));
+            const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sn), __fmul_rn(y1, cs)));
+            const int t0 = B[iy0 * (DWORDS * 4) + ix0], t1 = B[iy1 * (DWORDS * 4) + ix1];
             byte |= (unsigned)(t0 < t1) << t;
         }
-        const size_t slot = (size_t)f * cap + slot0 + j;
-        desc_out[slot * 32 + bi] = (uint8_t)byte;
-        if (bi < 7) {
-            const LevelGeom& L = g.L[s_lvl[j]];
+        const size_t o = (size_t)f * cap + slot;
+        desc_out[o * 32 + lane] = (uint8_t)byte;
+        if (lane < 7) {
             float val;
-            switch (bi) {
-                case 0: val = __fmul_rn((float)s_x[j], L.scale); break;
-                case 1: val = __fmul_rn((float)s_y[j], L.scale); break;
+            switch (lane) {
+                case 0: val = __fmul_rn((float)x, L.scale); break;
+                case 1: val = __fmul_rn((float)y, L.scale); break;
                 case 2: val = __fmul_rn(31.0f, L.scale); break;
-                case 3: val = s_ang[j]; break;
-                case 4: val = s_resp[j]; break;
-                case 5: val = __int_as_float(s_lvl[j]); break;
+                case 3: val = ang; break;
+                case 4: val = e.response; break;
+                case 5: val = __int_as_float(lvl); break;
                 default: val = __int_as_float(-1); break;
             }
-            kps_out[slot * 7 + bi] = val;
+            kps_out[o * 7 + lane] = val;
         }
     }
 }
+
 
 }  // namespace orbx
