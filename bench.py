@@ -51,7 +51,7 @@ def make_frames(batch: int, seed: int) -> np.ndarray:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms; only samples inside the timed region are reported."""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -69,9 +69,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.p.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.perf_counter()] + [c.strip() for c in line.split(",")])
 
-    def stop(self) -> dict:
+    def stop(self, t0: float = 0.0, t1: float = float("inf")) -> dict:
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -79,11 +79,14 @@ class ClockSampler:
             self.p.wait(timeout=5)
         except Exception:
             self.p.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        allrows = [r[1:] for r in self.rows if len(r) >= 7]
+        rows = [r[1:] for r in self.rows if len(r) >= 7 and t0 <= r[0] <= t1 + 0.15] or allrows[-1:]   # samples inside the timed region
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in allrows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm), "period_ms": 100}
 
 
 def cpu_reference_fps(frames: np.ndarray, map_desc: np.ndarray, threads: int, repeats: int = 1):
@@ -195,12 +198,13 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None   # started early; only samples inside the timed region count
     for _ in range(max(args.warmup, 3)):
         step()
     ctx.synchronize()
     barrier()
     launches0 = ctx.launch_count
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_wall0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(args.steps):
@@ -209,7 +213,7 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count - launches0
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_wall0, time.perf_counter()) if sampler else None
     ctx.synchronize()                                    # raises on any deferred device status
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -271,7 +275,7 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     n_out = float(counts.mean())
     b_alg = 3 * W * H + 2 * LEVEL_PIXELS_VGA + 60 * n_out
-    ext_stages = {k: v for k, v in stage_ms.items() if k != "match"}
+    ext_stages = {k: v for k, v in stage_ms.items() if k != "match"}   # gray, pyramid, fast_nms, select_harris, blur, describe
     dom = max(ext_stages, key=ext_stages.get) if ext_stages else None
     ext_total = sum(ext_stages.values())
     roofline = None

@@ -26,11 +26,10 @@ namespace {
 const int8_t k_pattern_host[256 * 4] = {
 #include "brief_pattern.inc"
 };
-const int k_umax_host[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 
 constexpr int FAST_R = 16, FAST_NT = 256;
-constexpr int N_STAGES = 6;
-const char* const k_stage_names[N_STAGES] = {"gray", "pyramid", "fast_nms", "select_harris", "blur_describe", "match"};
+constexpr int N_STAGES = 7;
+const char* const k_stage_names[N_STAGES] = {"gray", "pyramid", "fast_nms", "select_harris", "blur", "describe", "match"};
 
 size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -61,7 +60,9 @@ struct orbx_ctx {
     int last_batch = 0;
 
     bool profiling = false;
-    cudaEvent_t ev[N_STAGES + 2] = {};   // 0..5 bracket the extraction stages, 6..7 the matcher
+    cudaEvent_t ev[N_STAGES + 2] = {};   // 0..6 bracket the six extraction stages, 7..8 the matcher
+    cudaStream_t stream2 = nullptr;      // blur runs here, concurrently with FAST + selection (unless profiling)
+    cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
     float stage_ms[N_STAGES] = {};
     bool stage_valid[N_STAGES] = {};
 };
@@ -159,9 +160,9 @@ void build_geom(const orbx_ctx* c, int w, int h, Geom* g, std::vector<uint32_t>*
         L.ent_pitch = (int)round_up((size_t)(L.in_w + 1) / 2 + 1, 8);
         L.ws_cap = std::max(((L.in_w + 1) / 2) * ((L.in_h + 1) / 2), 1);
         L.band0 = bands; L.nbands = (L.in_h + FAST_R - 1) / FAST_R; bands += L.nbands;
-        if (L.in_w > 0) {                                    // blur tiles: 128-column groups x (4 strips of BLUR_RH rows)
-            L.blur_cgs = (L.w - 13 - BLUR_LO + 127) / 128;
-            L.nblur = L.blur_cgs * ((L.h - 26 + 4 * BLUR_RH - 1) / (4 * BLUR_RH));
+        if (L.in_w > 0) {                                    // blur work items: 8-column groups x strips of BLUR_RH rows, BLUR_NT per CTA
+            L.blur_cgs = (L.w - 13 - BLUR_LO + 7) / 8;
+            L.nblur = (L.blur_cgs * ((L.h - 26 + BLUR_RH - 1) / BLUR_RH) + BLUR_NT - 1) / BLUR_NT;
         }
         L.blur0 = blurs; blurs += L.nblur;
         L.img_off = pyr; pyr += round_up((size_t)L.pitch * std::max(L.h, 1), 256);
@@ -224,10 +225,17 @@ int run_extract(orbx_ctx* c, const uint8_t* d_imgs, int batch, int w, int h, siz
     stage_mark(c, 1);
     for (int l = 1; l < g.nlevels; ++l) {
         if (g.L[l].w <= 0 || g.L[l].h <= 0) continue;
-        const dim3 blk(64, 4);
-        const dim3 grd((unsigned)((g.L[l].pitch / 4 + 63) / 64), (unsigned)((g.L[l].h + 3) / 4), (unsigned)batch);
+        const dim3 blk(128);
+        const dim3 grd((unsigned)((g.L[l].pitch / 4 + 127) / 128), (unsigned)((g.L[l].h + PYR_RH - 1) / PYR_RH), (unsigned)batch);
         k_pyr_down<<<grd, blk, 0, c->stream>>>(g, l, pyr, (const uint32_t*)c->tabs.p);
         ++c->launches;
+    }
+    if (!c->profiling && g.total_blur > 0) {                 // blur only needs the pyramid: overlap it with FAST + selection
+        CU(cudaEventRecord(c->ev_pyr, c->stream));
+        CU(cudaStreamWaitEvent(c->stream2, c->ev_pyr, 0));
+        k_blur<<<dim3((unsigned)g.total_blur, (unsigned)batch), BLUR_NT, 0, c->stream2>>>(g, pyr, (uint8_t*)c->blur.p);
+        ++c->launches;
+        CU(cudaEventRecord(c->ev_blur, c->stream2));
     }
     stage_mark(c, 2);
     if (g.total_bands > 0) {
@@ -240,17 +248,19 @@ int run_extract(orbx_ctx* c, const uint8_t* d_imgs, int batch, int w, int h, siz
         g, pyr, (const uint32_t*)c->rowcnt.p, (const uint32_t*)c->rowent.p, (Elem*)c->work.p, (uint32_t*)c->selpos.p, (int*)c->fincnt.p, (int*)c->status.p);
     ++c->launches;
     stage_mark(c, 4);
-    if (g.total_blur > 0) {
+    if (c->profiling && g.total_blur > 0) {                  // serialised so that the stage events mean something
         k_blur<<<dim3((unsigned)g.total_blur, (unsigned)batch), BLUR_NT, 0, c->stream>>>(g, pyr, (uint8_t*)c->blur.p);
         ++c->launches;
     }
-    k_describe<<<dim3((unsigned)((std::max(cap, 1) + DESC_KPB - 1) / DESC_KPB), (unsigned)batch), DESC_NT, 0, c->stream>>>(
-        g, pyr, (const uint8_t*)c->blur.p, (const Elem*)c->work.p, (const int*)c->fincnt.p, (const int8_t*)c->pattern.p, d_kps, d_desc, d_counts, cap);
-    ++c->launches;
     stage_mark(c, 5);
+    if (!c->profiling && g.total_blur > 0) CU(cudaStreamWaitEvent(c->stream, c->ev_blur, 0));
+    k_describe<<<dim3((unsigned)((std::max(cap, 1) + DESC_KPB - 1) / DESC_KPB), (unsigned)batch), DESC_NT, 0, c->stream>>>(
+        g, pyr, (const uint8_t*)c->blur.p, (const Elem*)c->work.p, (const int*)c->fincnt.p, (const float4*)c->pattern.p, d_kps, d_desc, d_counts, cap);
+    ++c->launches;
+    stage_mark(c, 6);
     CU(cudaGetLastError());
     c->last_batch = batch;
-    if (c->profiling) for (int i = 0; i < 5; ++i) c->stage_valid[i] = true;
+    if (c->profiling) for (int i = 0; i < 6; ++i) c->stage_valid[i] = true;
     return ORBX_OK;
 }
 
@@ -284,7 +294,7 @@ int run_match(orbx_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int n
     int rc;
     if ((rc = ensure(c, c->mstatus, sizeof(int)))) return rc;
     CU(cudaMemsetAsync(c->mstatus.p, 0, sizeof(int), c->stream));
-    stage_mark(c, 6);
+    stage_mark(c, 7);
     if (nsplit > 1) {
         if ((rc = ensure(c, c->mkeys, nout * sizeof(int)))) return rc;
         keys = (int*)c->mkeys.p;
@@ -299,8 +309,8 @@ int run_match(orbx_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int n
         k_match_finalize<<<(unsigned)((nout + 255) / 256), 256, 0, c->stream>>>(keys, nq, nout, d_best);
         ++c->launches;
     }
-    stage_mark(c, 7);
-    if (c->profiling) c->stage_valid[5] = true;
+    stage_mark(c, 8);
+    if (c->profiling) c->stage_valid[6] = true;
     CU(cudaGetLastError());
     return ORBX_OK;
 }
@@ -360,16 +370,21 @@ int orbx_create(orbx_ctx** out, int device, int nfeatures, float scale_factor, i
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(ORBX_E_CUDA);
     if (prop.major != 10) return bail(ORBX_E_CUDA);          // sm_100a only: no other code path exists
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(ORBX_E_CUDA);
+    if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) return bail(ORBX_E_CUDA);
+    if (cudaEventCreateWithFlags(&c->ev_pyr, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_blur, cudaEventDisableTiming) != cudaSuccess) return bail(ORBX_E_CUDA);
     for (int i = 0; i < N_STAGES + 2; ++i) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail(ORBX_E_CUDA);
     build_geom(c, max_w, max_h, &c->geom_max, nullptr);
     const Geom& g = c->geom_max;
     const size_t B = (size_t)max_batch;
     if (ensure(c, c->pyr, g.pyr_frame * B) || ensure(c, c->blur, g.pyr_frame * B) || ensure(c, c->rowcnt, g.cnt_frame * 4 * B) || ensure(c, c->rowent, g.ent_frame * 4 * B) ||
         ensure(c, c->work, g.ws_frame * sizeof(Elem) * B) || ensure(c, c->selpos, g.ws_frame * 8 * B) || ensure(c, c->fincnt, sizeof(int) * ORBX_LEVELS_MAX * B) ||
-        ensure(c, c->status, sizeof(int) * B) || ensure(c, c->pattern, sizeof k_pattern_host))
+        ensure(c, c->status, sizeof(int) * B) || ensure(c, c->pattern, sizeof(float) * 1024))
         return bail(ORBX_E_NOMEM);
-    if (cudaMemcpy(c->pattern.p, k_pattern_host, sizeof k_pattern_host, cudaMemcpyHostToDevice) != cudaSuccess) return bail(ORBX_E_CUDA);
-    if (cudaMemcpyToSymbol(c_umax, k_umax_host, sizeof k_umax_host) != cudaSuccess) return bail(ORBX_E_CUDA);
+    {
+        float pat[1024];                                     // the rBRIEF pattern as float4 (x0, y0, x1, y1) per test
+        for (int i = 0; i < 1024; ++i) pat[i] = (float)k_pattern_host[i];
+        if (cudaMemcpy(c->pattern.p, pat, sizeof pat, cudaMemcpyHostToDevice) != cudaSuccess) return bail(ORBX_E_CUDA);
+    }
     if (cudaMemset(c->status.p, 0, sizeof(int) * B) != cudaSuccess) return bail(ORBX_E_CUDA);
     if (cudaMallocHost((void**)&c->h_small, sizeof(int) * (2 * B + 4)) != cudaSuccess) return bail(ORBX_E_NOMEM);
     if (cudaFuncSetAttribute(k_hamming_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES) != cudaSuccess ||
@@ -384,11 +399,15 @@ void orbx_destroy(orbx_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
     Buf* bufs[] = {&c->pyr, &c->blur, &c->rowcnt, &c->rowent, &c->work, &c->selpos, &c->fincnt, &c->status, &c->tabs, &c->pattern, &c->in, &c->kps,
                    &c->desc, &c->counts, &c->mq, &c->mt, &c->mbest, &c->msecond, &c->mkeys, &c->mstatus, &c->mcounts};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     if (c->h_small) cudaFreeHost(c->h_small);
     for (int i = 0; i < N_STAGES + 2; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->ev_pyr) cudaEventDestroy(c->ev_pyr);
+    if (c->ev_blur) cudaEventDestroy(c->ev_blur);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -617,7 +636,7 @@ int orbx_debug_stage_times(orbx_ctx* c, const char** names, float* ms, int cap)
     for (int i = 0; i < N_STAGES && n < cap; ++i) {
         if (!c->stage_valid[i]) continue;
         float t = 0.f;
-        const int e0 = i < 5 ? i : 6;
+        const int e0 = i < 6 ? i : 7;
         if (cudaEventElapsedTime(&t, c->ev[e0], c->ev[e0 + 1]) != cudaSuccess) continue;
         if (names) names[n] = k_stage_names[i];
         if (ms) ms[n] = t;

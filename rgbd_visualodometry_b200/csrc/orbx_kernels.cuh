@@ -4,7 +4,7 @@
 // round-to-nearest intrinsics (never contracted) and __fmaf_rn only where OpenCV's own build uses FMA (A.8).
 //
 //   k_gray          A.1   BGR -> gray (level 0)                         HBM-bound, 4 px / thread
-//   k_pyr_down      A.2   INTER_LINEAR_EXACT level l from level l-1     HBM/L2-bound, 4 px / thread
+//   k_pyr_down      A.2   INTER_LINEAR_EXACT level l from level l-1     thread = output column, horizontal pass reused
 //   k_fast_bands    A.3   FAST-9/16 score + 3x3 NMS -> per-row lists    smem tiles with halos, u16x2 SIMD min/max,
 //                                                                       ballot compaction, raster order kept
 //   k_select        A.4-6 retainBest(2n) -> Harris -> retainBest(n)     libstdc++ introselect order reproduced
@@ -68,49 +68,89 @@ __global__ void __launch_bounds__(256) k_gray(const uint8_t* __restrict__ in, un
 
 // ------------------------------------------------------------------------------------------------ A.2 pyramid
 // dst(x,y) = (h0*(256-cy) + h1*cy + 32768) >> 16,  h = p[i0]*(256-cx) + p[i1]*cx  (8.8 taps from host tables).
-__global__ void __launch_bounds__(256) k_pyr_down(const __grid_constant__ Geom g, int l, uint8_t* __restrict__ pyr,
+// One thread owns 4 adjacent output columns (taps, byte offsets and funnel-shift amounts stay in registers) and
+// walks PYR_RH output rows.  A source row costs three aligned 32-bit loads (the 4 outputs read <= 9 consecutive
+// source bytes); each output's horizontal pass is one funnel shift + one IDP.2A (u16 taps x u8 pixels), and it is
+// reused by the next output row when that row needs the same source row (the common case at ratio 1.2).
+// Load/store instructions per pixel drop ~6x against byte gathers -- the LSU issue rate was the bound.
+constexpr int PYR_RH = 32;
+struct PyrRow { uint32_t h[4]; };
+__device__ __forceinline__ PyrRow pyr_hpass(const uint8_t* __restrict__ row, bool w2ok, const uint32_t* coef, const uint32_t* sh, const bool* hi)
+{
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(row);
+    const uint32_t w0 = p[0], w1 = p[1], w2 = w2ok ? p[2] : 0u;
+    PyrRow r;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t v = __funnelshift_r(hi[k] ? w1 : w0, hi[k] ? w2 : w1, sh[k]);     // bytes: p[i0], p[i0 + 1], ...
+        r.h[k] = __dp2a_lo(coef[k], v, 0u);                                               // p[i0]*c0 + p[i0+1]*c1, exact 8.8
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(128) k_pyr_down(const __grid_constant__ Geom g, int l, uint8_t* __restrict__ pyr,
                                                   const uint32_t* __restrict__ tabs)
 {
     const LevelGeom& D = g.L[l];
     const LevelGeom& S = g.L[l - 1];
-    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = (blockIdx.x * 128 + threadIdx.x) * 4;
     const int f = blockIdx.z;
-    if (y >= D.h || x >= D.pitch) return;
-    const uint8_t* src = pyr + (size_t)f * g.pyr_frame + S.img_off;
-    const uint32_t ty = __ldg(tabs + D.ytab + y);
-    const int y0 = ty & 0xffff;
-    const uint32_t cy1 = ty >> 16, cy0 = 256u - cy1;
-    const int y1 = min(y0 + 1, S.h - 1);
-    const uint8_t* r0 = src + (size_t)y0 * S.pitch;
-    const uint8_t* r1 = src + (size_t)y1 * S.pitch;
-    uint32_t out = 0;
+    if (x >= D.pitch) return;
+    const int ys = blockIdx.y * PYR_RH, ye = min(ys + PYR_RH, D.h);
+    uint8_t* dst = pyr + (size_t)f * g.pyr_frame + D.img_off + (size_t)ys * D.pitch + x;
+    if (x >= D.w) {                                          // row padding: keep it zero
+        for (int y = ys; y < ye; ++y, dst += D.pitch) *reinterpret_cast<uint32_t*>(dst) = 0u;
+        return;
+    }
+    uint32_t coef[4], sh[4];
+    bool hi[4];
+    const uint32_t t0 = __ldg(tabs + D.xtab + x);
+    const int a = (int)(t0 & 0xffffu) & ~3;                  // aligned source byte all four outputs are addressed from
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        if (x + k < D.w) {
-            const uint32_t tx = __ldg(tabs + D.xtab + x + k);
-            const int i0 = tx & 0xffff;
-            const uint32_t cx1 = tx >> 16, cx0 = 256u - cx1;
-            const int i1 = min(i0 + 1, S.w - 1);
-            const uint32_t h0 = r0[i0] * cx0 + r0[i1] * cx1;
-            const uint32_t h1 = r1[i0] * cx0 + r1[i1] * cx1;
-            uint32_t v = (h0 * cy0 + h1 * cy1 + 32768u) >> 16;
-            v = min(v, 255u);
-            out |= v << (8 * k);
-        }
+        uint32_t t = (x + k < D.w) ? __ldg(tabs + D.xtab + x + k) : (uint32_t)a;       // padding columns: taps 0 -> output 0
+        const int off = (int)(t & 0xffffu) - a;              // 0 .. 7
+        const uint32_t c1 = t >> 16;
+        coef[k] = (x + k < D.w) ? ((256u - c1) | (c1 << 16)) : 0u;
+        hi[k] = off >= 4;
+        sh[k] = (uint32_t)(off & 3) * 8u;
     }
-    *reinterpret_cast<uint32_t*>(pyr + (size_t)f * g.pyr_frame + D.img_off + (size_t)y * D.pitch + x) = out;
+    const bool w2ok = a + 8 < S.pitch;
+    const uint8_t* src = pyr + (size_t)f * g.pyr_frame + S.img_off + a;
+    const uint32_t* ytab = tabs + D.ytab;
+    int have = -1;                                           // source row whose horizontal pass is in hb
+    PyrRow ha, hb;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { ha.h[k] = 0; hb.h[k] = 0; }
+#pragma unroll 2
+    for (int y = ys; y < ye; ++y, dst += D.pitch) {
+        const uint32_t ty = __ldg(ytab + y);                 // uniform across the block
+        const int y0 = ty & 0xffff, y1 = min(y0 + 1, S.h - 1);
+        const uint32_t cy1 = ty >> 16, cy0 = 256u - cy1;
+        if (y0 == have) ha = hb;
+        else ha = pyr_hpass(src + (size_t)y0 * S.pitch, w2ok, coef, sh, hi);
+        if (y1 != y0) hb = pyr_hpass(src + (size_t)y1 * S.pitch, w2ok, coef, sh, hi);
+        else hb = ha;
+        have = y1;
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t v = (ha.h[k] * cy0 + hb.h[k] * cy1 + 32768u) >> 16;
+            out |= min(v, 255u) << (8 * k);
+        }
+        *reinterpret_cast<uint32_t*>(dst) = out;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ A.3 FAST + NMS
-// One CTA = one band of R inner rows of one level of one frame, walked left to right in chunks of CWO = 252 output
+// One CTA = one band of R inner rows of one level of one frame, walked left to right in chunks of CWO = 248 output
 // columns, so every row's survivors come out in x order and the per-row lists concatenate to OpenCV's raster order.
 // Only the region that can survive the 31-px border filter is evaluated.
 //
-// Per chunk (score tile = (R+2) rows x 256 columns, x = ox0-2 .. ox0+253):
-//   load      (R+8) x 272 pixels widened to u16 into smem (one warp per row, aligned 32-bit loads)
-//   phase A   every pixel pair: 4-compass-point rejection test in u16x2 SIMD (native VIMNMX.U16x2); the pass bits
-//             leave as warp ballots (one word per 32 pairs and parity); a block scan turns them into a queue
+// Per chunk (score tile = (R+2) rows x 256 columns, x = ox0-4 .. ox0+251):
+//   load      (R+8) x 288 pixels widened to u16 into smem with 128-bit global loads (16-byte aligned tile origin)
+//   phase A   every pixel QUAD: 4-compass-point rejection test in u16x2 SIMD (native VIMNMX.U16x2) from five
+//             64-bit shared loads; the pass bits leave as warp ballots; a block scan turns them into a queue
 //   phase B   queued pixels: full 16-point test.  Each circle pixel is packed (p | (255-p) << 16) so ONE sliding
 //             max over the 16 nine-long arcs (VIMNMX3.U16x2) yields both min-of-max(p) and max-of-min(p):
 //             A = v - min_arcs max p,  -B = max_arcs min p - v,  score = max(A, -B) - 1  (corner iff > t)
@@ -120,24 +160,24 @@ template <int R, int NT>
 __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr,
                                                    uint32_t* __restrict__ rowcnt, uint32_t* __restrict__ rowent)
 {
-    constexpr int CWO = 252;               // output columns per chunk
+    constexpr int CWO = 248;               // output columns per chunk
     constexpr int SP = 256;                // score tile pitch (bytes) = pixels evaluated per row
     constexpr int SR = R + 2;              // score tile rows
-    constexpr int TP = SP + 16;            // image tile pitch (pixels, u16 each): x = ox0-8 .. ox0+263
+    constexpr int TP = SP + 32;            // image tile pitch (pixels, u16 each): 16-pixel aligned origin <= ox0-8, 18 x 16 pixels
     constexpr int TPW = TP / 2;            // ... in 32-bit words
     constexpr int TR = R + 8;              // image tile rows
-    constexpr int MW = 8;                  // mask words per row (252 bits used)
-    constexpr int NPW = SR * 8;            // pass-bit words: [row][pair-column block of 32][parity]
+    constexpr int MW = 8;                  // mask words per row (248 bits used)
+    constexpr int NPW = SR * 8;            // pass-bit words: [row][128-pixel block][pixel-in-quad]
     constexpr int T = ORBX_FAST_T;
     constexpr int NWARP = NT / 32;
-    static_assert(NT == 256, "phase A maps 128 pair columns x 2 row groups onto 256 threads");
+    static_assert(NT == 256, "phase A maps 64 quad columns x 4 row groups onto 256 threads");
     static_assert(R * MW <= NT && NPW <= NT, "one thread per mask / pass word");
 
     __shared__ __align__(16) uint16_t s_img[TR * TP];
     __shared__ __align__(16) uint8_t s_score[SR * SP];
     __shared__ uint16_t s_q[SR * SP];      // pass queue: sy << 8 | sx
-    __shared__ uint16_t s_cq[R * SP];      // corner queue (NMS candidates inside the output region; <= R x 252)
-    __shared__ uint32_t s_pass[NPW];
+    __shared__ uint16_t s_cq[R * SP];      // corner queue (NMS candidates inside the output region; <= R x 248)
+    __shared__ __align__(16) uint32_t s_pass[NPW];
     __shared__ uint32_t s_mask[R * MW];
     __shared__ uint32_t s_rowcnt[R];
     __shared__ int s_wsum[NWARP];
@@ -161,56 +201,59 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
 
     if (tid < R) s_rowcnt[tid] = 0;
 
-    const uint32_t* W = reinterpret_cast<const uint32_t*>(s_img);
     for (int ox0 = 28; ox0 < xend; ox0 += CWO) {
         const int ox1 = min(ox0 + CWO, xend);
-        const int ix0 = ox0 - 8;
-        const int need = min(ox1 + 2 - (ox0 - 2), SP);      // pixels per score row that matter: x = ox0-2 .. ox1+1
+        const int ix0 = (ox0 - 8) & ~15;                     // 16-byte aligned tile origin
+        const int xo = (ox0 - 8) - ix0;                      // 0, 4, 8 or 12: tile x of score column sx is sx + 4 + xo
+        const int need = min(ox1 - ox0 + 6, SP);             // score columns that matter: x = ox0-4 .. ox1+1
         __syncthreads();                                     // previous chunk fully consumed
-        // ---- load tile rows [y0-4, y1+4), one warp per row, 4 pixels per lane and step
+        // ---- load tile rows [y0-4, y1+4): 128-bit loads, 16 pixels widened to u16 per thread and step
         {
             const int rows = y1 - y0 + 8;
-            const int nq = min((need + 16 + 3) >> 2, TP / 4);
-            for (int ty = wid; ty < rows; ty += NWARP) {
-                const uint8_t* src = img + (size_t)(y0 - 4 + ty) * L.pitch + ix0;
-                for (int q = lane; q < nq; q += 32) {
-                    uint32_t w = 0;
-                    if (ix0 + q * 4 < L.pitch) w = __ldg(reinterpret_cast<const uint32_t*>(src) + q);
-                    uint2 o;
-                    o.x = __byte_perm(w, 0, 0x4140);
-                    o.y = __byte_perm(w, 0, 0x4342);
-                    *reinterpret_cast<uint2*>(&s_img[ty * TP + q * 4]) = o;
-                }
+            constexpr int CPR = TP / 16;                     // 16-pixel columns per tile row
+            const int clast = (xo + need + 16) >> 4;         // last column holding a pixel phase A / B can touch
+            for (int i = tid; i < rows * CPR; i += NT) {
+                const int ty = i / CPR, col = i - ty * CPR;
+                if (col > clast) continue;
+                const int gx = ix0 + col * 16;
+                uint4 w = make_uint4(0, 0, 0, 0);
+                if (gx < L.pitch) w = __ldg(reinterpret_cast<const uint4*>(img + (size_t)(y0 - 4 + ty) * L.pitch + gx));
+                uint4* d = reinterpret_cast<uint4*>(&s_img[ty * TP + col * 16]);
+                d[0] = make_uint4(__byte_perm(w.x, 0, 0x4140), __byte_perm(w.x, 0, 0x4342), __byte_perm(w.y, 0, 0x4140), __byte_perm(w.y, 0, 0x4342));
+                d[1] = make_uint4(__byte_perm(w.z, 0, 0x4140), __byte_perm(w.z, 0, 0x4342), __byte_perm(w.w, 0, 0x4140), __byte_perm(w.w, 0, 0x4342));
             }
             for (int i = tid; i < SR * SP / 16; i += NT) reinterpret_cast<uint4*>(s_score)[i] = make_uint4(0, 0, 0, 0);
             if (tid < R * MW) s_mask[tid] = 0;
             if (tid == 0) s_cn = 0;
         }
         __syncthreads();
-        // ---- phase A: compass rejection; thread = pair column (tid & 127), rows tid >> 7, +2, ...
+        // ---- phase A: compass rejection; thread = quad column (tid & 63), rows tid >> 6, +4, ...
         {
             constexpr unsigned K = ((511u - T) << 16) | (511u - T);
-            const int p = tid & 127, wc = (tid >> 5) & 3;
-            const bool warp_on = wc * 64 < need;            // warp-uniform: this 64-pixel block holds needed pixels
-            const bool col_on = 2 * p < need;
-            for (int sy = tid >> 7; sy < nsr; sy += 2) {
-                unsigned m = 0;
-                if (warp_on) {
+            const int q = tid & 63, wc = (tid >> 5) & 1, rg = tid >> 6;
+            const bool warp_on = wc * 128 < need;           // warp-uniform: this 128-pixel block holds needed pixels
+            const bool col_on = 4 * q < need;
+            // 8-byte aligned: word index (sy+3)*TPW + 2q + 2 + xo/2 is even (TPW, xo/2 even)
+            const uint2* wp = reinterpret_cast<const uint2*>(reinterpret_cast<const uint32_t*>(s_img) + (rg + 3) * TPW + 2 * q + 2 + (xo >> 1));
+            uint4* pp = reinterpret_cast<uint4*>(s_pass) + rg * 2 + wc;
+            if (warp_on) {
+                for (int sy = rg; sy < nsr; sy += 4, wp += 2 * TPW, pp += 8) {
+                    unsigned m0 = 0, m1 = 0;
                     if (col_on) {
-                        const int b = (sy + 3) * TPW + p + 3;
-                        const unsigned c = W[b], n = W[b - 3 * TPW], s = W[b + 3 * TPW];
-                        const unsigned e = __byte_perm(W[b + 1], W[b + 2], 0x5432);
-                        const unsigned w = __byte_perm(W[b - 2], W[b - 1], 0x5432);
-                        const unsigned D = vmax2(vmin2(n, s), vmin2(e, w));
-                        const unsigned B = vmin2(vmax2(n, s), vmax2(e, w));
-                        m = ((c + K - D) | (B + K - c)) & 0x02000200u;
+                        const uint2 c = wp[0], n = wp[-3 * (TPW / 2)], s = wp[3 * (TPW / 2)], e2 = wp[1], w2 = wp[-1];
+                        const unsigned e0 = __byte_perm(c.y, e2.x, 0x5432), e1 = __byte_perm(e2.x, e2.y, 0x5432);
+                        const unsigned w0 = __byte_perm(w2.x, w2.y, 0x5432), w1 = __byte_perm(w2.y, c.x, 0x5432);
+                        const unsigned D0 = vmax2(vmin2(n.x, s.x), vmin2(e0, w0)), B0 = vmin2(vmax2(n.x, s.x), vmax2(e0, w0));
+                        const unsigned D1 = vmax2(vmin2(n.y, s.y), vmin2(e1, w1)), B1 = vmin2(vmax2(n.y, s.y), vmax2(e1, w1));
+                        m0 = (c.x + K - D0) | (B0 + K - c.x);
+                        m1 = (c.y + K - D1) | (B1 + K - c.y);
                     }
-                    const unsigned blo = __ballot_sync(0xffffffffu, m & 0x200u);
-                    const unsigned bhi = __ballot_sync(0xffffffffu, m & 0x02000000u);
-                    if (lane == 0) { s_pass[(sy * 4 + wc) * 2] = blo; s_pass[(sy * 4 + wc) * 2 + 1] = bhi; }
-                } else if (lane == 0) {
-                    s_pass[(sy * 4 + wc) * 2] = 0; s_pass[(sy * 4 + wc) * 2 + 1] = 0;
+                    const unsigned b0 = __ballot_sync(0xffffffffu, m0 & 0x200u), b1 = __ballot_sync(0xffffffffu, m0 & 0x02000000u);
+                    const unsigned b2 = __ballot_sync(0xffffffffu, m1 & 0x200u), b3 = __ballot_sync(0xffffffffu, m1 & 0x02000000u);
+                    if (lane == 0) *pp = make_uint4(b0, b1, b2, b3);
                 }
+            } else if (lane == 0) {
+                for (int sy = rg; sy < nsr; sy += 4, pp += 8) *pp = make_uint4(0u, 0u, 0u, 0u);
             }
         }
         __syncthreads();
@@ -228,11 +271,11 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
 #pragma unroll
             for (int i = 0; i < NWARP; ++i) { const int s = s_wsum[i]; if (i < wid) off += s; tot += s; }
             if (tid == 0) s_qn = tot;
-            const int sy = tid >> 3, wc = (tid >> 1) & 3, par = tid & 1;
+            const int sy = tid >> 3, base = ((tid >> 2) & 1) * 128 + (tid & 3);      // word = (sy*2 + wc)*4 + j; bit L <-> sx = (wc*32 + L)*4 + j
             while (bits) {
                 const int b = __ffs(bits) - 1;
                 bits &= bits - 1;
-                s_q[off++] = (uint16_t)((sy << 8) | ((wc * 32 + b) * 2 + par));
+                s_q[off++] = (uint16_t)((sy << 8) | (base + b * 4));
             }
         }
         __syncthreads();
@@ -241,7 +284,7 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
         for (int i = tid; i < qn; i += NT) {
             const int e = s_q[i];
             const int sy = e >> 8, sx = e & 255;
-            const uint16_t* c = &s_img[(sy + 3) * TP + sx + 6];
+            const uint16_t* c = &s_img[(sy + 3) * TP + sx + 4 + xo];
             const int v = c[0];
             unsigned q[16];
 #define ORBX_PK(k, dx, dy) q[k] = (unsigned)c[(dy) * TP + (dx)] * 0xFFFF0001u + 0x00FF0000u
@@ -263,7 +306,7 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
             const int sc = max(A, nB);
             if (sc > T) {
                 s_score[sy * SP + sx] = (uint8_t)(sc - 1);
-                const int x = ox0 - 2 + sx;
+                const int x = ox0 - 4 + sx;
                 if (x >= max(ox0, ORBX_EDGE) && x < ox1 && sy >= 1 && sy <= y1 - y0) s_cq[atomicAdd(&s_cn, 1)] = (uint16_t)e;
             }
         }
@@ -276,7 +319,7 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
             const uint8_t* p = &s_score[sy * SP + sx];
             const int s = p[0];
             if (s > p[-1] && s > p[1] && s > p[-SP - 1] && s > p[-SP] && s > p[-SP + 1] && s > p[SP - 1] && s > p[SP] && s > p[SP + 1]) {
-                const int bit = sx - 2;
+                const int bit = sx - 4;
                 atomicOr(&s_mask[(sy - 1) * MW + (bit >> 5)], 1u << (bit & 31));
             }
         }
@@ -300,7 +343,7 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
                 const int b = __ffs(m) - 1;
                 m &= m - 1;
                 const int bit = wi * 32 + b;
-                const uint32_t sc = s_score[(row + 1) * SP + bit + 2];
+                const uint32_t sc = s_score[(row + 1) * SP + bit + 4];
                 dst[slot++] = (uint32_t)(ox0 + bit) | (sc << 16);
             }
             if (wi == MW - 1) s_rowcnt[row] = base + pre;
@@ -309,7 +352,6 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
     __syncthreads();
     if (tid < y1 - y0) cnt_out[y0 - ORBX_EDGE + tid] = s_rowcnt[tid];
 }
-
 
 // ------------------------------------------------------------------------------------------------ A.6 retainBest
 // Exact emulation of KeyPointsFilter::retainBest = libstdc++ std::nth_element (__introselect: median-of-3 to
@@ -664,13 +706,14 @@ __device__ __forceinline__ void glibc_sincosf(float ang, float* sn, float* cs)
 // 7x7 sigma-2 Gaussian of every level in OpenCV's float sepFilter2D arithmetic:
 //   row pass   acc = F(k0*p[x-3]); acc = fma(p[x-3+i], k_i, acc), i = 1..6
 //   col pass   acc = F(k3*r[y]);   acc = fma(F(r[y+j] + r[y-j]), k_{3+j}, acc), j = 1..3;  out = rint(acc)
-// Only the region a descriptor can sample is produced: [13, w-13) x [13, h-13) (keypoints keep 31 px from the
-// border, rBRIEF reaches 18).  One thread = 4 adjacent columns walked down BLUR_RH rows with a 7-deep register
-// window of row-pass values, so every input byte is loaded once per thread and converted to float once
-// (exactly: PRMT into the mantissa of 2^23, one FADD).  No clamp is needed: the taps sum to < 1.
-constexpr int BLUR_RH = 32;            // output rows per thread
-constexpr int BLUR_NT = 128;           // 4 warps = 4 vertically stacked strips of a 128-column group
-constexpr int BLUR_LO = 12;            // first produced row / column is BLUR_LO rounded to the quad grid (x) / 13 (y)
+// Only the region a descriptor can sample is produced: [12, w-13) x [13, h-13) (keypoints keep 31 px from the
+// border, rBRIEF reaches 18).  One thread = 8 adjacent columns walked down BLUR_RH rows with a 7-deep register
+// window of row-pass values (rotated by unrolling, no moves), so every input byte is loaded once per thread and
+// converted to float once (exactly: PRMT into the mantissa of 2^23, one FADD).  Work items (column group, strip)
+// of a level are flattened so warps stay full on narrow levels.  No clamp is needed: the taps sum to < 1.
+constexpr int BLUR_RH = 64;            // output rows per thread
+constexpr int BLUR_NT = 128;           // work items per CTA
+constexpr int BLUR_LO = 12;            // first produced column (8-column groups start at 12 + 8q, so x0 - 4 is 8-byte aligned)
 
 __device__ __forceinline__ float u8f(uint32_t w, uint32_t sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f; }
 
@@ -681,47 +724,55 @@ __global__ void __launch_bounds__(BLUR_NT) k_blur(const __grid_constant__ Geom g
 #pragma unroll 1
     for (int i = 1; i < g.nlevels; ++i) if ((int)blockIdx.x >= g.L[i].blur0) l = i;
     const LevelGeom& L = g.L[l];
-    const int tile = blockIdx.x - L.blur0;
-    if (tile >= L.nblur) return;
-    const int cg = tile % L.blur_cgs, sg = tile / L.blur_cgs;
-    const int x0 = BLUR_LO + (cg * 32 + (threadIdx.x & 31)) * 4;                 // first of this thread's 4 columns (multiple of 4)
-    const int ys = 13 + (sg * 4 + (threadIdx.x >> 5)) * BLUR_RH;                  // first output row of this warp's strip
+    const int item = (blockIdx.x - L.blur0) * BLUR_NT + threadIdx.x;
+    const int strip = item / L.blur_cgs, cg = item - strip * L.blur_cgs;
+    const int x0 = BLUR_LO + cg * 8;                                              // first of this thread's 8 columns
+    const int ys = 13 + strip * BLUR_RH;                                          // first output row
     const int ye = min(ys + BLUR_RH, L.h - 13);
-    if (x0 >= L.w - 13 || ys >= ye) return;
+    if ((int)blockIdx.x - L.blur0 >= L.nblur || ys >= ye) return;
     const float k0 = __int_as_float(0x3d8fafb1), k1 = __int_as_float(0x3e06387e), k2 = __int_as_float(0x3e434a39), k3 = __int_as_float(0x3e5d4ae0);
     const uint8_t* src = pyr + (size_t)f * g.pyr_frame + L.img_off + (size_t)(ys - 3) * L.pitch + (x0 - 4);
     uint8_t* dst = blur + (size_t)f * g.pyr_frame + L.img_off + (size_t)ys * L.pitch + x0;
-    float w[4][7];
+    const bool hi_ok = x0 + 4 < L.pitch;                                          // second 8-byte load inside the row
+    const int nrows = (ye - ys) + 6;
+    float w[8][7];
 #pragma unroll 1
-    for (int r = 0; r < (ye - ys) + 6; ++r, src += L.pitch) {
-        const uint32_t a = __ldg(reinterpret_cast<const uint32_t*>(src));
-        const uint32_t b = __ldg(reinterpret_cast<const uint32_t*>(src) + 1);
-        const uint32_t c = (x0 + 4 < L.pitch) ? __ldg(reinterpret_cast<const uint32_t*>(src) + 2) : 0u;
-        float p[10];                                                              // pixels x0-3 .. x0+6
-        p[0] = u8f(a, 0x7651); p[1] = u8f(a, 0x7652); p[2] = u8f(a, 0x7653);
-        p[3] = u8f(b, 0x7650); p[4] = u8f(b, 0x7651); p[5] = u8f(b, 0x7652); p[6] = u8f(b, 0x7653);
-        p[7] = u8f(c, 0x7650); p[8] = u8f(c, 0x7651); p[9] = u8f(c, 0x7652);
+    for (int r0 = 0; r0 < nrows; r0 += 7) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float acc = __fmul_rn(k0, p[j]);
-            acc = __fmaf_rn(p[j + 1], k1, acc); acc = __fmaf_rn(p[j + 2], k2, acc); acc = __fmaf_rn(p[j + 3], k3, acc);
-            acc = __fmaf_rn(p[j + 4], k2, acc); acc = __fmaf_rn(p[j + 5], k1, acc); acc = __fmaf_rn(p[j + 6], k0, acc);
+        for (int k = 0; k < 7; ++k) {
+            const int r = r0 + k;
+            if (r < nrows) {
+                const uint2 a = __ldg(reinterpret_cast<const uint2*>(src));
+                const uint2 b = hi_ok ? __ldg(reinterpret_cast<const uint2*>(src) + 1) : make_uint2(0u, 0u);
+                src += L.pitch;
+                float p[14];                                                       // pixels x0-3 .. x0+10
+                p[0] = u8f(a.x, 0x7651); p[1] = u8f(a.x, 0x7652); p[2] = u8f(a.x, 0x7653);
+                p[3] = u8f(a.y, 0x7650); p[4] = u8f(a.y, 0x7651); p[5] = u8f(a.y, 0x7652); p[6] = u8f(a.y, 0x7653);
+                p[7] = u8f(b.x, 0x7650); p[8] = u8f(b.x, 0x7651); p[9] = u8f(b.x, 0x7652); p[10] = u8f(b.x, 0x7653);
+                p[11] = u8f(b.y, 0x7650); p[12] = u8f(b.y, 0x7651); p[13] = u8f(b.y, 0x7652);
 #pragma unroll
-            for (int i = 0; i < 6; ++i) w[j][i] = w[j][i + 1];
-            w[j][6] = acc;
-        }
-        if (r >= 6) {
-            uint32_t out = 0;
+                for (int j = 0; j < 8; ++j) {
+                    float acc = __fmul_rn(k0, p[j]);
+                    acc = __fmaf_rn(p[j + 1], k1, acc); acc = __fmaf_rn(p[j + 2], k2, acc); acc = __fmaf_rn(p[j + 3], k3, acc);
+                    acc = __fmaf_rn(p[j + 4], k2, acc); acc = __fmaf_rn(p[j + 5], k1, acc); acc = __fmaf_rn(p[j + 6], k0, acc);
+                    w[j][k] = acc;                                                 // window slot of source row r is r % 7 == k
+                }
+                if (r >= 6) {
+                    uint32_t o0 = 0, o1 = 0;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float o = __fmul_rn(k3, w[j][3]);
-                o = __fmaf_rn(__fadd_rn(w[j][4], w[j][2]), k2, o);
-                o = __fmaf_rn(__fadd_rn(w[j][5], w[j][1]), k1, o);
-                o = __fmaf_rn(__fadd_rn(w[j][6], w[j][0]), k0, o);
-                out |= (uint32_t)__float2int_rn(o) << (8 * j);
+                    for (int j = 0; j < 8; ++j) {
+                        float o = __fmul_rn(k3, w[j][(k + 4) % 7]);                                          // row r-3
+                        o = __fmaf_rn(__fadd_rn(w[j][(k + 5) % 7], w[j][(k + 3) % 7]), k2, o);              // r-2, r-4
+                        o = __fmaf_rn(__fadd_rn(w[j][(k + 6) % 7], w[j][(k + 2) % 7]), k1, o);              // r-1, r-5
+                        o = __fmaf_rn(__fadd_rn(w[j][k], w[j][(k + 1) % 7]), k0, o);                         // r,   r-6
+                        const uint32_t q = (uint32_t)(__float_as_int(__fadd_rn(o, 12582912.0f)) & 0xff);    // rint via 1.5 * 2^23
+                        if (j < 4) o0 |= q << (8 * j); else o1 |= q << (8 * (j - 4));
+                    }
+                    reinterpret_cast<uint32_t*>(dst)[0] = o0;
+                    reinterpret_cast<uint32_t*>(dst)[1] = o1;
+                    dst += L.pitch;
+                }
             }
-            *reinterpret_cast<uint32_t*>(dst) = out;
-            dst += L.pitch;
         }
     }
 }
@@ -730,20 +781,19 @@ __global__ void __launch_bounds__(BLUR_NT) k_blur(const __grid_constant__ Geom g
 // One warp = one final keypoint (no block-level sync): IC moments over the radius-15 disc of the unblurred level
 // (lane = column, shuffle reduction), fastAtan2, glibc-exact sin/cos, then the 37x37 window of the blurred level is
 // staged in shared memory with aligned word loads and the 256 steered tests are sampled from it
-// (lane = descriptor byte).  Keypoint records and descriptors leave as coalesced stores.
+// (lane = descriptor byte).  cvRound of the rotated coordinates is the exact magic-number add (|v| < 2^22).
+// Keypoint records and descriptors leave as coalesced stores.
 constexpr int DESC_KPB = 4;            // keypoints (warps) per CTA
 constexpr int DESC_NT = DESC_KPB * 32;
-constexpr int DWIN = 37, DWORDS = 12;  // staged window: 37 rows x 12 words (48 bytes >= 37 + 3 alignment slack)
-
-__constant__ int c_umax[16];
+constexpr int DWIN = 37, DWORDS = 16;  // staged window: 37 rows x 16 words (12 used: 48 bytes >= 37 + 3 alignment slack)
 
 __global__ void __launch_bounds__(DESC_NT) k_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr,
                                                       const uint8_t* __restrict__ blur, const Elem* __restrict__ work,
-                                                      const int* __restrict__ fincnt, const int8_t* __restrict__ pattern,
+                                                      const int* __restrict__ fincnt, const float4* __restrict__ pattern,
                                                       float* __restrict__ kps_out, uint8_t* __restrict__ desc_out,
                                                       int* __restrict__ counts_out, int cap)
 {
-    __shared__ uint32_t s_win[DESC_KPB][DWIN * DWORDS];
+    __shared__ uint32_t s_win[DESC_KPB][(DWIN + 1) * DWORDS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, f = blockIdx.y;
     const int slot = blockIdx.x * DESC_KPB + wid;
     int total = 0, lvl = -1, idx = 0;
@@ -760,28 +810,37 @@ __global__ void __launch_bounds__(DESC_NT) k_describe(const __grid_constant__ Ge
     const LevelGeom& L = g.L[lvl];
     const Elem e = work[(size_t)f * g.ws_frame + L.ws_off + idx];
     const int x = (int)(e.pos & 0xffffu), y = (int)(e.pos >> 16);
+    const int pitch = L.pitch;
     const uint8_t* img = pyr + (size_t)f * g.pyr_frame + L.img_off;
     const uint8_t* bimg = blur + (size_t)f * g.pyr_frame + L.img_off;
 
-    // ---- stage the blurred window rows y-18 .. y+18, bytes (x-18) .. (x+18), as aligned words
+    // ---- stage the blurred window rows y-18 .. y+18, bytes (x-18) .. (x+18), as aligned words; 2 rows per step
     const int xa = (x - 18) & ~3, sh = (x - 18) & 3;
     uint32_t* win = s_win[wid];
-    for (int i = lane; i < DWIN * DWORDS; i += 32) {
-        const int r = i / DWORDS, c = i - r * DWORDS;
-        uint32_t v = 0;
-        if (xa + c * 4 < L.pitch) v = __ldg(reinterpret_cast<const uint32_t*>(bimg + (size_t)(y - 18 + r) * L.pitch + xa) + c);
-        win[i] = v;
-    }
-    // ---- IC moments on the unblurred level: lane <-> column u = lane - 15
-    int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        const int u = lane - 15, au = u < 0 ? -u : u;
-        const uint8_t* p = img + (size_t)(y - 15) * L.pitch + (x + u);
-#pragma unroll 1
-        for (int vv = -15; vv <= 15; ++vv, p += L.pitch) {
-            const int av = vv < 0 ? -vv : vv;
-            if (au <= c_umax[av]) { const int I = __ldg(p); m10 += u * I; m01 += vv * I; }
+    {
+        const int c = lane & 15, half = lane >> 4;
+        const bool on = c < 12 && xa + c * 4 < pitch;
+        const uint8_t* p = bimg + (size_t)(y - 18 + half) * pitch + xa + c * 4;
+        uint32_t* d = win + half * DWORDS + c;
+#pragma unroll
+        for (int it = 0; it < (DWIN + 1) / 2; ++it, p += 2 * pitch, d += 2 * DWORDS) {
+            uint32_t v = 0;
+            if (on && (2 * it + half) < DWIN) v = __ldg(reinterpret_cast<const uint32_t*>(p));
+            *d = v;
         }
+    }
+    // ---- IC moments on the unblurred level: lane <-> column u = lane - 15; umax[|v|] unrolled at compile time
+    int m10 = 0, m01 = 0;
+    {
+        const int u = lane - 15, au = u < 0 ? -u : u;
+        const uint8_t* p = img + (size_t)(y - 15) * pitch + (x + u);
+        int colsum = 0;
+        constexpr int UMAX[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+#pragma unroll
+        for (int vv = -15; vv <= 15; ++vv, p += pitch) {
+            if (lane < 31 && au <= UMAX[vv < 0 ? -vv : vv]) { const int I = __ldg(p); colsum += I; m01 += vv * I; }
+        }
+        m10 = u * colsum;
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, d); m01 += __shfl_xor_sync(0xffffffffu, m01, d); }
@@ -792,15 +851,18 @@ __global__ void __launch_bounds__(DESC_NT) k_describe(const __grid_constant__ Ge
     // ---- steered rBRIEF: lane <-> descriptor byte
     {
         const uint8_t* B = reinterpret_cast<const uint8_t*>(win) + 18 * (DWORDS * 4) + 18 + sh;
+        constexpr float MAGIC = 12582912.0f;                 // 1.5 * 2^23: (v + MAGIC) holds rint(v) in its low mantissa bits
+        constexpr int MBITS = 0x4B400000;
         unsigned byte = 0;
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-            const char4 pt = *reinterpret_cast<const char4*>(pattern + (lane * 8 + t) * 4);
-            const float x0 = (float)pt.x, y0 = (float)pt.y, x1 = (float)pt.z, y1 = (float)pt.w;
-            const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, cs), __fmul_rn(y0, sn)));
-            const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sn), __fmul_rn(y0, cs)));
-            const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, cs), __fmul_rn(y1, sn)));
-            const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sn), __fmul_rn(y1, cs)));
+            const float4 pt = __ldg(pattern + lane * 8 + t);
+            const float fx0 = __fsub_rn(__fmul_rn(pt.x, cs), __fmul_rn(pt.y, sn));
+            const float fy0 = __fadd_rn(__fmul_rn(pt.x, sn), __fmul_rn(pt.y, cs));
+            const float fx1 = __fsub_rn(__fmul_rn(pt.z, cs), __fmul_rn(pt.w, sn));
+            const float fy1 = __fadd_rn(__fmul_rn(pt.z, sn), __fmul_rn(pt.w, cs));
+            const int ix0 = __float_as_int(__fadd_rn(fx0, MAGIC)) - MBITS, iy0 = __float_as_int(__fadd_rn(fy0, MAGIC)) - MBITS;
+            const int ix1 = __float_as_int(__fadd_rn(fx1, MAGIC)) - MBITS, iy1 = __float_as_int(__fadd_rn(fy1, MAGIC)) - MBITS;
             const int t0 = B[iy0 * (DWORDS * 4) + ix0], t1 = B[iy1 * (DWORDS * 4) + ix1];
             byte |= (unsigned)(t0 < t1) << t;
         }
@@ -821,6 +883,5 @@ __global__ void __launch_bounds__(DESC_NT) k_describe(const __grid_constant__ Ge
         }
     }
 }
-
 
 }  // namespace orbx
