@@ -225,8 +225,8 @@ int run_extract(orbx_ctx* c, const uint8_t* d_imgs, int batch, int w, int h, siz
     stage_mark(c, 1);
     for (int l = 1; l < g.nlevels; ++l) {
         if (g.L[l].w <= 0 || g.L[l].h <= 0) continue;
-        const dim3 blk(128);
-        const dim3 grd((unsigned)((g.L[l].pitch / 4 + 127) / 128), (unsigned)((g.L[l].h + PYR_RH - 1) / PYR_RH), (unsigned)batch);
+        const dim3 blk(32, PYR_BY);
+        const dim3 grd((unsigned)((g.L[l].pitch / 4 + 31) / 32), (unsigned)((g.L[l].h + PYR_RH * PYR_BY - 1) / (PYR_RH * PYR_BY)), (unsigned)batch);
         k_pyr_down<<<grd, blk, 0, c->stream>>>(g, l, pyr, (const uint32_t*)c->tabs.p);
         ++c->launches;
     }
@@ -281,14 +281,18 @@ int run_match(orbx_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int n
     const bool knn2 = d_second != nullptr;
     const int tiles_m = (nq + MT_QROWS - 1) / MT_QROWS;
     const int ntile_n = (nt + MT_BN - 1) / MT_BN;
+    constexpr int kSMs = 148;                                // one CTA per SM (163 KB of shared memory each)
+    // Few (query tile, set) pairs: split the train rows across CTAs and merge with atomicMax on the packed key.
     int nsplit = 1;
     if (!knn2) {
         const long base = (long)tiles_m * nsets;
-        nsplit = (int)std::min<long>(ntile_n, std::max<long>(1, (2 * 148 + base - 1) / base));
+        if (base < kSMs) nsplit = (int)std::min<long>(ntile_n, std::max<long>(1, (kSMs + base - 1) / base));
     }
     const int tiles_per_split = (ntile_n + nsplit - 1) / nsplit;
     const int rows_per_split = tiles_per_split * MT_BN;
     nsplit = (nt + rows_per_split - 1) / rows_per_split;
+    // Many sets: each CTA keeps its expanded query tile and walks sets z, z + zgroups, ... (persistent pipelines).
+    const int zgroups = std::max(1, std::min(nsets, kSMs / std::max(1, tiles_m * nsplit)));
     int* keys = nullptr;
     const size_t nout = (size_t)nq * nsets;
     int rc;
@@ -301,9 +305,9 @@ int run_match(orbx_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int n
         k_match_keys_init<<<(unsigned)((nout + 255) / 256), 256, 0, c->stream>>>(keys, nout);
         ++c->launches;
     }
-    const dim3 grd((unsigned)tiles_m, (unsigned)nsplit, (unsigned)nsets);
-    if (knn2) k_hamming_umma<true><<<grd, MT_THREADS, MT_SMEM_BYTES, c->stream>>>(d_q, nq, d_t, nt, stride_rows, d_counts, rows_per_split, d_best, d_second, keys, (int*)c->mstatus.p);
-    else      k_hamming_umma<false><<<grd, MT_THREADS, MT_SMEM_BYTES, c->stream>>>(d_q, nq, d_t, nt, stride_rows, d_counts, rows_per_split, d_best, d_second, keys, (int*)c->mstatus.p);
+    const dim3 grd((unsigned)tiles_m, (unsigned)nsplit, (unsigned)zgroups);
+    if (knn2) k_hamming_umma<true><<<grd, MT_THREADS, MT_SMEM_BYTES, c->stream>>>(d_q, nq, d_t, nt, stride_rows, d_counts, nsets, rows_per_split, d_best, d_second, keys, (int*)c->mstatus.p);
+    else      k_hamming_umma<false><<<grd, MT_THREADS, MT_SMEM_BYTES, c->stream>>>(d_q, nq, d_t, nt, stride_rows, d_counts, nsets, rows_per_split, d_best, d_second, keys, (int*)c->mstatus.p);
     ++c->launches;
     if (nsplit > 1) {
         k_match_finalize<<<(unsigned)((nout + 255) / 256), 256, 0, c->stream>>>(keys, nq, nout, d_best);

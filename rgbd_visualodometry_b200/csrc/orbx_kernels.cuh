@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(256) k_gray(const uint8_t* __restrict__ in, un
 // source bytes); each output's horizontal pass is one funnel shift + one IDP.2A (u16 taps x u8 pixels), and it is
 // reused by the next output row when that row needs the same source row (the common case at ratio 1.2).
 // Load/store instructions per pixel drop ~6x against byte gathers -- the LSU issue rate was the bound.
-constexpr int PYR_RH = 32;
+constexpr int PYR_RH = 16;          // output rows per thread
+constexpr int PYR_BY = 4;           // row strips (warps) per CTA; a warp covers 128 output columns
 struct PyrRow { uint32_t h[4]; };
 __device__ __forceinline__ PyrRow pyr_hpass(const uint8_t* __restrict__ row, bool w2ok, const uint32_t* coef, const uint32_t* sh, const bool* hi)
 {
@@ -93,10 +94,10 @@ __global__ void __launch_bounds__(128) k_pyr_down(const __grid_constant__ Geom g
 {
     const LevelGeom& D = g.L[l];
     const LevelGeom& S = g.L[l - 1];
-    const int x = (blockIdx.x * 128 + threadIdx.x) * 4;
+    const int x = (blockIdx.x * 32 + threadIdx.x) * 4;
     const int f = blockIdx.z;
-    if (x >= D.pitch) return;
-    const int ys = blockIdx.y * PYR_RH, ye = min(ys + PYR_RH, D.h);
+    const int ys = (blockIdx.y * PYR_BY + threadIdx.y) * PYR_RH, ye = min(ys + PYR_RH, D.h);
+    if (x >= D.pitch || ys >= ye) return;
     uint8_t* dst = pyr + (size_t)f * g.pyr_frame + D.img_off + (size_t)ys * D.pitch + x;
     if (x >= D.w) {                                          // row padding: keep it zero
         for (int y = ys; y < ye; ++y, dst += D.pitch) *reinterpret_cast<uint32_t*>(dst) = 0u;

@@ -8,16 +8,20 @@
 //   dot(q, t) = 256 - 2 * hamming(q, t)   =>   hamming = (256 - dot) / 2          (exact, |dot| <= 256)
 // so the M x N distance matrix is one int8 GEMM with K = 256 and int32 accumulation.
 //
-// One CTA owns 256 query rows (two 128-row A tiles, expanded once into 128B-swizzled K-major smem) and walks a
-// range of train rows in tiles of 128 (B tiles).  Warp roles:
-//   warps 8-11  expanders : 32-byte descriptor rows -> +-1 int8 rows written straight into the swizzled UMMA
-//                           layout through a 256-entry smem LUT (the bit expansion never touches HBM)
-//   warp  12    issuer    : one thread issues 2 x 8 tcgen05.mma.kind::i8 (M128 N128 K32) per B tile into a
+// One CTA owns 256 query rows (two 128-row A tiles).  The map is shared by every frame, so the A operand is expanded
+// ONCE per CTA and parked in TENSOR MEMORY (tcgen05.st; the MMA then takes A from TMEM, "TS" form), which removes
+// half of the shared-memory operand traffic of every MMA.  The CTA then walks train sets and, inside a set, tiles of
+// 96 train rows (B tiles).  Warp roles:
+//   warps 8-10  expanders : 32-byte descriptor rows -> +-1 int8 rows written straight into the 128B-swizzled K-major
+//                           UMMA layout; the bit expansion is pure ALU (multiply-spread), never touches HBM or a LUT
+//   warp  11    issuer    : one thread issues 2 x 8 tcgen05.mma.kind::i8 (M128 N96 K32, A from TMEM) per B tile into a
 //                           double-buffered pair of TMEM accumulators, commits to mbarriers
-//   warps 0-7   epilogue  : tcgen05.ld 32 lanes x 32 columns, pack key = dot << 20 | (0xFFFFF - j) so a single
+//   warps 0-7   epilogue  : tcgen05.ld 32 lanes x 96 columns, pack key = dot << 20 | (0xFFFFF - j) so a single
 //                           integer max carries both the best distance and the lowest-index tie-break
-// Pipelines: smem stages (expanders <-> issuer) and TMEM accumulators (issuer <-> epilogue), all mbarrier based.
-// Train-row ranges can be split across CTAs (small M); partial results merge with atomicMax on the packed key.
+// TMEM map (512 columns): accumulators [buffer 0..1][A tile 0..1] x 96 columns at 0..383, A tiles 2 x 64 columns at 384.
+// Pipelines: smem stages (expanders <-> issuer) and TMEM accumulators (issuer <-> epilogue), all mbarrier based,
+// running continuously across set boundaries (persistent CTAs).  Train-row ranges can be split across CTAs (small
+// problems); partial results merge with atomicMax on the packed key.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,19 +29,20 @@
 namespace orbx {
 
 constexpr int MT_QROWS = 256;          // query rows per CTA (two UMMA M=128 tiles)
-constexpr int MT_BN = 128;             // train rows per B tile (UMMA N)
-constexpr int MT_STAGES = 3;
-constexpr int MT_THREADS = 13 * 32;
-constexpr int MT_A_BYTES = 128 * 256;  // one A tile, int8
+constexpr int MT_BN = 96;              // train rows per B tile (UMMA N)
+constexpr int MT_STAGES = 4;
+constexpr int MT_EXP_WARPS = MT_BN / 32;
+constexpr int MT_ISSUER_WARP = 8 + MT_EXP_WARPS;
+constexpr int MT_THREADS = (MT_ISSUER_WARP + 1) * 32;
 constexpr int MT_B_BYTES = MT_BN * 256;
-constexpr int MT_SMEM_A = 0;
-constexpr int MT_SMEM_B = 2 * MT_A_BYTES;
-constexpr int MT_SMEM_LUT = MT_SMEM_B + MT_STAGES * MT_B_BYTES;
-constexpr int MT_SMEM_BAR = MT_SMEM_LUT + 256 * 8;
+constexpr int MT_SMEM_B = 0;
+constexpr int MT_SMEM_BAR = MT_SMEM_B + MT_STAGES * MT_B_BYTES;
 constexpr int MT_SMEM_BYTES = MT_SMEM_BAR + 128 + 1024;   // + barriers/tmem slot + 1 KB alignment slack
 constexpr uint32_t MT_TMEM_COLS = 512;
+constexpr uint32_t MT_TMEM_A = 4 * MT_BN;                  // first column of the A tiles
 constexpr int MT_KEY_SHIFT = 20;
 constexpr int MT_MAX_TRAIN = 1 << MT_KEY_SHIFT;            // train rows per set representable in the packed key
+static_assert(4 * MT_BN + 128 <= 512, "TMEM budget");
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -74,6 +79,23 @@ __device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t da, uint64_t
                  "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from tensor memory (TS form): D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void tc_mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                 "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                 "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                   "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+                   "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+                   "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+                 : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -91,127 +113,168 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// instruction descriptor: D = S32 (c_format 2), A = B = signed int8 (format 1), both K-major, N = 128, M = 128
+// instruction descriptor: D = S32 (c_format 2), A = B = signed int8 (format 1), both K-major, N = MT_BN, M = 128
 constexpr uint32_t MT_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MT_BN >> 3) << 17) | ((128u >> 4) << 24);
+
+// 4 descriptor bits -> 4 int8 (+1 for a set bit, -1 otherwise): multiply-spread the nibble to one bit per byte, then
+// 0xFF - 0xFE * bit.  No table, no shared-memory traffic.
+__device__ __forceinline__ uint32_t pm1x4(uint32_t nibble) {
+    const uint32_t spread = (nibble * 0x00204081u) & 0x01010101u;
+    return 0xFFFFFFFFu - spread * 0xFEu;
+}
+// word i (0..63) of the expanded row = int8 values of descriptor bits 4i .. 4i+3
+__device__ __forceinline__ uint32_t pm1_word(const uint32_t* w, int i) { return pm1x4((w[i >> 3] >> ((i & 7) * 4)) & 15u); }
 
 // Expand one 32-byte descriptor row into 256 +-1 int8 in the canonical K-major SW128 layout of a `rows`-row tile:
 //   byte k of row r  ->  tile + (k / 128) * rows * 128 + (r / 8) * 1024 + (r % 8) * 128 + (((k % 128) / 16) ^ (r % 8)) * 16 + k % 16
-__device__ __forceinline__ void expand_row(uint8_t* tile, int rows, int r, const uint4 lo, const uint4 hi, const uint2* lut)
+__device__ __forceinline__ void expand_row(uint8_t* tile, int rows, int r, const uint4 lo, const uint4 hi)
 {
     const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
     uint8_t* rbase = tile + (r >> 3) * 1024 + (r & 7) * 128;
 #pragma unroll
     for (int c16 = 0; c16 < 16; ++c16) {                     // 16 descriptor bits -> 16 int8 -> one 16-byte chunk
-        const uint32_t two = (w[c16 >> 1] >> ((c16 & 1) * 16)) & 0xffffu;
-        const uint2 a = lut[two & 255u], b = lut[two >> 8];
         uint8_t* dst = rbase + (c16 >> 3) * rows * 128 + (((c16 & 7) ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(dst) = make_uint4(a.x, a.y, b.x, b.y);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pm1_word(w, 4 * c16), pm1_word(w, 4 * c16 + 1), pm1_word(w, 4 * c16 + 2), pm1_word(w, 4 * c16 + 3));
     }
 }
 
 // KNN2 = false: best match only (cv match);  true: best and second best (cv knnMatch k = 2; needs nsplit == 1).
 // Outputs: if keys != nullptr (split mode) atomicMax of the packed key, finalised by k_match_finalize;
 //          else DMatch records are written directly.
+// Persistent over train sets: CTA (x = query tile, y = train-row split, z = set group) expands its 256 query rows
+// ONCE and then walks sets z, z + gridDim.z, ... with all three pipelines running continuously across set
+// boundaries (the map is shared by every frame, so the A operand never has to be rebuilt).
+struct MatchSetRange { int n0, n1, ntiles; };
+__device__ __forceinline__ MatchSetRange match_set_range(const int* __restrict__ counts, int set, int nt, int split, int rows_per_split)
+{
+    const int nvalid = counts ? max(0, min(__ldg(counts + set), nt)) : nt;               // ragged sets: rows actually present
+    MatchSetRange r;
+    r.n0 = split * rows_per_split;
+    r.n1 = min(nvalid, r.n0 + rows_per_split);
+    r.ntiles = r.n1 > r.n0 ? (r.n1 - r.n0 + MT_BN - 1) / MT_BN : 0;
+    return r;
+}
+
 template <bool KNN2>
 __global__ void __launch_bounds__(MT_THREADS, 1)
 k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restrict__ train, int nt, int train_stride_rows,
-               const int* __restrict__ train_counts, int rows_per_split, int4* __restrict__ best, int4* __restrict__ second,
-               int* __restrict__ keys, int* __restrict__ status)
+               const int* __restrict__ train_counts, int nsets, int rows_per_split, int4* __restrict__ best,
+               int4* __restrict__ second, int* __restrict__ keys, int* __restrict__ status)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
-    uint2* lut = reinterpret_cast<uint2*>(smem + MT_SMEM_LUT);
     const uint32_t bar0 = sbase + MT_SMEM_BAR;
     const uint32_t bar_full = bar0, bar_empty = bar0 + 8 * MT_STAGES, bar_tfull = bar0 + 16 * MT_STAGES, bar_tempty = bar_tfull + 16;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + MT_SMEM_BAR + 16 * MT_STAGES + 32);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int set = blockIdx.z, split = blockIdx.y;
+    const int split = blockIdx.y;
     const int q0 = blockIdx.x * MT_QROWS;
-    const int nvalid = train_counts ? max(0, min(__ldg(train_counts + set), nt)) : nt;   // ragged sets: rows actually present
-    const int n0 = split * rows_per_split, n1 = min(nvalid, n0 + rows_per_split);
-    const int ntiles = n1 > n0 ? (n1 - n0 + MT_BN - 1) / MT_BN : 0;
-    const uint8_t* tr = train + (size_t)set * train_stride_rows * 32;
 
-    // ---- setup: LUT, barriers, TMEM, A tiles
-    if (tid < 256) {
-        uint32_t lo = 0, hi = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            lo |= (((tid >> i) & 1) ? 0x01u : 0xFFu) << (8 * i);
-            hi |= (((tid >> (i + 4)) & 1) ? 0x01u : 0xFFu) << (8 * i);
-        }
-        lut[tid] = make_uint2(lo, hi);
-    }
+    // ---- setup: barriers, TMEM, A tiles (expanded in registers and parked in tensor memory)
     if (tid == 0) {
-        for (int s = 0; s < MT_STAGES; ++s) { mbar_init(bar_full + 8 * s, 128); mbar_init(bar_empty + 8 * s, 1); }
+        for (int s = 0; s < MT_STAGES; ++s) { mbar_init(bar_full + 8 * s, MT_BN); mbar_init(bar_empty + 8 * s, 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 256); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 12) {
+    if (warp == MT_ISSUER_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(MT_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    __syncthreads();                                         // LUT visible
-    if (tid < MT_QROWS) {
-        const int q = q0 + tid;
-        uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
-        if (q < nq) {
-            const uint4* p = reinterpret_cast<const uint4*>(query + (size_t)q * 32);
-            lo = __ldg(p); hi = __ldg(p + 1);
-        }
-        expand_row(smem + MT_SMEM_A + (tid >> 7) * MT_A_BYTES, 128, tid & 127, lo, hi, lut);
-    }
-    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     bool ok = true;
+    if (warp < 8) {                                          // thread <-> query row <-> TMEM lane (same mapping as the epilogue)
+        const int q = q0 + (warp >> 2) * 128 + (warp & 3) * 32 + lane;
+        uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+        if (q < nq) {
+            const uint4* p = reinterpret_cast<const uint4*>(query + (size_t)q * 32);
+            lo = __ldg(p); hi = __ldg(p + 1);
+        }
+        const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + MT_TMEM_A + (uint32_t)(warp >> 2) * 64u;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {               // 64 columns = K 256 int8, four per 32-bit column
+            uint32_t r[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = pm1_word(w, half * 32 + i);
+            tc_st32(ta + half * 32, r);
+        }
+        tc_wait_st();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
-    if (warp >= 8 && warp < 12) {
-        // ================= expanders =================
-        const int r = tid - 256;                             // row of the B tile owned by this thread
-        for (int t = 0; t < ntiles; ++t) {
+    if (warp >= 8 && warp < MT_ISSUER_WARP) {
+        // ================= expanders: one B-tile row per thread, next tile's row prefetched into registers =================
+        const int r = tid - 256;                             // 0 .. MT_BN-1
+        int set = blockIdx.z, i = 0, t = 0;
+        MatchSetRange rg = {0, 0, 0};
+        if (set < nsets) rg = match_set_range(train_counts, set, nt, split, rows_per_split);
+        // make (set, i) name an existing tile, skipping empty sets; false when this CTA's work is exhausted
+        auto seek = [&]() -> bool {
+            while (set < nsets && i >= rg.ntiles) {
+                set += gridDim.z; i = 0;
+                if (set < nsets) rg = match_set_range(train_counts, set, nt, split, rows_per_split);
+            }
+            return set < nsets;
+        };
+        auto load_row = [&](uint4& lo, uint4& hi) {
+            const int j = rg.n0 + i * MT_BN + r;
+            lo = make_uint4(0, 0, 0, 0); hi = lo;
+            if (j < rg.n1) {
+                const uint4* p = reinterpret_cast<const uint4*>(train + ((size_t)set * train_stride_rows + j) * 32);
+                lo = __ldg(p); hi = __ldg(p + 1);
+            }
+        };
+        uint4 lo, hi;
+        bool have = seek();
+        if (have) load_row(lo, hi);
+        while (have) {
+            const uint4 clo = lo, chi = hi;
+            ++i;
+            have = seek();
+            if (have) load_row(lo, hi);                      // in flight while this tile is expanded
             const int s = t % MT_STAGES;
             const uint32_t ph = (uint32_t)(t / MT_STAGES) & 1u;
             if (!mbar_wait(bar_empty + 8 * s, ph ^ 1u)) { ok = false; break; }
-            const int j = n0 + t * MT_BN + r;
-            uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
-            if (j < n1) {
-                const uint4* p = reinterpret_cast<const uint4*>(tr + (size_t)j * 32);
-                lo = __ldg(p); hi = __ldg(p + 1);
-            }
-            expand_row(smem + MT_SMEM_B + s * MT_B_BYTES, MT_BN, r, lo, hi, lut);
+            expand_row(smem + MT_SMEM_B + s * MT_B_BYTES, MT_BN, r, clo, chi);
             fence_proxy_async_smem();
             mbar_arrive(bar_full + 8 * s);
+            ++t;
         }
-    } else if (warp == 12) {
+    } else if (warp == MT_ISSUER_WARP) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            for (int t = 0; t < ntiles; ++t) {
-                const int s = t % MT_STAGES;
-                const uint32_t ph = (uint32_t)(t / MT_STAGES) & 1u;
-                const int b = t & 1;
-                const uint32_t bph = (uint32_t)(t >> 1) & 1u;
-                if (!mbar_wait(bar_tempty + 8 * b, bph ^ 1u)) { ok = false; break; }
-                if (!mbar_wait(bar_full + 8 * s, ph)) { ok = false; break; }
-                tc_fence_after();
-                const uint32_t sb = sbase + MT_SMEM_B + s * MT_B_BYTES;
+            int t = 0;
+            for (int set = blockIdx.z; set < nsets && ok; set += gridDim.z) {
+                const MatchSetRange rg = match_set_range(train_counts, set, nt, split, rows_per_split);
+                for (int i = 0; i < rg.ntiles; ++i, ++t) {
+                    const int s = t % MT_STAGES;
+                    const uint32_t ph = (uint32_t)(t / MT_STAGES) & 1u;
+                    const int b = t & 1;
+                    const uint32_t bph = (uint32_t)(t >> 1) & 1u;
+                    if (!mbar_wait(bar_tempty + 8 * b, bph ^ 1u)) { ok = false; break; }
+                    if (!mbar_wait(bar_full + 8 * s, ph)) { ok = false; break; }
+                    tc_fence_after();
+                    const uint32_t sb = sbase + MT_SMEM_B + s * MT_B_BYTES;
 #pragma unroll
-                for (int a = 0; a < 2; ++a) {
-                    const uint32_t sa = sbase + MT_SMEM_A + a * MT_A_BYTES;
-                    const uint32_t d = tmem_base + (uint32_t)((b * 2 + a) * MT_BN);
+                    for (int a = 0; a < 2; ++a) {
+                        const uint32_t d = tmem_base + (uint32_t)((b * 2 + a) * MT_BN);
+                        const uint32_t ta = tmem_base + MT_TMEM_A + (uint32_t)a * 64u;
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {          // K = 256 = 8 x UMMA_K(32 int8); 4 k-steps per 128-B swizzle atom
-                        const uint64_t da = umma_desc_sw128(sa + (ks >> 2) * (128 * 128) + (ks & 3) * 32);
-                        const uint64_t db = umma_desc_sw128(sb + (ks >> 2) * (MT_BN * 128) + (ks & 3) * 32);
-                        tc_mma_i8(d, da, db, MT_IDESC, ks > 0 ? 1u : 0u);
+                        for (int ks = 0; ks < 8; ++ks) {      // K = 256 = 8 x UMMA_K(32 int8): 8 TMEM columns of A, 4 k-steps per 128-B swizzle atom of B
+                            const uint64_t db = umma_desc_sw128(sb + (ks >> 2) * (MT_BN * 128) + (ks & 3) * 32);
+                            tc_mma_i8_ts(d, ta + (uint32_t)ks * 8u, db, MT_IDESC, ks > 0 ? 1u : 0u);
+                        }
                     }
+                    tc_commit(bar_empty + 8 * s);            // smem stage reusable once these MMAs retire
+                    tc_commit(bar_tfull + 8 * b);            // accumulators of this tile complete
                 }
-                tc_commit(bar_empty + 8 * s);                // smem stage reusable once these MMAs retire
-                tc_commit(bar_tfull + 8 * b);                // accumulators of this tile complete
             }
         }
         __syncwarp();
@@ -220,62 +283,66 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
         const int a = warp >> 2;                             // A tile
         const int qrow = q0 + a * 128 + (warp & 3) * 32 + lane;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        int m1 = INT_MIN, m2 = INT_MIN;
-        for (int t = 0; t < ntiles; ++t) {
-            const int b = t & 1;
-            const uint32_t bph = (uint32_t)(t >> 1) & 1u;
-            if (!mbar_wait(bar_tfull + 8 * b, bph)) { ok = false; break; }
-            tc_fence_after();
-            const int j0 = n0 + t * MT_BN;
-            const bool full = (j0 + MT_BN <= n1);
+        int t = 0;
+        for (int set = blockIdx.z; set < nsets && ok; set += gridDim.z) {
+            const MatchSetRange rg = match_set_range(train_counts, set, nt, split, rows_per_split);
+            int m1 = INT_MIN, m2 = INT_MIN;
+            for (int i = 0; i < rg.ntiles; ++i, ++t) {
+                const int b = t & 1;
+                const uint32_t bph = (uint32_t)(t >> 1) & 1u;
+                if (!mbar_wait(bar_tfull + 8 * b, bph)) { ok = false; break; }
+                tc_fence_after();
+                const int j0 = rg.n0 + i * MT_BN;
+                const bool full = (j0 + MT_BN <= rg.n1);
 #pragma unroll 1
-            for (int ch = 0; ch < MT_BN / 32; ++ch) {
-                uint32_t r[32];
-                tc_ld32(tmem_base + lane_base + (uint32_t)((b * 2 + a) * MT_BN + ch * 32), r);
-                tc_wait_ld();
-                const int cb = (MT_MAX_TRAIN - 1) - (j0 + ch * 32);
-                if (!KNN2) {
-                    int m = INT_MIN;
-                    if (full) {
+                for (int ch = 0; ch < MT_BN / 32; ++ch) {
+                    uint32_t r[32];
+                    tc_ld32(tmem_base + lane_base + (uint32_t)((b * 2 + a) * MT_BN + ch * 32), r);
+                    tc_wait_ld();
+                    const int cb = (MT_MAX_TRAIN - 1) - (j0 + ch * 32);
+                    if (!KNN2) {
+                        int m = INT_MIN;
+                        if (full) {
 #pragma unroll
-                        for (int c = 0; c < 32; c += 2)
-                            m = __vimax3_s32(m, (int)r[c] * (1 << MT_KEY_SHIFT) - c, (int)r[c + 1] * (1 << MT_KEY_SHIFT) - (c + 1));
+                            for (int c = 0; c < 32; c += 2)
+                                m = __vimax3_s32(m, (int)r[c] * (1 << MT_KEY_SHIFT) - c, (int)r[c + 1] * (1 << MT_KEY_SHIFT) - (c + 1));
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 32; ++c)
+                                if (j0 + ch * 32 + c < rg.n1) m = max(m, (int)r[c] * (1 << MT_KEY_SHIFT) - c);
+                        }
+                        if (m != INT_MIN) m1 = max(m1, m + cb);
                     } else {
 #pragma unroll
-                        for (int c = 0; c < 32; ++c)
-                            if (j0 + ch * 32 + c < n1) m = max(m, (int)r[c] * (1 << MT_KEY_SHIFT) - c);
-                    }
-                    if (m != INT_MIN) m1 = max(m1, m + cb);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        if (full || j0 + ch * 32 + c < n1) {
-                            const int k = (int)r[c] * (1 << MT_KEY_SHIFT) + (cb - c);
-                            m2 = max(m2, min(m1, k));
-                            m1 = max(m1, k);
+                        for (int c = 0; c < 32; ++c) {
+                            if (full || j0 + ch * 32 + c < rg.n1) {
+                                const int k = (int)r[c] * (1 << MT_KEY_SHIFT) + (cb - c);
+                                m2 = max(m2, min(m1, k));
+                                m1 = max(m1, k);
+                            }
                         }
                     }
                 }
+                tc_fence_before();
+                mbar_arrive(bar_tempty + 8 * b);
             }
-            tc_fence_before();
-            mbar_arrive(bar_tempty + 8 * b);
-        }
-        if (ok && qrow < nq) {
-            const size_t o = (size_t)set * nq + qrow;
-            if (keys) {
-                if (m1 != INT_MIN) atomicMax(&keys[o], m1);
-            } else if (m1 == INT_MIN) {                       // empty train set: no match (trainIdx -1)
-                best[o] = make_int4(qrow, -1, 0, 0);
-                if (KNN2) second[o] = make_int4(qrow, -1, 0, 0);
-            } else {
-                const int dot = m1 >> MT_KEY_SHIFT, j = (MT_MAX_TRAIN - 1) - (m1 & (MT_MAX_TRAIN - 1));
-                best[o] = make_int4(qrow, j, 0, __float_as_int((float)((256 - dot) >> 1)));
-                if (KNN2) {
-                    if (m2 != INT_MIN) {
-                        const int dot2 = m2 >> MT_KEY_SHIFT, j2 = (MT_MAX_TRAIN - 1) - (m2 & (MT_MAX_TRAIN - 1));
-                        second[o] = make_int4(qrow, j2, 0, __float_as_int((float)((256 - dot2) >> 1)));
-                    } else {
-                        second[o] = make_int4(qrow, -1, 0, 0);
+            if (ok && qrow < nq) {
+                const size_t o = (size_t)set * nq + qrow;
+                if (keys) {
+                    if (m1 != INT_MIN) atomicMax(&keys[o], m1);
+                } else if (m1 == INT_MIN) {                   // empty train set: no match (trainIdx -1)
+                    best[o] = make_int4(qrow, -1, 0, 0);
+                    if (KNN2) second[o] = make_int4(qrow, -1, 0, 0);
+                } else {
+                    const int dot = m1 >> MT_KEY_SHIFT, j = (MT_MAX_TRAIN - 1) - (m1 & (MT_MAX_TRAIN - 1));
+                    best[o] = make_int4(qrow, j, 0, __float_as_int((float)((256 - dot) >> 1)));
+                    if (KNN2) {
+                        if (m2 != INT_MIN) {
+                            const int dot2 = m2 >> MT_KEY_SHIFT, j2 = (MT_MAX_TRAIN - 1) - (m2 & (MT_MAX_TRAIN - 1));
+                            second[o] = make_int4(qrow, j2, 0, __float_as_int((float)((256 - dot2) >> 1)));
+                        } else {
+                            second[o] = make_int4(qrow, -1, 0, 0);
+                        }
                     }
                 }
             }
@@ -284,7 +351,7 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
     if (!ok) atomicOr(status, 2);
     tc_fence_before();
     __syncthreads();
-    if (warp == 12) {
+    if (warp == MT_ISSUER_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(MT_TMEM_COLS) : "memory");
     }
