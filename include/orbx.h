@@ -136,6 +136,8 @@ int orbx_debug_read_fast(orbx_ctx* ctx, int frame, int level, int32_t* x, int32_
 /* Average device time (ms) of each pipeline stage over the last extraction / match call, measured with CUDA
  * events on the context's stream; names[i] are static strings.  Returns the number of stages written. */
 int orbx_debug_stage_times(orbx_ctx* ctx, const char** names, float* ms, int cap);
+/* Matcher pipeline trace (only when the environment variable ORBX_MATCH_TRACE is set): 16 tiles x 16 SM-clock stamps. */
+int orbx_debug_match_trace(orbx_ctx* ctx, long long* out);
 /* Enable (1) / disable (0) per-stage CUDA-event timing (adds event records between kernels). */
 int orbx_set_profiling(orbx_ctx* ctx, int enable);
 

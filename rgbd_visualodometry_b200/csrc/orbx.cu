@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <new>
@@ -55,7 +56,7 @@ struct orbx_ctx {
     Buf pyr, blur, rowcnt, rowent, work, selpos, fincnt, status, tabs, pattern;
     Buf in, kps, desc, counts;               // host-path staging on the device
     int out_cap = 0;
-    Buf mq, mt, mbest, msecond, mkeys, mstatus, mcounts;
+    Buf mq, mt, mbest, msecond, mkeys, mstatus, mcounts, mtrace;
     int* h_small = nullptr;                  // pinned: counts[max_batch] + status[max_batch] + 1
     int last_batch = 0;
 
@@ -306,8 +307,10 @@ int run_match(orbx_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int n
         ++c->launches;
     }
     const dim3 grd((unsigned)tiles_m, (unsigned)nsplit, (unsigned)zgroups);
-    if (knn2) k_hamming_umma<true><<<grd, MT_THREADS, MT_SMEM_BYTES, c->stream>>>(d_q, nq, d_t, nt, stride_rows, d_counts, nsets, rows_per_split, d_best, d_second, keys, (int*)c->mstatus.p);
-    else      k_hamming_umma<false><<<grd, MT_THREADS, MT_SMEM_BYTES, c->stream>>>(d_q, nq, d_t, nt, stride_rows, d_counts, nsets, rows_per_split, d_best, d_second, keys, (int*)c->mstatus.p);
+    if (getenv("ORBX_MATCH_TRACE") && !c->mtrace.p) { if ((rc = ensure(c, c->mtrace, 16 * 16 * 8))) return rc; cudaMemset(c->mtrace.p, 0, 16 * 16 * 8); }
+    static const int dbg = getenv("ORBX_MATCH_DBG") ? atoi(getenv("ORBX_MATCH_DBG")) : 0;   // perf experiments only: skips a role's work (wrong results)
+    if (knn2) k_hamming_umma<true><<<grd, MT_THREADS, MT_SMEM_BYTES, c->stream>>>(d_q, nq, d_t, nt, stride_rows, d_counts, nsets, rows_per_split, d_best, d_second, keys, (int*)c->mstatus.p, dbg, (long long*)c->mtrace.p);
+    else      k_hamming_umma<false><<<grd, MT_THREADS, MT_SMEM_BYTES, c->stream>>>(d_q, nq, d_t, nt, stride_rows, d_counts, nsets, rows_per_split, d_best, d_second, keys, (int*)c->mstatus.p, dbg, (long long*)c->mtrace.p);
     ++c->launches;
     if (nsplit > 1) {
         k_match_finalize<<<(unsigned)((nout + 255) / 256), 256, 0, c->stream>>>(keys, nq, nout, d_best);
@@ -405,7 +408,7 @@ void orbx_destroy(orbx_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream2) cudaStreamSynchronize(c->stream2);
     Buf* bufs[] = {&c->pyr, &c->blur, &c->rowcnt, &c->rowent, &c->work, &c->selpos, &c->fincnt, &c->status, &c->tabs, &c->pattern, &c->in, &c->kps,
-                   &c->desc, &c->counts, &c->mq, &c->mt, &c->mbest, &c->msecond, &c->mkeys, &c->mstatus, &c->mcounts};
+                   &c->desc, &c->counts, &c->mq, &c->mt, &c->mbest, &c->msecond, &c->mkeys, &c->mstatus, &c->mcounts, &c->mtrace};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     if (c->h_small) cudaFreeHost(c->h_small);
     for (int i = 0; i < N_STAGES + 2; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -629,6 +632,13 @@ int orbx_set_profiling(orbx_ctx* c, int enable)
     c->profiling = enable != 0;
     for (int i = 0; i < N_STAGES; ++i) c->stage_valid[i] = false;
     return ORBX_OK;
+}
+
+int orbx_debug_match_trace(orbx_ctx* c, long long* out /*256*/)
+{
+    if (!c || !out || !c->mtrace.p) return ORBX_E_ARG;
+    cudaStreamSynchronize(c->stream);
+    return cudaMemcpy(out, c->mtrace.p, 16 * 16 * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? ORBX_OK : ORBX_E_CUDA;
 }
 
 int orbx_debug_stage_times(orbx_ctx* c, const char** names, float* ms, int cap)

@@ -12,12 +12,16 @@
 // ONCE per CTA and parked in TENSOR MEMORY (tcgen05.st; the MMA then takes A from TMEM, "TS" form), which removes
 // half of the shared-memory operand traffic of every MMA.  The CTA then walks train sets and, inside a set, tiles of
 // 96 train rows (B tiles).  Warp roles:
-//   warps 8-10  expanders : 32-byte descriptor rows -> +-1 int8 rows written straight into the 128B-swizzled K-major
+//   warps 8-13  expanders : (two threads per row) 32-byte descriptor rows -> +-1 int8 rows written straight into the 128B-swizzled K-major
 //                           UMMA layout; the bit expansion is pure ALU (multiply-spread), never touches HBM or a LUT
-//   warp  11    issuer    : one thread issues 2 x 8 tcgen05.mma.kind::i8 (M128 N96 K32, A from TMEM) per B tile into a
+//   warp  14    issuer    : one thread issues 2 x 8 tcgen05.mma.kind::i8 (M128 N96 K32, A from TMEM) per B tile into a
 //                           double-buffered pair of TMEM accumulators, commits to mbarriers
 //   warps 0-7   epilogue  : tcgen05.ld 32 lanes x 96 columns, pack key = dot << 20 | (0xFFFFF - j) so a single
 //                           integer max carries both the best distance and the lowest-index tie-break
+// Index tie-break folded into the GEMM: query bits expand to +-127, and one extra k-step multiplies a constant A
+// tile (a single 1 per row) with a constant B tile whose row jl holds (MT_BN-1 - jl).  The accumulator then reads
+// 127 * dot + (MT_BN-1 - jl): its plain integer maximum over a tile IS "largest dot, lowest train index", so the
+// epilogue is one VIMNMX3 per two columns instead of a multiply-and-pack per column.
 // TMEM map (512 columns): accumulators [buffer 0..1][A tile 0..1] x 96 columns at 0..383, A tiles 2 x 64 columns at 384.
 // Pipelines: smem stages (expanders <-> issuer) and TMEM accumulators (issuer <-> epilogue), all mbarrier based,
 // running continuously across set boundaries (persistent CTAs).  Train-row ranges can be split across CTAs (small
@@ -31,12 +35,23 @@ namespace orbx {
 constexpr int MT_QROWS = 256;          // query rows per CTA (two UMMA M=128 tiles)
 constexpr int MT_BN = 96;              // train rows per B tile (UMMA N)
 constexpr int MT_STAGES = 4;
-constexpr int MT_EXP_WARPS = MT_BN / 32;
-constexpr int MT_ISSUER_WARP = 8 + MT_EXP_WARPS;
-constexpr int MT_THREADS = (MT_ISSUER_WARP + 1) * 32;
+constexpr int MT_EXP_GROUPS = 2;                  // expander groups take alternate B tiles, so a group has two tile periods per tile
+constexpr int MT_EXP_WARPS = MT_EXP_GROUPS * MT_BN / 32;
+// Warp ids: the SM's warp arbiter favours HIGHER warp ids, so the latency-critical roles sit on top:
+//   0 .. 5 expanders (run ahead, not critical) | 6 idle | 7 .. 14 epilogue | 15 MMA issuer
+constexpr int MT_EPI_WARP0 = 7;
+constexpr int MT_ISSUER_WARP = 15;
+constexpr int MT_THREADS = 16 * 32;
+static_assert(MT_EXP_WARPS <= MT_EPI_WARP0, "role layout");
 constexpr int MT_B_BYTES = MT_BN * 256;
 constexpr int MT_SMEM_B = 0;
-constexpr int MT_SMEM_BAR = MT_SMEM_B + MT_STAGES * MT_B_BYTES;
+constexpr int MT_PREFETCH = 6;          // raw descriptor rows are fetched this many B tiles ahead (cp.async ring)
+constexpr int MT_SMEM_RAW = MT_SMEM_B + MT_STAGES * MT_B_BYTES;
+constexpr int MT_SMEM_CA = MT_SMEM_RAW + MT_EXP_GROUPS * MT_PREFETCH * MT_BN * 32;   // constant A tile of the bias k-step (128 rows x 128 B, SW128)
+constexpr int MT_SMEM_CB = MT_SMEM_CA + 128 * 128;                  // constant B tile of the bias k-step (MT_BN rows x 128 B, SW128)
+constexpr int MT_SMEM_BAR = MT_SMEM_CB + MT_BN * 128;
+constexpr int MT_ASCALE = 127;         // query bits expand to +-127, train bits to +-1: accumulator = 127 * dot + bias
+static_assert(MT_BN <= MT_ASCALE, "the per-tile index bias must stay below the dot-product quantum");
 constexpr int MT_SMEM_BYTES = MT_SMEM_BAR + 128 + 1024;   // + barriers/tmem slot + 1 KB alignment slack
 constexpr uint32_t MT_TMEM_COLS = 512;
 constexpr uint32_t MT_TMEM_A = 4 * MT_BN;                  // first column of the A tiles
@@ -67,6 +82,18 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
             else if (t - t0 > 250000000ull) return false;
         }
     }
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// single non-blocking probe of an mbarrier phase
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -122,6 +149,10 @@ __device__ __forceinline__ uint32_t pm1x4(uint32_t nibble) {
     const uint32_t spread = (nibble * 0x00204081u) & 0x01010101u;
     return 0xFFFFFFFFu - spread * 0xFEu;
 }
+__device__ __forceinline__ uint32_t pm127x4(uint32_t nibble) {          // +127 for a set bit, -127 otherwise
+    const uint32_t spread = (nibble * 0x00204081u) & 0x01010101u;
+    return 0x81818181u ^ (spread * 0xFEu);
+}
 // word i (0..63) of the expanded row = int8 values of descriptor bits 4i .. 4i+3
 __device__ __forceinline__ uint32_t pm1_word(const uint32_t* w, int i) { return pm1x4((w[i >> 3] >> ((i & 7) * 4)) & 15u); }
 
@@ -135,6 +166,19 @@ __device__ __forceinline__ void expand_row(uint8_t* tile, int rows, int r, const
     for (int c16 = 0; c16 < 16; ++c16) {                     // 16 descriptor bits -> 16 int8 -> one 16-byte chunk
         uint8_t* dst = rbase + (c16 >> 3) * rows * 128 + (((c16 & 7) ^ (r & 7)) << 4);
         *reinterpret_cast<uint4*>(dst) = make_uint4(pm1_word(w, 4 * c16), pm1_word(w, 4 * c16 + 1), pm1_word(w, 4 * c16 + 2), pm1_word(w, 4 * c16 + 3));
+    }
+}
+
+// One K half (descriptor bytes 16h .. 16h+15 -> int8 columns 128h .. 128h+127) of row r.
+__device__ __forceinline__ void expand_half_row(uint8_t* tile, int rows, int r, int h, const uint4 v)
+{
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint8_t* rbase = tile + h * rows * 128 + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {                            // 16 descriptor bits -> 16 int8 -> one 16-byte chunk
+        const uint32_t two = w[c >> 1] >> ((c & 1) * 16);
+        *reinterpret_cast<uint4*>(rbase + ((c ^ (r & 7)) << 4)) =
+            make_uint4(pm1x4(two & 15u), pm1x4((two >> 4) & 15u), pm1x4((two >> 8) & 15u), pm1x4((two >> 12) & 15u));
     }
 }
 
@@ -159,7 +203,7 @@ template <bool KNN2>
 __global__ void __launch_bounds__(MT_THREADS, 1)
 k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restrict__ train, int nt, int train_stride_rows,
                const int* __restrict__ train_counts, int nsets, int rows_per_split, int4* __restrict__ best,
-               int4* __restrict__ second, int* __restrict__ keys, int* __restrict__ status)
+               int4* __restrict__ second, int* __restrict__ keys, int* __restrict__ status, int dbg, long long* __restrict__ trace)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -174,113 +218,170 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
 
     // ---- setup: barriers, TMEM, A tiles (expanded in registers and parked in tensor memory)
     if (tid == 0) {
-        for (int s = 0; s < MT_STAGES; ++s) { mbar_init(bar_full + 8 * s, MT_BN); mbar_init(bar_empty + 8 * s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 256); }
+        for (int s = 0; s < MT_STAGES; ++s) { mbar_init(bar_full + 8 * s, MT_BN / 32); mbar_init(bar_empty + 8 * s, 1); }   // one arrive per warp:
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 8); }             // same-address arrives serialise
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MT_ISSUER_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(MT_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    for (int i = tid; i < (128 * 128 + MT_BN * 128) / 16; i += MT_THREADS) reinterpret_cast<uint4*>(smem + MT_SMEM_CA)[i] = make_uint4(0, 0, 0, 0);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // bias k-step operands: logical byte k = 0 of row r sits at (r / 8) * 1024 + (r % 8) * 128 + ((0 ^ (r % 8)) << 4)
+    if (tid < 128) smem[MT_SMEM_CA + (tid >> 3) * 1024 + (tid & 7) * 128 + ((tid & 7) << 4)] = 1;
+    else if (tid < 128 + MT_BN) {
+        const int jl = tid - 128;
+        smem[MT_SMEM_CB + (jl >> 3) * 1024 + (jl & 7) * 128 + ((jl & 7) << 4)] = (uint8_t)(MT_BN - 1 - jl);
+    }
     const uint32_t tmem_base = *tmem_slot;
     bool ok = true;
-    if (warp < 8) {                                          // thread <-> query row <-> TMEM lane (same mapping as the epilogue)
-        const int q = q0 + (warp >> 2) * 128 + (warp & 3) * 32 + lane;
+    if (warp >= MT_EPI_WARP0 && warp < MT_EPI_WARP0 + 8) {   // thread <-> query row <-> TMEM lane (same mapping as the epilogue)
+        const int q = q0 + ((warp - MT_EPI_WARP0) >> 2) * 128 + (warp & 3) * 32 + lane;
         uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
         if (q < nq) {
             const uint4* p = reinterpret_cast<const uint4*>(query + (size_t)q * 32);
             lo = __ldg(p); hi = __ldg(p + 1);
         }
         const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-        const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + MT_TMEM_A + (uint32_t)(warp >> 2) * 64u;
+        const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + MT_TMEM_A + (uint32_t)((warp - MT_EPI_WARP0) >> 2) * 64u;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {               // 64 columns = K 256 int8, four per 32-bit column
             uint32_t r[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = pm1_word(w, half * 32 + i);
+            for (int i = 0; i < 32; ++i) r[i] = pm127x4((w[(half * 32 + i) >> 3] >> (((half * 32 + i) & 7) * 4)) & 15u);
             tc_st32(ta + half * 32, r);
         }
         tc_wait_st();
     }
+    fence_proxy_async_smem();                                // constant bias tiles (generic-proxy stores) -> visible to the tensor core
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
 
-    if (warp >= 8 && warp < MT_ISSUER_WARP) {
-        // ================= expanders: one B-tile row per thread, next tile's row prefetched into registers =================
-        const int r = tid - 256;                             // 0 .. MT_BN-1
-        int set = blockIdx.z, i = 0, t = 0;
-        MatchSetRange rg = {0, 0, 0};
-        if (set < nsets) rg = match_set_range(train_counts, set, nt, split, rows_per_split);
-        // make (set, i) name an existing tile, skipping empty sets; false when this CTA's work is exhausted
-        auto seek = [&]() -> bool {
-            while (set < nsets && i >= rg.ntiles) {
-                set += gridDim.z; i = 0;
-                if (set < nsets) rg = match_set_range(train_counts, set, nt, split, rows_per_split);
-            }
-            return set < nsets;
+    if (warp < MT_EXP_WARPS) {
+        // ================= expanders: one B-tile row per thread; raw rows arrive through a cp.async ring
+        //                   MT_PREFETCH tiles ahead, so global-load latency never sits on the pipeline's critical path
+        const int grp = tid / MT_BN, r = tid - grp * MT_BN;   // expander group and B-tile row of this thread
+        struct TileIter {
+            int set, i; MatchSetRange rg;
         };
-        auto load_row = [&](uint4& lo, uint4& hi) {
-            const int j = rg.n0 + i * MT_BN + r;
-            lo = make_uint4(0, 0, 0, 0); hi = lo;
-            if (j < rg.n1) {
-                const uint4* p = reinterpret_cast<const uint4*>(train + ((size_t)set * train_stride_rows + j) * 32);
-                lo = __ldg(p); hi = __ldg(p + 1);
+        auto seek = [&](TileIter& it) -> bool {              // make (set, i) name an existing tile, skipping empty sets
+            while (it.set < nsets && it.i >= it.rg.ntiles) {
+                it.set += gridDim.z; it.i = 0;
+                if (it.set < nsets) it.rg = match_set_range(train_counts, it.set, nt, split, rows_per_split);
             }
+            return it.set < nsets;
         };
-        uint4 lo, hi;
-        bool have = seek();
-        if (have) load_row(lo, hi);
-        while (have) {
-            const uint4 clo = lo, chi = hi;
-            ++i;
-            have = seek();
-            if (have) load_row(lo, hi);                      // in flight while this tile is expanded
+        auto step = [&](TileIter& it) -> bool { if (it.set < nsets) ++it.i; return seek(it); };
+        TileIter cur = {(int)blockIdx.z, 0, {0, 0, 0}};
+        if (cur.set < nsets) cur.rg = match_set_range(train_counts, cur.set, nt, split, rows_per_split);
+        seek(cur);
+        for (int k = 0; k < grp; ++k) step(cur);             // group g owns tiles g, g + GROUPS, g + 2 GROUPS, ...
+        TileIter ahead = cur;
+        uint8_t* raw = smem + MT_SMEM_RAW + (grp * MT_PREFETCH * MT_BN + r) * 32;
+        auto fetch = [&](int slot) {                         // raw row of the tile `ahead` names -> ring slot (own row only)
+            uint8_t* dst = raw + slot * (MT_BN * 32);
+            if (ahead.set < nsets) {
+                const int j = ahead.rg.n0 + ahead.i * MT_BN + r;
+                if (j < ahead.rg.n1) {
+                    const uint8_t* src = train + ((size_t)ahead.set * train_stride_rows + j) * 32;
+                    const uint32_t d = smem_u32(dst);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16), "l"(src + 16) : "memory");
+                } else {
+                    reinterpret_cast<uint4*>(dst)[0] = make_uint4(0, 0, 0, 0);
+                    reinterpret_cast<uint4*>(dst)[1] = make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll 1
+                for (int k = 0; k < MT_EXP_GROUPS; ++k) step(ahead);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");   // one group per tile slot, empty or not
+        };
+#pragma unroll 1
+        for (int k = 0; k < MT_PREFETCH; ++k) fetch(k);
+        int t = grp, n = 0;                                  // global tile number (pipeline stage / phase), own tile count (ring slot)
+        while (cur.set < nsets) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(MT_PREFETCH - 1) : "memory");
+            const int slot = n % MT_PREFETCH;
+            const uint4 clo = reinterpret_cast<const uint4*>(raw + slot * (MT_BN * 32))[0];
+            const uint4 chi = reinterpret_cast<const uint4*>(raw + slot * (MT_BN * 32))[1];
+            fetch(slot);                                     // refill the slot just consumed
             const int s = t % MT_STAGES;
             const uint32_t ph = (uint32_t)(t / MT_STAGES) & 1u;
+            const bool tr_on = trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && t >= 40 && t < 56 && r == 0;
+            if (tr_on) trace[(t - 40) * 16 + 8] = clock64();
             if (!mbar_wait(bar_empty + 8 * s, ph ^ 1u)) { ok = false; break; }
-            expand_row(smem + MT_SMEM_B + s * MT_B_BYTES, MT_BN, r, clo, chi);
-            fence_proxy_async_smem();
-            mbar_arrive(bar_full + 8 * s);
-            ++t;
+            if (tr_on) trace[(t - 40) * 16 + 9] = clock64();
+            if (!(dbg & 4)) expand_row(smem + MT_SMEM_B + s * MT_B_BYTES, MT_BN, r, clo, chi);
+            fence_proxy_async_smem();                        // every writer fences, then one lane arrives for the warp
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full + 8 * s);
+            if (tr_on) trace[(t - 40) * 16 + 10] = clock64();
+#pragma unroll 1
+            for (int k = 0; k < MT_EXP_GROUPS; ++k) step(cur);
+            t += MT_EXP_GROUPS;
+            ++n;
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else if (warp == MT_ISSUER_WARP) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            int t = 0;
-            for (int set = blockIdx.z; set < nsets && ok; set += gridDim.z) {
-                const MatchSetRange rg = match_set_range(train_counts, set, nt, split, rows_per_split);
-                for (int i = 0; i < rg.ntiles; ++i, ++t) {
-                    const int s = t % MT_STAGES;
-                    const uint32_t ph = (uint32_t)(t / MT_STAGES) & 1u;
-                    const int b = t & 1;
-                    const uint32_t bph = (uint32_t)(t >> 1) & 1u;
+        // The whole warp runs the loop so that every operand is computed in warp-uniform code (uniform registers, no
+        // per-instruction ELECT / R2UR waterfall); one elected lane issues the tcgen05 instructions.
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t sbu = __shfl_sync(0xffffffffu, sbase, 0);
+        const uint64_t dca = umma_desc_sw128(sbu + MT_SMEM_CA), dcb = umma_desc_sw128(sbu + MT_SMEM_CB);
+        int t = 0;
+        bool ready_next = false;                             // barriers of tile t already observed complete (probed mid-tile)
+        for (int set = blockIdx.z; set < nsets && ok; set += gridDim.z) {
+            const MatchSetRange rg = match_set_range(train_counts, set, nt, split, rows_per_split);
+            for (int i = 0; i < rg.ntiles; ++i, ++t) {
+                const int s = t % MT_STAGES;
+                const uint32_t ph = (uint32_t)(t / MT_STAGES) & 1u;
+                const int b = t & 1;
+                const uint32_t bph = (uint32_t)(t >> 1) & 1u;
+                const bool tr_on = trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && t >= 40 && t < 56 && lane == 0;
+                if (tr_on) trace[(t - 40) * 16 + 0] = clock64();
+                if (!ready_next) {
                     if (!mbar_wait(bar_tempty + 8 * b, bph ^ 1u)) { ok = false; break; }
+                    if (tr_on) trace[(t - 40) * 16 + 1] = clock64();
                     if (!mbar_wait(bar_full + 8 * s, ph)) { ok = false; break; }
-                    tc_fence_after();
-                    const uint32_t sb = sbase + MT_SMEM_B + s * MT_B_BYTES;
+                }
+                if (tr_on) trace[(t - 40) * 16 + 2] = clock64();
+                tc_fence_after();
+                const uint32_t sb = sbu + MT_SMEM_B + s * MT_B_BYTES;
+                const uint64_t db0 = umma_desc_sw128(sb);
+                // barriers of the NEXT tile (same pipelines, consecutive tile numbers even across set boundaries)
+                const int s1 = (t + 1) % MT_STAGES, b1 = (t + 1) & 1;
+                const uint32_t ph1 = (uint32_t)((t + 1) / MT_STAGES) & 1u, bph1 = (uint32_t)((t + 1) >> 1) & 1u;
 #pragma unroll
-                    for (int a = 0; a < 2; ++a) {
-                        const uint32_t d = tmem_base + (uint32_t)((b * 2 + a) * MT_BN);
-                        const uint32_t ta = tmem_base + MT_TMEM_A + (uint32_t)a * 64u;
+                for (int a = 0; a < 2; ++a) {
+                    if (elect_one() && !(dbg & 2)) {
+                        const uint32_t d = tb + (uint32_t)((b * 2 + a) * MT_BN);
+                        const uint32_t ta = tb + MT_TMEM_A + (uint32_t)a * 64u;
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks) {      // K = 256 = 8 x UMMA_K(32 int8): 8 TMEM columns of A, 4 k-steps per 128-B swizzle atom of B
-                            const uint64_t db = umma_desc_sw128(sb + (ks >> 2) * (MT_BN * 128) + (ks & 3) * 32);
+                            const uint64_t db = db0 + (uint64_t)(((ks >> 2) * (MT_BN * 128) + (ks & 3) * 32) >> 4);   // start-address field, 16-byte units
                             tc_mma_i8_ts(d, ta + (uint32_t)ks * 8u, db, MT_IDESC, ks > 0 ? 1u : 0u);
                         }
+                        tc_mma_i8(d, dca, dcb, MT_IDESC, 1u);  // bias k-step: + (MT_BN-1 - jl) in every row
                     }
+                    // while the queued MMAs execute, probe the next tile's barriers so its issue can start without a wait
+                    if (a == 0) ready_next = mbar_test(bar_tempty + 8 * b1, bph1 ^ 1u) && mbar_test(bar_full + 8 * s1, ph1);
+                }
+                if (elect_one()) {
                     tc_commit(bar_empty + 8 * s);            // smem stage reusable once these MMAs retire
                     tc_commit(bar_tfull + 8 * b);            // accumulators of this tile complete
                 }
+                __syncwarp();
+                if (tr_on) trace[(t - 40) * 16 + 3] = clock64();
             }
         }
-        __syncwarp();
-    } else {
-        // ================= epilogue (warps 0-7) =================
-        const int a = warp >> 2;                             // A tile
+    } else if (warp >= MT_EPI_WARP0 && warp < MT_EPI_WARP0 + 8) {
+        // ================= epilogue =================
+        const int a = (warp - MT_EPI_WARP0) >> 2;            // A tile; the TMEM lane quarter is fixed by hardware to warp % 4
         const int qrow = q0 + a * 128 + (warp & 3) * 32 + lane;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         int t = 0;
@@ -290,41 +391,65 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
             for (int i = 0; i < rg.ntiles; ++i, ++t) {
                 const int b = t & 1;
                 const uint32_t bph = (uint32_t)(t >> 1) & 1u;
+                const bool tr_on = trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && t >= 40 && t < 56 && warp == MT_EPI_WARP0 + 1 && lane == 0;
+                if (tr_on) trace[(t - 40) * 16 + 4] = clock64();
                 if (!mbar_wait(bar_tfull + 8 * b, bph)) { ok = false; break; }
+                if (tr_on) trace[(t - 40) * 16 + 5] = clock64();
                 tc_fence_after();
                 const int j0 = rg.n0 + i * MT_BN;
                 const bool full = (j0 + MT_BN <= rg.n1);
-#pragma unroll 1
-                for (int ch = 0; ch < MT_BN / 32; ++ch) {
-                    uint32_t r[32];
-                    tc_ld32(tmem_base + lane_base + (uint32_t)((b * 2 + a) * MT_BN + ch * 32), r);
+                constexpr int NCH = MT_BN / 32;
+                uint32_t r[NCH][32];
+                if (!(dbg & 1)) {
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch) tc_ld32(tmem_base + lane_base + (uint32_t)((b * 2 + a) * MT_BN + ch * 32), r[ch]);
                     tc_wait_ld();
-                    const int cb = (MT_MAX_TRAIN - 1) - (j0 + ch * 32);
-                    if (!KNN2) {
-                        int m = INT_MIN;
-                        if (full) {
+                    if (tr_on) trace[(t - 40) * 16 + 6] = clock64();
+                    // accumulator = 127 * dot + (MT_BN-1 - jl): the raw integer maximum is (largest dot, lowest index)
+                    int k1 = INT_MIN, k2 = INT_MIN;
+                    if (!KNN2 && full) {
+                        int p[8];                                // eight independent max chains (ILP), then a short tree
 #pragma unroll
-                            for (int c = 0; c < 32; c += 2)
-                                m = __vimax3_s32(m, (int)r[c] * (1 << MT_KEY_SHIFT) - c, (int)r[c + 1] * (1 << MT_KEY_SHIFT) - (c + 1));
-                        } else {
+                        for (int u = 0; u < 8; ++u) p[u] = __vimax3_s32((int)r[0][u * 4], (int)r[0][u * 4 + 1], max((int)r[0][u * 4 + 2], (int)r[0][u * 4 + 3]));
 #pragma unroll
-                            for (int c = 0; c < 32; ++c)
-                                if (j0 + ch * 32 + c < rg.n1) m = max(m, (int)r[c] * (1 << MT_KEY_SHIFT) - c);
-                        }
-                        if (m != INT_MIN) m1 = max(m1, m + cb);
+                        for (int ch = 1; ch < NCH; ++ch)
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) {
+                                p[u] = __vimax3_s32(p[u], (int)r[ch][u * 4], (int)r[ch][u * 4 + 1]);
+                                p[u] = __vimax3_s32(p[u], (int)r[ch][u * 4 + 2], (int)r[ch][u * 4 + 3]);
+                            }
+                        k1 = __vimax3_s32(__vimax3_s32(p[0], p[1], p[2]), __vimax3_s32(p[3], p[4], p[5]), max(p[6], p[7]));
                     } else {
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            if (full || j0 + ch * 32 + c < rg.n1) {
-                                const int k = (int)r[c] * (1 << MT_KEY_SHIFT) + (cb - c);
-                                m2 = max(m2, min(m1, k));
-                                m1 = max(m1, k);
-                            }
+                        for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+                            for (int c = 0; c < 32; ++c)
+                                if (full || j0 + ch * 32 + c < rg.n1) {
+                                    const int k = (int)r[ch][c];
+                                    if (KNN2) k2 = max(k2, min(k1, k));
+                                    k1 = max(k1, k);
+                                }
+                    }
+                    // decode the tile winner(s) into the global key  dot << 20 | (0xFFFFF - j)
+#pragma unroll
+                    for (int w = 0; w < (KNN2 ? 2 : 1); ++w) {
+                        const int k = w == 0 ? k1 : k2;
+                        if (k != INT_MIN) {
+                            const unsigned kk = (unsigned)(k + MT_ASCALE * 256);
+                            const unsigned q = kk / (unsigned)MT_ASCALE;          // dot + 256
+                            const int jl = (MT_BN - 1) - (int)(kk - q * (unsigned)MT_ASCALE);
+                            const int gk = ((int)q - 256) * (1 << MT_KEY_SHIFT) + ((MT_MAX_TRAIN - 1) - (j0 + jl));
+                            if (KNN2) m2 = max(m2, min(m1, gk));
+                            m1 = max(m1, gk);
                         }
                     }
                 }
+                if (tr_on) trace[(t - 40) * 16 + 11] = clock64() + (m1 & 1);
                 tc_fence_before();
-                mbar_arrive(bar_tempty + 8 * b);
+                if (tr_on) trace[(t - 40) * 16 + 12] = clock64();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+                if (tr_on) trace[(t - 40) * 16 + 7] = clock64();
             }
             if (ok && qrow < nq) {
                 const size_t o = (size_t)set * nq + qrow;
