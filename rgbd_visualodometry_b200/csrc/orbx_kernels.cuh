@@ -148,14 +148,16 @@ __global__ void __launch_bounds__(128) k_pyr_down(const __grid_constant__ Geom g
 // columns, so every row's survivors come out in x order and the per-row lists concatenate to OpenCV's raster order.
 // Only the region that can survive the 31-px border filter is evaluated.
 //
-// Per chunk (score tile = (R+2) rows x 256 columns, x = ox0-4 .. ox0+251):
+// Per chunk (score tile = (R+2) rows x 256 columns, x = ox0-4 .. ox0+251), four block barriers:
 //   load      (R+8) x 288 pixels widened to u16 into smem with 128-bit global loads (16-byte aligned tile origin)
-//   phase A   every pixel QUAD: 4-compass-point rejection test in u16x2 SIMD (native VIMNMX.U16x2) from five
-//             64-bit shared loads; the pass bits leave as warp ballots; a block scan turns them into a queue
-//   phase B   queued pixels: full 16-point test.  Each circle pixel is packed (p | (255-p) << 16) so ONE sliding
-//             max over the 16 nine-long arcs (VIMNMX3.U16x2) yields both min-of-max(p) and max-of-min(p):
-//             A = v - min_arcs max p,  -B = max_arcs min p - v,  score = max(A, -B) - 1  (corner iff > t)
-//   phase C   3x3 NMS (strict >) of the corners on the smem score tile -> per-row bit masks
+//   phase A   per WARP, on its own (row, 128-pixel half) items: 4-compass-point rejection test of every pixel quad in
+//             u16x2 SIMD (native VIMNMX.U16x2) from five 64-bit shared loads; survivors are appended to the warp's
+//             private queue straight from the ballots (no atomics, no block scan, no barrier)
+//   phase B   the same warp runs the full 16-point test on its queue.  Each circle pixel is packed
+//             (p | (255-p) << 16) so ONE sliding max over the 16 nine-long arcs (VIMNMX3.U16x2) yields both
+//             min-of-max(p) and max-of-min(p):  A = v - min_arcs max p,  -B = max_arcs min p - v,
+//             score = max(A, -B) - 1 (corner iff > t).  Corners inside the output region go to a private NMS queue.
+//   phase C   3x3 NMS (strict >) of the queued corners on the shared score tile -> per-row bit masks
 //   phase D   ordered extraction of the bit masks (popc prefix) -> global per-row lists
 template <int R, int NT>
 __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr,
@@ -168,23 +170,21 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
     constexpr int TPW = TP / 2;            // ... in 32-bit words
     constexpr int TR = R + 8;              // image tile rows
     constexpr int MW = 8;                  // mask words per row (248 bits used)
-    constexpr int NPW = SR * 8;            // pass-bit words: [row][128-pixel block][pixel-in-quad]
     constexpr int T = ORBX_FAST_T;
     constexpr int NWARP = NT / 32;
-    static_assert(NT == 256, "phase A maps 64 quad columns x 4 row groups onto 256 threads");
-    static_assert(R * MW <= NT && NPW <= NT, "one thread per mask / pass word");
+    constexpr int ITEMS = (2 * SR + NWARP - 1) / NWARP;   // (row, half) items per warp
+    constexpr int QCAP = ITEMS * 128;      // private queue capacity: every pixel of the warp's items
+    static_assert(R * MW <= NT, "phase D needs one thread per mask word");
 
     __shared__ __align__(16) uint16_t s_img[TR * TP];
     __shared__ __align__(16) uint8_t s_score[SR * SP];
-    __shared__ uint16_t s_q[SR * SP];      // pass queue: sy << 8 | sx
-    __shared__ uint16_t s_cq[R * SP];      // corner queue (NMS candidates inside the output region; <= R x 248)
-    __shared__ __align__(16) uint32_t s_pass[NPW];
+    __shared__ uint16_t s_q[NWARP][QCAP];  // pass queues:   sy << 8 | sx
+    __shared__ uint16_t s_cq[NWARP][QCAP]; // corner queues (NMS candidates inside the output region)
     __shared__ uint32_t s_mask[R * MW];
     __shared__ uint32_t s_rowcnt[R];
-    __shared__ int s_wsum[NWARP];
-    __shared__ int s_qn, s_cn;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const unsigned lt = lanemask_lt();
     const int f = blockIdx.y;
     int l = 0;
 #pragma unroll 1
@@ -201,6 +201,8 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
     uint32_t* ent_out = rowent + (size_t)f * g.ent_frame + L.ent_off;
 
     if (tid < R) s_rowcnt[tid] = 0;
+    uint16_t* myq = s_q[wid];
+    uint16_t* mycq = s_cq[wid];
 
     for (int ox0 = 28; ox0 < xend; ox0 += CWO) {
         const int ox1 = min(ox0 + CWO, xend);
@@ -225,97 +227,86 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
             }
             for (int i = tid; i < SR * SP / 16; i += NT) reinterpret_cast<uint4*>(s_score)[i] = make_uint4(0, 0, 0, 0);
             if (tid < R * MW) s_mask[tid] = 0;
-            if (tid == 0) s_cn = 0;
         }
         __syncthreads();
-        // ---- phase A: compass rejection; thread = quad column (tid & 63), rows tid >> 6, +4, ...
+        // ---- phase A (per warp): compass rejection on (row, 128-pixel half) items -> private queue
+        int qn = 0;
         {
             constexpr unsigned K = ((511u - T) << 16) | (511u - T);
-            const int q = tid & 63, wc = (tid >> 5) & 1, rg = tid >> 6;
-            const bool warp_on = wc * 128 < need;           // warp-uniform: this 128-pixel block holds needed pixels
-            const bool col_on = 4 * q < need;
-            // 8-byte aligned: word index (sy+3)*TPW + 2q + 2 + xo/2 is even (TPW, xo/2 even)
-            const uint2* wp = reinterpret_cast<const uint2*>(reinterpret_cast<const uint32_t*>(s_img) + (rg + 3) * TPW + 2 * q + 2 + (xo >> 1));
-            uint4* pp = reinterpret_cast<uint4*>(s_pass) + rg * 2 + wc;
-            if (warp_on) {
-                for (int sy = rg; sy < nsr; sy += 4, wp += 2 * TPW, pp += 8) {
-                    unsigned m0 = 0, m1 = 0;
-                    if (col_on) {
-                        const uint2 c = wp[0], n = wp[-3 * (TPW / 2)], s = wp[3 * (TPW / 2)], e2 = wp[1], w2 = wp[-1];
-                        const unsigned e0 = __byte_perm(c.y, e2.x, 0x5432), e1 = __byte_perm(e2.x, e2.y, 0x5432);
-                        const unsigned w0 = __byte_perm(w2.x, w2.y, 0x5432), w1 = __byte_perm(w2.y, c.x, 0x5432);
-                        const unsigned D0 = vmax2(vmin2(n.x, s.x), vmin2(e0, w0)), B0 = vmin2(vmax2(n.x, s.x), vmax2(e0, w0));
-                        const unsigned D1 = vmax2(vmin2(n.y, s.y), vmin2(e1, w1)), B1 = vmin2(vmax2(n.y, s.y), vmax2(e1, w1));
-                        m0 = (c.x + K - D0) | (B0 + K - c.x);
-                        m1 = (c.y + K - D1) | (B1 + K - c.y);
-                    }
-                    const unsigned b0 = __ballot_sync(0xffffffffu, m0 & 0x200u), b1 = __ballot_sync(0xffffffffu, m0 & 0x02000000u);
-                    const unsigned b2 = __ballot_sync(0xffffffffu, m1 & 0x200u), b3 = __ballot_sync(0xffffffffu, m1 & 0x02000000u);
-                    if (lane == 0) *pp = make_uint4(b0, b1, b2, b3);
+            for (int item = wid; item < 2 * nsr; item += NWARP) {
+                const int sy = item >> 1, half = item & 1;
+                if (half * 128 >= need) continue;            // warp-uniform: no needed pixel in this half
+                const int q = half * 32 + lane;              // quad column
+                unsigned m0 = 0, m1 = 0;
+                if (4 * q < need) {
+                    // 8-byte aligned: word index (sy+3)*TPW + 2q + 2 + xo/2 is even (TPW, xo/2 even)
+                    const uint2* wp = reinterpret_cast<const uint2*>(reinterpret_cast<const uint32_t*>(s_img) + (sy + 3) * TPW + 2 * q + 2 + (xo >> 1));
+                    const uint2 c = wp[0], n = wp[-3 * (TPW / 2)], s = wp[3 * (TPW / 2)], e2 = wp[1], w2 = wp[-1];
+                    const unsigned e0 = __byte_perm(c.y, e2.x, 0x5432), e1 = __byte_perm(e2.x, e2.y, 0x5432);
+                    const unsigned w0 = __byte_perm(w2.x, w2.y, 0x5432), w1 = __byte_perm(w2.y, c.x, 0x5432);
+                    const unsigned D0 = vmax2(vmin2(n.x, s.x), vmin2(e0, w0)), B0 = vmin2(vmax2(n.x, s.x), vmax2(e0, w0));
+                    const unsigned D1 = vmax2(vmin2(n.y, s.y), vmin2(e1, w1)), B1 = vmin2(vmax2(n.y, s.y), vmax2(e1, w1));
+                    m0 = (c.x + K - D0) | (B0 + K - c.x);
+                    m1 = (c.y + K - D1) | (B1 + K - c.y);
                 }
-            } else if (lane == 0) {
-                for (int sy = rg; sy < nsr; sy += 4, pp += 8) *pp = make_uint4(0u, 0u, 0u, 0u);
+                const unsigned ent = (unsigned)(sy << 8) | (unsigned)(4 * q);
+                const bool p0 = m0 & 0x200u, p1 = m0 & 0x02000000u, p2 = m1 & 0x200u, p3 = m1 & 0x02000000u;
+                const unsigned b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
+                const unsigned b2 = __ballot_sync(0xffffffffu, p2), b3 = __ballot_sync(0xffffffffu, p3);
+                if (p0) myq[qn + __popc(b0 & lt)] = (uint16_t)ent;
+                qn += __popc(b0);
+                if (p1) myq[qn + __popc(b1 & lt)] = (uint16_t)(ent + 1);
+                qn += __popc(b1);
+                if (p2) myq[qn + __popc(b2 & lt)] = (uint16_t)(ent + 2);
+                qn += __popc(b2);
+                if (p3) myq[qn + __popc(b3 & lt)] = (uint16_t)(ent + 3);
+                qn += __popc(b3);
             }
         }
-        __syncthreads();
-        // ---- pass bits -> queue (block scan of the popcounts, then every word owner expands its bits)
-        {
-            const int nw = nsr * 8;
-            unsigned bits = tid < nw ? s_pass[tid] : 0u;
-            const int cnt = __popc(bits);
-            int inc = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
-            if (lane == 31) s_wsum[wid] = inc;
-            __syncthreads();
-            int off = inc - cnt, tot = 0;
-#pragma unroll
-            for (int i = 0; i < NWARP; ++i) { const int s = s_wsum[i]; if (i < wid) off += s; tot += s; }
-            if (tid == 0) s_qn = tot;
-            const int sy = tid >> 3, base = ((tid >> 2) & 1) * 128 + (tid & 3);      // word = (sy*2 + wc)*4 + j; bit L <-> sx = (wc*32 + L)*4 + j
-            while (bits) {
-                const int b = __ffs(bits) - 1;
-                bits &= bits - 1;
-                s_q[off++] = (uint16_t)((sy << 8) | (base + b * 4));
-            }
-        }
-        __syncthreads();
-        const int qn = s_qn;
-        // ---- phase B: full segment test + score on the queued pixels; corners inside the output region are queued for NMS
-        for (int i = tid; i < qn; i += NT) {
-            const int e = s_q[i];
-            const int sy = e >> 8, sx = e & 255;
-            const uint16_t* c = &s_img[(sy + 3) * TP + sx + 4 + xo];
-            const int v = c[0];
-            unsigned q[16];
+        __syncwarp();
+        // ---- phase B (same warp): full segment test + score; corners inside the output region -> private NMS queue
+        int cn = 0;
+        for (int i0 = 0; i0 < qn; i0 += 32) {
+            const int i = i0 + lane;
+            bool corner = false;
+            int e = 0;
+            if (i < qn) {
+                e = myq[i];
+                const int sy = e >> 8, sx = e & 255;
+                const uint16_t* c = &s_img[(sy + 3) * TP + sx + 4 + xo];
+                const int v = c[0];
+                unsigned q[16];
 #define ORBX_PK(k, dx, dy) q[k] = (unsigned)c[(dy) * TP + (dx)] * 0xFFFF0001u + 0x00FF0000u
-            ORBX_PK(0, 0, 3);   ORBX_PK(1, 1, 3);   ORBX_PK(2, 2, 2);    ORBX_PK(3, 3, 1);
-            ORBX_PK(4, 3, 0);   ORBX_PK(5, 3, -1);  ORBX_PK(6, 2, -2);   ORBX_PK(7, 1, -3);
-            ORBX_PK(8, 0, -3);  ORBX_PK(9, -1, -3); ORBX_PK(10, -2, -2); ORBX_PK(11, -3, -1);
-            ORBX_PK(12, -3, 0); ORBX_PK(13, -3, 1); ORBX_PK(14, -2, 2);  ORBX_PK(15, -1, 3);
+                ORBX_PK(0, 0, 3);   ORBX_PK(1, 1, 3);   ORBX_PK(2, 2, 2);    ORBX_PK(3, 3, 1);
+                ORBX_PK(4, 3, 0);   ORBX_PK(5, 3, -1);  ORBX_PK(6, 2, -2);   ORBX_PK(7, 1, -3);
+                ORBX_PK(8, 0, -3);  ORBX_PK(9, -1, -3); ORBX_PK(10, -2, -2); ORBX_PK(11, -3, -1);
+                ORBX_PK(12, -3, 0); ORBX_PK(13, -3, 1); ORBX_PK(14, -2, 2);  ORBX_PK(15, -1, 3);
 #undef ORBX_PK
-            unsigned m3[16], m9[16];
+                unsigned m3[16], m9[16];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) m3[k] = vmax3(q[k], q[(k + 1) & 15], q[(k + 2) & 15]);
+                for (int k = 0; k < 16; ++k) m3[k] = vmax3(q[k], q[(k + 1) & 15], q[(k + 2) & 15]);
 #pragma unroll
-            for (int k = 0; k < 16; ++k) m9[k] = vmax3(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
-            unsigned mm = vmin3(vmin3(vmin3(m9[0], m9[1], m9[2]), vmin3(m9[3], m9[4], m9[5]), vmin3(m9[6], m9[7], m9[8])),
-                                vmin3(vmin3(m9[9], m9[10], m9[11]), vmin3(m9[12], m9[13], m9[14]), m9[15]),
-                                0xFFFFFFFFu);
-            const int A = v - (int)(mm & 0xffffu);
-            const int nB = 255 - (int)(mm >> 16) - v;
-            const int sc = max(A, nB);
-            if (sc > T) {
-                s_score[sy * SP + sx] = (uint8_t)(sc - 1);
-                const int x = ox0 - 4 + sx;
-                if (x >= max(ox0, ORBX_EDGE) && x < ox1 && sy >= 1 && sy <= y1 - y0) s_cq[atomicAdd(&s_cn, 1)] = (uint16_t)e;
+                for (int k = 0; k < 16; ++k) m9[k] = vmax3(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+                unsigned mm = vmin3(vmin3(vmin3(m9[0], m9[1], m9[2]), vmin3(m9[3], m9[4], m9[5]), vmin3(m9[6], m9[7], m9[8])),
+                                    vmin3(vmin3(m9[9], m9[10], m9[11]), vmin3(m9[12], m9[13], m9[14]), m9[15]),
+                                    0xFFFFFFFFu);
+                const int A = v - (int)(mm & 0xffffu);
+                const int nB = 255 - (int)(mm >> 16) - v;
+                const int sc = max(A, nB);
+                if (sc > T) {
+                    s_score[sy * SP + sx] = (uint8_t)(sc - 1);
+                    const int x = ox0 - 4 + sx;
+                    corner = x >= max(ox0, ORBX_EDGE) && x < ox1 && sy >= 1 && sy <= y1 - y0;
+                }
             }
+            const unsigned bc = __ballot_sync(0xffffffffu, corner);
+            if (corner) mycq[cn + __popc(bc & lt)] = (uint16_t)e;
+            cn += __popc(bc);
         }
-        __syncthreads();
-        // ---- phase C: 3x3 NMS of the queued corners
-        const int cn = s_cn;
-        for (int i = tid; i < cn; i += NT) {
-            const int e = s_cq[i];
+        __syncthreads();                                     // every score of the tile is in place
+        // ---- phase C (per warp): 3x3 NMS of its queued corners
+        for (int i = lane; i < cn; i += 32) {
+            const int e = mycq[i];
             const int sy = e >> 8, sx = e & 255;
             const uint8_t* p = &s_score[sy * SP + sx];
             const int s = p[0];
@@ -830,18 +821,26 @@ __global__ void __launch_bounds__(DESC_NT) k_describe(const __grid_constant__ Ge
             *d = v;
         }
     }
-    // ---- IC moments on the unblurred level: lane <-> column u = lane - 15; umax[|v|] unrolled at compile time
+    // ---- IC moments on the unblurred level: lane <-> column u = lane - 15.  All 31 rows are loaded first (every
+    //      address is inside the level: the disc radius 15 is below the 31-px border), so the loads are in flight
+    //      together; the disc shape umax[|v|] is applied afterwards with compile-time thresholds.
     int m10 = 0, m01 = 0;
     {
-        const int u = lane - 15, au = u < 0 ? -u : u;
+        const int u = min(lane, 30) - 15, au = u < 0 ? -u : u;
         const uint8_t* p = img + (size_t)(y - 15) * pitch + (x + u);
-        int colsum = 0;
-        constexpr int UMAX[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+        int I[31];
 #pragma unroll
-        for (int vv = -15; vv <= 15; ++vv, p += pitch) {
-            if (lane < 31 && au <= UMAX[vv < 0 ? -vv : vv]) { const int I = __ldg(p); colsum += I; m01 += vv * I; }
+        for (int k = 0; k < 31; ++k) I[k] = __ldg(p + (size_t)k * pitch);
+        constexpr int UMAX[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+        int colsum = 0;
+#pragma unroll
+        for (int k = 0; k < 31; ++k) {
+            const int vv = k - 15;
+            const int Iv = (au <= UMAX[vv < 0 ? -vv : vv]) ? I[k] : 0;
+            colsum += Iv; m01 += vv * Iv;
         }
         m10 = u * colsum;
+        if (lane == 31) { m10 = 0; m01 = 0; }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, d); m01 += __shfl_xor_sync(0xffffffffu, m01, d); }

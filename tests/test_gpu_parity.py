@@ -242,3 +242,22 @@ def test_cv2_live_if_available(orbmod):
     t = synth_descriptors(2000, 1); q = synth_map_queries(t, 3000, 2)
     m = orbmod.BFMatcher(orbmod.NORM_HAMMING).match(q, t)
     assert m.tobytes() == O.cv2_matches_to_array(cv2.BFMatcher(cv2.NORM_HAMMING).match(q, t)).tobytes()
+
+
+def test_orb_4k_5000(orbmod, oracle):
+    """BASELINE config 5 shape: 3840x2160, 5000 features (one frame against the oracle; the oracle itself is pinned
+    to cv2 at this size by tools/check_oracle_4k.py, run in the build container)."""
+    from rgbd_visualodometry_b200.synth import synth_frame
+    img = synth_frame(2160, 3840, 6, shapes=400)
+    k, d = orbmod.ORB_create(5000, 1.2, 8).detectAndCompute(img, None)
+    ko, do = oracle.detect_and_compute(img, 5000)
+    _assert_kp_equal(k, d, ko, do, "4k")
+
+
+def test_orb_noise_global_workspace(orbmod, oracle):
+    """Pure noise at 640x480: ~30 000 FAST survivors on level 0 -> the selection runs from the global-memory
+    workspace (more candidates than the shared-memory array holds) and must still reproduce libstdc++'s order."""
+    img = np.random.default_rng(11).integers(0, 256, (480, 640), dtype=np.uint8)
+    k, d = orbmod.ORB_create(500, 1.2, 8).detectAndCompute(img, None)
+    ko, do = oracle.detect_and_compute(img, 500)
+    _assert_kp_equal(k, d, ko, do, "noise vga")
