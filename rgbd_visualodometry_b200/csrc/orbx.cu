@@ -29,6 +29,9 @@ const int8_t k_pattern_host[256 * 4] = {
 };
 
 constexpr int FAST_R = 16, FAST_NT = 256;
+constexpr int MAX_LANES = 4;               // concurrent frame-range pipelines of one extraction call
+constexpr int LANE_MIN_FRAMES = 64;        // a lane must still fill the GPU on its own
+constexpr int FUSED_PYR_MIN_BATCH = 128;   // from this batch size on, one CTA per frame (k_gray_pyr) fills the GPU
 constexpr int N_STAGES = 7;
 const char* const k_stage_names[N_STAGES] = {"gray", "pyramid", "fast_nms", "select_harris", "blur", "describe", "match"};
 
@@ -64,6 +67,8 @@ struct orbx_ctx {
     cudaEvent_t ev[N_STAGES + 2] = {};   // 0..6 bracket the six extraction stages, 7..8 the matcher
     cudaStream_t stream2 = nullptr;      // blur runs here, concurrently with FAST + selection (unless profiling)
     cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
+    cudaStream_t lane[4] = {};           // extra frame-range pipelines (lane 0 is `stream`)
+    cudaEvent_t ev_fork = nullptr, ev_join[4] = {};
     float stage_ms[N_STAGES] = {};
     bool stage_valid[N_STAGES] = {};
 };
@@ -206,59 +211,112 @@ void stage_mark(orbx_ctx* c, int i)
 }
 
 // The extraction pipeline on device-resident frames; everything asynchronous on c->stream.
+// The kernel sequence for frames [f0, f0 + nb) on stream `st`.  Every buffer is frame-major, so a frame range is
+// just a base-pointer offset.  `side` (may be null) is a second stream the blur is queued on behind FAST.
+int run_extract_range(orbx_ctx* c, cudaStream_t st, cudaStream_t side, cudaEvent_t ev_a, cudaEvent_t ev_b, bool marks, int f0, int nb,
+                      const uint8_t* d_imgs, size_t step, size_t frame_stride, int channels, float* d_kps, uint8_t* d_desc, int cap,
+                      int* d_counts)
+{
+    const Geom& g = c->geom;
+    const size_t F = (size_t)f0;
+    d_imgs += F * frame_stride;
+    uint8_t* pyr = (uint8_t*)c->pyr.p + F * g.pyr_frame;
+    uint8_t* blur = (uint8_t*)c->blur.p + F * g.pyr_frame;
+    uint32_t* rowcnt = (uint32_t*)c->rowcnt.p + F * g.cnt_frame;
+    uint32_t* rowent = (uint32_t*)c->rowent.p + F * g.ent_frame;
+    Elem* work = (Elem*)c->work.p + F * g.ws_frame;
+    uint32_t* selpos = (uint32_t*)c->selpos.p + 2 * F * g.ws_frame;
+    int* fincnt = (int*)c->fincnt.p + F * g.nlevels;
+    int* status = (int*)c->status.p + F;
+    d_kps += F * cap * 7; d_desc += F * cap * 32; d_counts += F;
+    const uint32_t* tabs = (const uint32_t*)c->tabs.p;
+    const unsigned B = (unsigned)nb;
+
+    if (marks) stage_mark(c, 0);
+    const int aligned4 = ((reinterpret_cast<uintptr_t>(d_imgs) | step | frame_stride) & 3) == 0;
+    if (nb >= FUSED_PYR_MIN_BATCH) {
+        // the batch alone fills the GPU: one CTA per frame runs gray + the whole level chain in a single launch
+        if (channels == 3) k_gray_pyr<3><<<B, GP_NT, 0, st>>>(d_imgs, frame_stride, step, aligned4, g, pyr, tabs);
+        else               k_gray_pyr<1><<<B, GP_NT, 0, st>>>(d_imgs, frame_stride, step, aligned4, g, pyr, tabs);
+        ++c->launches;
+        if (marks) stage_mark(c, 1);
+    } else {
+        {
+            const dim3 blk(64, 4);
+            const dim3 grd((unsigned)((g.L[0].pitch / 4 + 63) / 64), (unsigned)((g.L[0].h + 3) / 4), B);
+            if (channels == 3) k_gray<3><<<grd, blk, 0, st>>>(d_imgs, frame_stride, step, aligned4, g, pyr);
+            else               k_gray<1><<<grd, blk, 0, st>>>(d_imgs, frame_stride, step, aligned4, g, pyr);
+            ++c->launches;
+        }
+        if (marks) stage_mark(c, 1);
+        for (int l = 1; l < g.nlevels; ++l) {
+            if (g.L[l].w <= 0 || g.L[l].h <= 0) continue;
+            const dim3 blk(32, PYR_BY);
+            const dim3 grd((unsigned)((g.L[l].pitch / 4 + 31) / 32), (unsigned)((g.L[l].h + PYR_RH * PYR_BY - 1) / (PYR_RH * PYR_BY)), B);
+            k_pyr_down<<<grd, blk, 0, st>>>(g, l, pyr, tabs);
+            ++c->launches;
+        }
+    }
+    if (marks) stage_mark(c, 2);
+    if (g.total_bands > 0) {
+        k_fast_bands<FAST_R, FAST_NT><<<dim3((unsigned)g.total_bands, B), FAST_NT, 0, st>>>(g, pyr, rowcnt, rowent);
+        ++c->launches;
+    }
+    if (side && g.total_blur > 0) {
+        // The blur only needs the pyramid.  It is issue-bound while the selection kernel is latency-bound (serial
+        // introselect chains), so it is queued on a second stream BEHIND FAST and runs underneath k_select.
+        CU(cudaEventRecord(ev_a, st));
+        CU(cudaStreamWaitEvent(side, ev_a, 0));
+        k_blur<<<dim3((unsigned)g.total_blur, B), BLUR_NT, 0, side>>>(g, pyr, blur);
+        ++c->launches;
+        CU(cudaEventRecord(ev_b, side));
+    }
+    if (marks) stage_mark(c, 3);
+    k_select<<<dim3((unsigned)g.nlevels, B), SEL_NT, 0, st>>>(g, pyr, rowcnt, rowent, work, selpos, fincnt, status);
+    ++c->launches;
+    if (marks) stage_mark(c, 4);
+    if (!side && g.total_blur > 0) {
+        k_blur<<<dim3((unsigned)g.total_blur, B), BLUR_NT, 0, st>>>(g, pyr, blur);
+        ++c->launches;
+    }
+    if (marks) stage_mark(c, 5);
+    if (side && g.total_blur > 0) CU(cudaStreamWaitEvent(st, ev_b, 0));
+    k_describe<<<dim3((unsigned)((std::max(cap, 1) + DESC_KPB - 1) / DESC_KPB), B), DESC_NT, 0, st>>>(
+        g, pyr, blur, work, fincnt, (const float4*)c->pattern.p, d_kps, d_desc, d_counts, cap);
+    ++c->launches;
+    if (marks) stage_mark(c, 6);
+    return ORBX_OK;
+}
+
+// The extraction pipeline on device-resident frames; everything asynchronous, ordered on c->stream.
+// Large batches are cut into `lanes` frame ranges that run the same kernel sequence on their own streams: the stages
+// bound differently (FAST issue-bound, pyramid / selection / describe latency-bound), so CTAs of different stages
+// from different lanes share the SMs and fill each other's stalls.  Frames are independent, so no lane ever waits
+// for another; the lanes fork from and join back into c->stream with events.
 int run_extract(orbx_ctx* c, const uint8_t* d_imgs, int batch, int w, int h, size_t step, size_t frame_stride, int channels,
                 float* d_kps, uint8_t* d_desc, int cap, int* d_counts)
 {
     int rc = set_geometry(c, w, h);
     if (rc) return rc;
-    const Geom& g = c->geom;
-    uint8_t* pyr = (uint8_t*)c->pyr.p;
     CU(cudaMemsetAsync(c->status.p, 0, sizeof(int) * (size_t)batch, c->stream));
-    stage_mark(c, 0);
-    {
-        const dim3 blk(64, 4);
-        const dim3 grd((unsigned)((g.L[0].pitch / 4 + 63) / 64), (unsigned)((g.L[0].h + 3) / 4), (unsigned)batch);
-        const int aligned4 = ((reinterpret_cast<uintptr_t>(d_imgs) | step | frame_stride) & 3) == 0;
-        if (channels == 3) k_gray<3><<<grd, blk, 0, c->stream>>>(d_imgs, frame_stride, step, aligned4, g, pyr);
-        else               k_gray<1><<<grd, blk, 0, c->stream>>>(d_imgs, frame_stride, step, aligned4, g, pyr);
-        ++c->launches;
+    static const int env_lanes = getenv("ORBX_LANES") ? atoi(getenv("ORBX_LANES")) : 3;
+    int lanes = std::max(1, std::min(env_lanes, MAX_LANES));
+    if (c->profiling || batch < lanes * LANE_MIN_FRAMES) lanes = 1;
+    if (lanes == 1) {
+        rc = run_extract_range(c, c->stream, c->profiling ? nullptr : c->stream2, c->ev_pyr, c->ev_blur, c->profiling, 0, batch, d_imgs, step,
+                               frame_stride, channels, d_kps, d_desc, cap, d_counts);
+        if (rc) return rc;
+    } else {
+        CU(cudaEventRecord(c->ev_fork, c->stream));
+        for (int k = 0; k < lanes; ++k) {
+            const int f0 = (int)((long)batch * k / lanes), f1 = (int)((long)batch * (k + 1) / lanes);
+            cudaStream_t st = k == 0 ? c->stream : c->lane[k];
+            if (k > 0) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
+            rc = run_extract_range(c, st, nullptr, nullptr, nullptr, false, f0, f1 - f0, d_imgs, step, frame_stride, channels, d_kps, d_desc, cap, d_counts);
+            if (rc) return rc;
+            if (k > 0) { CU(cudaEventRecord(c->ev_join[k], st)); CU(cudaStreamWaitEvent(c->stream, c->ev_join[k], 0)); }
+        }
     }
-    stage_mark(c, 1);
-    for (int l = 1; l < g.nlevels; ++l) {
-        if (g.L[l].w <= 0 || g.L[l].h <= 0) continue;
-        const dim3 blk(32, PYR_BY);
-        const dim3 grd((unsigned)((g.L[l].pitch / 4 + 31) / 32), (unsigned)((g.L[l].h + PYR_RH * PYR_BY - 1) / (PYR_RH * PYR_BY)), (unsigned)batch);
-        k_pyr_down<<<grd, blk, 0, c->stream>>>(g, l, pyr, (const uint32_t*)c->tabs.p);
-        ++c->launches;
-    }
-    if (!c->profiling && g.total_blur > 0) {                 // blur only needs the pyramid: overlap it with FAST + selection
-        CU(cudaEventRecord(c->ev_pyr, c->stream));
-        CU(cudaStreamWaitEvent(c->stream2, c->ev_pyr, 0));
-        k_blur<<<dim3((unsigned)g.total_blur, (unsigned)batch), BLUR_NT, 0, c->stream2>>>(g, pyr, (uint8_t*)c->blur.p);
-        ++c->launches;
-        CU(cudaEventRecord(c->ev_blur, c->stream2));
-    }
-    stage_mark(c, 2);
-    if (g.total_bands > 0) {
-        k_fast_bands<FAST_R, FAST_NT><<<dim3((unsigned)g.total_bands, (unsigned)batch), FAST_NT, 0, c->stream>>>(
-            g, pyr, (uint32_t*)c->rowcnt.p, (uint32_t*)c->rowent.p);
-        ++c->launches;
-    }
-    stage_mark(c, 3);
-    k_select<<<dim3((unsigned)g.nlevels, (unsigned)batch), SEL_NT, 0, c->stream>>>(
-        g, pyr, (const uint32_t*)c->rowcnt.p, (const uint32_t*)c->rowent.p, (Elem*)c->work.p, (uint32_t*)c->selpos.p, (int*)c->fincnt.p, (int*)c->status.p);
-    ++c->launches;
-    stage_mark(c, 4);
-    if (c->profiling && g.total_blur > 0) {                  // serialised so that the stage events mean something
-        k_blur<<<dim3((unsigned)g.total_blur, (unsigned)batch), BLUR_NT, 0, c->stream>>>(g, pyr, (uint8_t*)c->blur.p);
-        ++c->launches;
-    }
-    stage_mark(c, 5);
-    if (!c->profiling && g.total_blur > 0) CU(cudaStreamWaitEvent(c->stream, c->ev_blur, 0));
-    k_describe<<<dim3((unsigned)((std::max(cap, 1) + DESC_KPB - 1) / DESC_KPB), (unsigned)batch), DESC_NT, 0, c->stream>>>(
-        g, pyr, (const uint8_t*)c->blur.p, (const Elem*)c->work.p, (const int*)c->fincnt.p, (const float4*)c->pattern.p, d_kps, d_desc, d_counts, cap);
-    ++c->launches;
-    stage_mark(c, 6);
     CU(cudaGetLastError());
     c->last_batch = batch;
     if (c->profiling) for (int i = 0; i < 6; ++i) c->stage_valid[i] = true;
@@ -378,6 +436,9 @@ int orbx_create(orbx_ctx** out, int device, int nfeatures, float scale_factor, i
     if (prop.major != 10) return bail(ORBX_E_CUDA);          // sm_100a only: no other code path exists
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(ORBX_E_CUDA);
     if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) return bail(ORBX_E_CUDA);
+    for (int k = 1; k < 4; ++k)
+        if (cudaStreamCreateWithFlags(&c->lane[k], cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming) != cudaSuccess) return bail(ORBX_E_CUDA);
+    if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(ORBX_E_CUDA);
     if (cudaEventCreateWithFlags(&c->ev_pyr, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_blur, cudaEventDisableTiming) != cudaSuccess) return bail(ORBX_E_CUDA);
     for (int i = 0; i < N_STAGES + 2; ++i) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail(ORBX_E_CUDA);
     build_geom(c, max_w, max_h, &c->geom_max, nullptr);
@@ -412,6 +473,8 @@ void orbx_destroy(orbx_ctx* c)
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     if (c->h_small) cudaFreeHost(c->h_small);
     for (int i = 0; i < N_STAGES + 2; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int k = 1; k < 4; ++k) { if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); if (c->lane[k]) { cudaStreamSynchronize(c->lane[k]); cudaStreamDestroy(c->lane[k]); } }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_pyr) cudaEventDestroy(c->ev_pyr);
     if (c->ev_blur) cudaEventDestroy(c->ev_blur);
     if (c->stream2) cudaStreamDestroy(c->stream2);

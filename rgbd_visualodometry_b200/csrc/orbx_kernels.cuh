@@ -3,6 +3,7 @@
 // and is bit-exact against OpenCV: integer stages in integer arithmetic, float stages with explicit
 // round-to-nearest intrinsics (never contracted) and __fmaf_rn only where OpenCV's own build uses FMA (A.8).
 //
+//   k_gray_pyr      A.1+2 fused gray + 8-level pyramid, one CTA per frame (large batches); k_gray / k_pyr_down per level otherwise
 //   k_gray          A.1   BGR -> gray (level 0)                         HBM-bound, 4 px / thread
 //   k_pyr_down      A.2   INTER_LINEAR_EXACT level l from level l-1     thread = output column, horizontal pass reused
 //   k_fast_bands    A.3   FAST-9/16 score + 3x3 NMS -> per-row lists    smem tiles with halos, u16x2 SIMD min/max,
@@ -76,7 +77,9 @@ __global__ void __launch_bounds__(256) k_gray(const uint8_t* __restrict__ in, un
 constexpr int PYR_RH = 16;          // output rows per thread
 constexpr int PYR_BY = 4;           // row strips (warps) per CTA; a warp covers 128 output columns
 struct PyrRow { uint32_t h[4]; };
-__device__ __forceinline__ PyrRow pyr_hpass(const uint8_t* __restrict__ row, bool w2ok, const uint32_t* coef, const uint32_t* sh, const bool* hi)
+// NOTE: plain (coherent) loads on purpose -- the fused per-frame kernel reads rows that other threads of the same
+// CTA wrote earlier in the same launch, which the non-coherent read-only path does not guarantee to see.
+__device__ __forceinline__ PyrRow pyr_hpass(const uint8_t* row, bool w2ok, const uint32_t* coef, const uint32_t* sh, const bool* hi)
 {
     const uint32_t* p = reinterpret_cast<const uint32_t*>(row);
     const uint32_t w0 = p[0], w1 = p[1], w2 = w2ok ? p[2] : 0u;
@@ -89,15 +92,11 @@ __device__ __forceinline__ PyrRow pyr_hpass(const uint8_t* __restrict__ row, boo
     return r;
 }
 
-__global__ void __launch_bounds__(128) k_pyr_down(const __grid_constant__ Geom g, int l, uint8_t* __restrict__ pyr,
-                                                  const uint32_t* __restrict__ tabs)
+// output columns x .. x+3, rows [ys, ye) of level l of frame f
+__device__ __forceinline__ void pyr_down_item(const Geom& g, int l, int f, int x, int ys, int ye, uint8_t* pyr, const uint32_t* __restrict__ tabs)
 {
     const LevelGeom& D = g.L[l];
     const LevelGeom& S = g.L[l - 1];
-    const int x = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int f = blockIdx.z;
-    const int ys = (blockIdx.y * PYR_BY + threadIdx.y) * PYR_RH, ye = min(ys + PYR_RH, D.h);
-    if (x >= D.pitch || ys >= ye) return;
     uint8_t* dst = pyr + (size_t)f * g.pyr_frame + D.img_off + (size_t)ys * D.pitch + x;
     if (x >= D.w) {                                          // row padding: keep it zero
         for (int y = ys; y < ye; ++y, dst += D.pitch) *reinterpret_cast<uint32_t*>(dst) = 0u;
@@ -125,7 +124,7 @@ __global__ void __launch_bounds__(128) k_pyr_down(const __grid_constant__ Geom g
     for (int k = 0; k < 4; ++k) { ha.h[k] = 0; hb.h[k] = 0; }
 #pragma unroll 2
     for (int y = ys; y < ye; ++y, dst += D.pitch) {
-        const uint32_t ty = __ldg(ytab + y);                 // uniform across the block
+        const uint32_t ty = __ldg(ytab + y);
         const int y0 = ty & 0xffff, y1 = min(y0 + 1, S.h - 1);
         const uint32_t cy1 = ty >> 16, cy0 = 256u - cy1;
         if (y0 == have) ha = hb;
@@ -140,6 +139,81 @@ __global__ void __launch_bounds__(128) k_pyr_down(const __grid_constant__ Geom g
             out |= min(v, 255u) << (8 * k);
         }
         *reinterpret_cast<uint32_t*>(dst) = out;
+    }
+}
+
+// one level per launch (small batches / large frames: plenty of CTAs per level)
+__global__ void __launch_bounds__(128) k_pyr_down(const __grid_constant__ Geom g, int l, uint8_t* pyr, const uint32_t* __restrict__ tabs)
+{
+    const LevelGeom& D = g.L[l];
+    const int x = (blockIdx.x * 32 + threadIdx.x) * 4;
+    const int ys = (blockIdx.y * PYR_BY + threadIdx.y) * PYR_RH, ye = min(ys + PYR_RH, D.h);
+    if (x >= D.pitch || ys >= ye) return;
+    pyr_down_item(g, l, blockIdx.z, x, ys, ye, pyr, tabs);
+}
+
+// 4 gray pixels from 12 BGR bytes: coefficients split into high / low bytes so each pixel is two IDP.4A
+//   3735 B + 19235 G + 9798 R + 16384 = 256 (14 B + 75 G + 38 R) + (151 B + 35 G + 70 R) + 16384      (exact)
+__device__ __forceinline__ uint32_t gray4(uint32_t w0, uint32_t w1, uint32_t w2)
+{
+    constexpr uint32_t CH_ = 14u | (75u << 8) | (38u << 16), CL_ = 151u | (35u << 8) | (70u << 16);
+    const uint32_t p0 = w0, p1 = __byte_perm(w0, w1, 0x0543), p2 = __byte_perm(w1, w2, 0x0432), p3 = w2 >> 8;
+    const uint32_t g0 = (__dp4a(p0, CH_, 0u) * 256u + __dp4a(p0, CL_, 16384u)) >> 15;
+    const uint32_t g1 = (__dp4a(p1, CH_, 0u) * 256u + __dp4a(p1, CL_, 16384u)) >> 15;
+    const uint32_t g2 = (__dp4a(p2, CH_, 0u) * 256u + __dp4a(p2, CL_, 16384u)) >> 15;
+    const uint32_t g3 = (__dp4a(p3, CH_, 0u) * 256u + __dp4a(p3, CL_, 16384u)) >> 15;
+    return g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+}
+
+// Fused gray + whole pyramid, ONE CTA PER FRAME: the level chain l-1 -> l is a dependency only inside a frame, so a
+// frame-private CTA walks it with block barriers -- one launch instead of eight, no per-level launch tails, and the
+// frame's levels stay hot in L1/L2 while they are consumed.  Used when the batch alone fills the GPU.
+constexpr int GP_NT = 512;
+constexpr int GP_RS = 8;               // output rows per work item
+template <int CH>
+__global__ void __launch_bounds__(GP_NT, 2) k_gray_pyr(const uint8_t* __restrict__ in, unsigned long long frame_stride,
+                                                       unsigned long long step, int aligned4, const __grid_constant__ Geom g,
+                                                       uint8_t* pyr, const uint32_t* __restrict__ tabs)
+{
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    {
+        const LevelGeom& L = g.L[0];
+        const int nq = L.pitch >> 2;
+        for (int y = wid; y < L.h; y += GP_NT / 32) {
+            const uint8_t* srow = in + (size_t)f * frame_stride + (size_t)y * step;
+            uint32_t* drow = reinterpret_cast<uint32_t*>(pyr + (size_t)f * g.pyr_frame + L.img_off + (size_t)y * L.pitch);
+            for (int q = lane; q < nq; q += 32) {
+                const int x = q * 4;
+                uint32_t out = 0;
+                if (aligned4 && x + 3 < L.w) {
+                    if (CH == 3) {
+                        const uint32_t* s4 = reinterpret_cast<const uint32_t*>(srow + (size_t)x * 3);
+                        out = gray4(__ldg(s4), __ldg(s4 + 1), __ldg(s4 + 2));
+                    } else {
+                        out = __ldg(reinterpret_cast<const uint32_t*>(srow + x));
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (x + k < L.w) {
+                            const uint8_t* s = srow + (size_t)(x + k) * CH;
+                            const uint32_t p = CH == 3 ? (3735u * __ldg(s) + 19235u * __ldg(s + 1) + 9798u * __ldg(s + 2) + 16384u) >> 15 : (uint32_t)__ldg(s);
+                            out |= p << (8 * k);
+                        }
+                }
+                drow[q] = out;
+            }
+        }
+    }
+    for (int l = 1; l < g.nlevels; ++l) {
+        __syncthreads();                                     // level l-1 of this frame is complete (block-visible)
+        const LevelGeom& D = g.L[l];
+        if (D.w <= 0 || D.h <= 0) continue;
+        const int nq = D.pitch >> 2, nstrips = (D.h + GP_RS - 1) / GP_RS;
+        for (int item = tid; item < nq * nstrips; item += GP_NT) {
+            const int strip = item / nq, q = item - strip * nq;
+            pyr_down_item(g, l, f, q * 4, strip * GP_RS, min(strip * GP_RS + GP_RS, D.h), pyr, tabs);
+        }
     }
 }
 
@@ -445,7 +519,7 @@ __device__ int partition_tail_warp(Elem* v, int m, int len, float thr, int lane)
 
 constexpr int SEL_NT = 128;
 constexpr int SEL_SMEM_ELEMS = 3072;
-constexpr int SEL_PAR_MIN = 96;        // ranges up to this length are finished by one warp
+constexpr int SEL_PAR_MIN = 32;        // ranges up to this length are finished by one warp
 
 struct SelShared {
     int warp_a[SEL_NT / 32], warp_b[SEL_NT / 32];
@@ -707,6 +781,10 @@ constexpr int BLUR_RH = 64;            // output rows per thread
 constexpr int BLUR_NT = 128;           // work items per CTA
 constexpr int BLUR_LO = 12;            // first produced column (8-column groups start at 12 + 8q, so x0 - 4 is 8-byte aligned)
 
+// Loads the compiler may not sink next to their first use: issued back to back, they are all in flight together.
+__device__ __forceinline__ uint32_t ldg_u8_now(const uint8_t* p) { uint32_t v; asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ uint32_t ldg_u32_now(const void* p) { uint32_t v; asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+
 __device__ __forceinline__ float u8f(uint32_t w, uint32_t sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f; }
 
 __global__ void __launch_bounds__(BLUR_NT) k_blur(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur)
@@ -812,10 +890,10 @@ __global__ void __launch_bounds__(DESC_NT) k_describe(const __grid_constant__ Ge
     {
         const int c = lane & 15, half = lane >> 4;
         const bool on = c < 12 && xa + c * 4 < pitch;
-        const uint8_t* p = bimg + (size_t)(y - 18 + half) * pitch + xa + c * 4;
+        const uint8_t* p = bimg + (size_t)(y - 18 + half) * pitch + xa + (on ? c * 4 : 0);
         uint32_t* d = win + half * DWORDS + c;
 #pragma unroll
-        for (int it = 0; it < (DWIN + 1) / 2; ++it, p += 2 * pitch, d += 2 * DWORDS) {
+        for (int it = 0; it < (DWIN + 1) / 2; ++it, p += 2 * pitch, d += 2 * DWORDS) {   // rows 2*it + half; row 37 is padding
             uint32_t v = 0;
             if (on && (2 * it + half) < DWIN) v = __ldg(reinterpret_cast<const uint32_t*>(p));
             *d = v;
@@ -830,7 +908,7 @@ __global__ void __launch_bounds__(DESC_NT) k_describe(const __grid_constant__ Ge
         const uint8_t* p = img + (size_t)(y - 15) * pitch + (x + u);
         int I[31];
 #pragma unroll
-        for (int k = 0; k < 31; ++k) I[k] = __ldg(p + (size_t)k * pitch);
+        for (int k = 0; k < 31; ++k) I[k] = (int)__ldg(p + (size_t)k * pitch);
         constexpr int UMAX[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
         int colsum = 0;
 #pragma unroll

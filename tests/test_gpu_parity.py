@@ -261,3 +261,22 @@ def test_orb_noise_global_workspace(orbmod, oracle):
     k, d = orbmod.ORB_create(500, 1.2, 8).detectAndCompute(img, None)
     ko, do = oracle.detect_and_compute(img, 500)
     _assert_kp_equal(k, d, ko, do, "noise vga")
+
+
+def test_orb_large_batch_fused_pyramid(orbmod, oracle):
+    """Batches >= 128 frames take the fused one-CTA-per-frame gray+pyramid kernel: every frame checked, plus the
+    level images of two frames."""
+    from rgbd_visualodometry_b200.synth import synth_frame
+    b = 130
+    frames = [synth_frame(150, 200, 5000 + i) for i in range(b)]
+    ctx = orbmod.Context(200, 1.2, 8, 200, 150, b)
+    kps, desc, cnt = ctx.detect_and_compute_batch(frames)
+    for i in (0, b - 1):
+        _, _, dump = oracle.detect_and_compute(frames[i], 200, dump=True)
+        ws, hs, _ = oracle.level_geometry(200, 150)
+        for l in range(8):
+            assert np.array_equal(ctx.debug_level(i, l, ws[l], hs[l]), dump["levels"][l]), f"frame {i} level {l}"
+    for i, fr in enumerate(frames):
+        ko, do = oracle.detect_and_compute(fr, 200)
+        _assert_kp_equal(kps[i, :cnt[i]], desc[i, :cnt[i]], ko, do, f"fused batch frame {i}")
+    ctx.close()
