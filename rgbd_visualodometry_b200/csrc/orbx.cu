@@ -31,6 +31,7 @@ const int8_t k_pattern_host[256 * 4] = {
 constexpr int FAST_R = 16, FAST_NT = 256;
 constexpr int MAX_LANES = 4;               // concurrent frame-range pipelines of one extraction call
 constexpr int LANE_MIN_FRAMES = 64;        // a lane must still fill the GPU on its own
+constexpr int HOST_LANE_MIN_FRAMES = 16;   // host-buffer batches: lanes mainly overlap PCIe copies with kernels
 constexpr int FUSED_PYR_MIN_BATCH = 128;   // from this batch size on, one CTA per frame (k_gray_pyr) fills the GPU
 constexpr int N_STAGES = 7;
 const char* const k_stage_names[N_STAGES] = {"gray", "pyramid", "fast_nms", "select_harris", "blur", "describe", "match"};
@@ -526,22 +527,38 @@ int orbx_detect_and_compute_batch(orbx_ctx* c, const uint8_t* const* imgs, int b
     if ((rc = ensure(c, c->kps, sizeof(orbx_keypoint) * (size_t)std::max(cap, 1) * batch))) return rc;
     if ((rc = ensure(c, c->desc, (size_t)32 * std::max(cap, 1) * batch))) return rc;
     if ((rc = ensure(c, c->counts, sizeof(int) * (size_t)batch))) return rc;
-    for (int i = 0; i < batch; ++i) {
-        if (!imgs[i]) return fail(c, ORBX_E_ARG, "null frame pointer");
-        CU(cudaMemcpy2DAsync((uint8_t*)c->in.p + fstride * i, dstep, imgs[i], step, row, (size_t)h, cudaMemcpyHostToDevice, c->stream));
-    }
-    if ((rc = run_extract(c, (const uint8_t*)c->in.p, batch, w, h, dstep, fstride, channels, (float*)c->kps.p, (uint8_t*)c->desc.p, cap,
-                          (int*)c->counts.p)))
-        return rc;
+    for (int i = 0; i < batch; ++i) if (!imgs[i]) return fail(c, ORBX_E_ARG, "null frame pointer");
+    if ((rc = set_geometry(c, w, h))) return rc;
+    CU(cudaMemsetAsync(c->status.p, 0, sizeof(int) * (size_t)batch, c->stream));
     int* h_counts = c->h_small;
     int* h_status = c->h_small + batch;
-    CU(cudaMemcpyAsync(h_counts, c->counts.p, sizeof(int) * (size_t)batch, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(h_status, c->status.p, sizeof(int) * (size_t)batch, cudaMemcpyDeviceToHost, c->stream));
-    if (cap > 0) {
-        // outputs are [batch][cap] on both sides: two bulk copies (records past n_out[i] are unspecified)
-        CU(cudaMemcpyAsync(kps, c->kps.p, sizeof(orbx_keypoint) * (size_t)cap * batch, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpyAsync(desc, c->desc.p, (size_t)32 * cap * batch, cudaMemcpyDeviceToHost, c->stream));
+    // Frame ranges ("lanes") on their own streams: upload -> kernels -> download per lane, so the H2D copy of lane k+1
+    // runs under the kernels of lane k and the D2H of lane k under the kernels of lane k+1 (PCIe is the bound here).
+    const int lanes = c->profiling ? 1 : std::max(1, std::min(MAX_LANES, batch / HOST_LANE_MIN_FRAMES));
+    if (lanes > 1) CU(cudaEventRecord(c->ev_fork, c->stream));
+    for (int k = 0; k < lanes; ++k) {
+        const int f0 = (int)((long)batch * k / lanes), f1 = (int)((long)batch * (k + 1) / lanes);
+        cudaStream_t st = k == 0 ? c->stream : c->lane[k];
+        if (k > 0) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
+        for (int i = f0; i < f1; ++i)
+            CU(cudaMemcpy2DAsync((uint8_t*)c->in.p + fstride * i, dstep, imgs[i], step, row, (size_t)h, cudaMemcpyHostToDevice, st));
+        const bool side = lanes == 1 && !c->profiling;
+        if ((rc = run_extract_range(c, st, side ? c->stream2 : nullptr, c->ev_pyr, c->ev_blur, c->profiling, f0, f1 - f0, (const uint8_t*)c->in.p, dstep,
+                                    fstride, channels, (float*)c->kps.p, (uint8_t*)c->desc.p, cap, (int*)c->counts.p)))
+            return rc;
+        const size_t n = (size_t)(f1 - f0);
+        CU(cudaMemcpyAsync(h_counts + f0, (int*)c->counts.p + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h_status + f0, (int*)c->status.p + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+        if (cap > 0) {
+            // outputs are [batch][cap] on both sides: bulk copies per lane (records past n_out[i] are unspecified)
+            CU(cudaMemcpyAsync(kps + (size_t)f0 * cap, (orbx_keypoint*)c->kps.p + (size_t)f0 * cap, sizeof(orbx_keypoint) * (size_t)cap * n, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, (uint8_t*)c->desc.p + (size_t)f0 * cap * 32, (size_t)32 * cap * n, cudaMemcpyDeviceToHost, st));
+        }
+        if (k > 0) { CU(cudaEventRecord(c->ev_join[k], st)); CU(cudaStreamWaitEvent(c->stream, c->ev_join[k], 0)); }
     }
+    CU(cudaGetLastError());
+    c->last_batch = batch;
+    if (c->profiling) for (int i = 0; i < 6; ++i) c->stage_valid[i] = true;
     CU(cudaStreamSynchronize(c->stream));
     bool over = false;
     for (int i = 0; i < batch; ++i) {
