@@ -279,9 +279,19 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
     dom = max(ext_stages, key=ext_stages.get) if ext_stages else None
     ext_total = sum(ext_stages.values())
     roofline = None
+    traffic = None                                       # DRAM bytes of the dominant kernel per launch, from the committed ncu --set full capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_dram_traffic.json")))["kernels"]
+        kname = {"gray": "k_gray", "fast_nms": "k_fast_bands", "select_harris": "k_select", "blur": "k_blur", "describe": "k_describe"}.get(dom)
+        if kname in tj and B == 256:
+            last = tj[kname][-1]
+            traffic = last["dram_read_bytes"] + last["dram_write_bytes"]
+    except Exception:
+        pass
     if dom:
         ach = b_alg * B / (ext_stages[dom] / 1e3) / 1e9
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
+                    "traffic_source": "profiles/r1_ncu_dram_traffic.json (ncu --set full, same 256-frame launch)" if traffic else None,
                     "peak_source": peak_src, "algorithmic_bytes_per_frame": b_alg, "frames_per_launch": B,
                     "kernel_ms": ext_stages[dom], "kernel_share_of_extraction": ext_stages[dom] / ext_total}
     pipe_ach = b_alg * B / (ext_total / 1e3) / 1e9 if ext_total else None
