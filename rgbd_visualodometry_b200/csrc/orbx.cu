@@ -352,7 +352,17 @@ int run_match(orbx_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int n
     const int rows_per_split = tiles_per_split * MT_BN;
     nsplit = (nt + rows_per_split - 1) / rows_per_split;
     // Many sets: each CTA keeps its expanded query tile and walks sets z, z + zgroups, ... (persistent pipelines).
-    const int zgroups = std::max(1, std::min(nsets, kSMs / std::max(1, tiles_m * nsplit)));
+    // zgroups: waves(z) * sets-per-CTA(z) is the time in units of one (query tile, set) pass; +1 per wave for the setup
+    int zgroups = 1;
+    {
+        const long per_z = (long)tiles_m * nsplit;
+        long best_cost = -1;
+        for (int z = 1; z <= nsets; ++z) {
+            const long waves = (per_z * z + kSMs - 1) / kSMs;
+            const long cost = waves * ((nsets + z - 1) / z + 1);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; zgroups = z; }
+        }
+    }
     int* keys = nullptr;
     const size_t nout = (size_t)nq * nsets;
     int rc;
