@@ -232,6 +232,7 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, cudaStream_t side, cudaEvent
     d_kps += F * cap * 7; d_desc += F * cap * 32; d_counts += F;
     const uint32_t* tabs = (const uint32_t*)c->tabs.p;
     const unsigned B = (unsigned)nb;
+    static const int dbg_skip = getenv("ORBX_SKIP") ? atoi(getenv("ORBX_SKIP")) : 0;   // debugging only: 1 = no blur, 2 = no describe
 
     if (marks) stage_mark(c, 0);
     const int aligned4 = ((reinterpret_cast<uintptr_t>(d_imgs) | step | frame_stride) & 3) == 0;
@@ -263,7 +264,7 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, cudaStream_t side, cudaEvent
         k_fast_bands<FAST_R, FAST_NT><<<dim3((unsigned)g.total_bands, B), FAST_NT, 0, st>>>(g, pyr, rowcnt, rowent);
         ++c->launches;
     }
-    if (side && g.total_blur > 0) {
+    if (side && g.total_blur > 0 && !(dbg_skip & 1)) {
         // The blur only needs the pyramid.  It is issue-bound while the selection kernel is latency-bound (serial
         // introselect chains), so it is queued on a second stream BEHIND FAST and runs underneath k_select.
         CU(cudaEventRecord(ev_a, st));
@@ -276,13 +277,13 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, cudaStream_t side, cudaEvent
     k_select<<<dim3((unsigned)g.nlevels, B), SEL_NT, 0, st>>>(g, pyr, rowcnt, rowent, work, selpos, fincnt, status);
     ++c->launches;
     if (marks) stage_mark(c, 4);
-    if (!side && g.total_blur > 0) {
+    if (!side && g.total_blur > 0 && !(dbg_skip & 1)) {
         k_blur<<<dim3((unsigned)g.total_blur, B), BLUR_NT, 0, st>>>(g, pyr, blur);
         ++c->launches;
     }
     if (marks) stage_mark(c, 5);
-    if (side && g.total_blur > 0) CU(cudaStreamWaitEvent(st, ev_b, 0));
-    k_describe<<<dim3((unsigned)((std::max(cap, 1) + DESC_KPB - 1) / DESC_KPB), B), DESC_NT, 0, st>>>(
+    if (side && g.total_blur > 0 && !(dbg_skip & 1)) CU(cudaStreamWaitEvent(st, ev_b, 0));
+    if (!(dbg_skip & 2)) k_describe<<<dim3((unsigned)((std::max(cap, 1) + DESC_KPB * DESC_KPW - 1) / (DESC_KPB * DESC_KPW)), B), DESC_NT, 0, st>>>(
         g, pyr, blur, work, fincnt, (const float4*)c->pattern.p, d_kps, d_desc, d_counts, cap);
     ++c->launches;
     if (marks) stage_mark(c, 6);
@@ -460,8 +461,10 @@ int orbx_create(orbx_ctx** out, int device, int nfeatures, float scale_factor, i
         ensure(c, c->status, sizeof(int) * B) || ensure(c, c->pattern, sizeof(float) * 1024))
         return bail(ORBX_E_NOMEM);
     {
-        float pat[1024];                                     // the rBRIEF pattern as float4 (x0, y0, x1, y1) per test
-        for (int i = 0; i < 1024; ++i) pat[i] = (float)k_pattern_host[i];
+        float pat[1024];                                     // the rBRIEF pattern as float4 (x0, y0, x1, y1) per test,
+        for (int t = 0; t < 8; ++t)                          // transposed to [t][lane]: test lane * 8 + t  (k_describe)
+            for (int lane = 0; lane < 32; ++lane)
+                for (int k = 0; k < 4; ++k) pat[(t * 32 + lane) * 4 + k] = (float)k_pattern_host[(lane * 8 + t) * 4 + k];
         if (cudaMemcpy(c->pattern.p, pat, sizeof pat, cudaMemcpyHostToDevice) != cudaSuccess) return bail(ORBX_E_CUDA);
     }
     if (cudaMemset(c->status.p, 0, sizeof(int) * B) != cudaSuccess) return bail(ORBX_E_CUDA);

@@ -14,6 +14,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include "orbx_geom.h"
 
 namespace orbx {
@@ -736,17 +737,18 @@ __device__ __forceinline__ float sin_poly_d(double x, double x2)
     const double s = __dadd_rn(x, __dmul_rn(x3, S0));
     return (float)__dadd_rn(s, __dmul_rn(x7, s1));
 }
-__device__ __forceinline__ float cos_poly_d(double x2, double sg)
+__device__ __forceinline__ float cos_poly_d(double x2)
 {
     const double C0 = 1.0, C1 = -0x1.ffffffd0c621cp-2, C2 = 0x1.55553e1068f19p-5, C3 = -0x1.6c087e89a359dp-10, C4 = 0x1.99343027bf8c3p-16;
-    const double c0 = C0 * sg, c1v = C1 * sg, c2v = C2 * sg, c3v = C3 * sg, c4v = C4 * sg;   // exact sign flips
     const double x4 = __dmul_rn(x2, x2);
-    const double c2 = __dadd_rn(c3v, __dmul_rn(x2, c4v));
-    const double c1 = __dadd_rn(c0, __dmul_rn(x2, c1v));
+    const double c2 = __dadd_rn(C3, __dmul_rn(x2, C4));
+    const double c1 = __dadd_rn(C0, __dmul_rn(x2, C1));
     const double x6 = __dmul_rn(x4, x2);
-    const double c = __dadd_rn(c1, __dmul_rn(x4, c2v));
+    const double c = __dadd_rn(c1, __dmul_rn(x4, C2));
     return (float)__dadd_rn(c, __dmul_rn(x6, c2));
 }
+// glibc negates the polynomial's coefficients (cos) or its argument (sin) for the quadrant sign; round-to-nearest is
+// sign-symmetric, so negating the float result is bit-identical and both polynomials are evaluated once, unsigned.
 __device__ __forceinline__ void glibc_sincosf(float ang, float* sn, float* cs)
 {
     const unsigned top = (__float_as_uint(ang) >> 20) & 0x7ffu;
@@ -755,17 +757,19 @@ __device__ __forceinline__ void glibc_sincosf(float ang, float* sn, float* cs)
         if (top < ((0x39800000u >> 20) & 0x7ffu)) { *sn = ang; *cs = 1.0f; return; }   // |ang| < 2^-12
         const double x2 = __dmul_rn(x, x);
         *sn = sin_poly_d(x, x2);
-        *cs = cos_poly_d(x2, 1.0);
+        *cs = cos_poly_d(x2);
         return;
     }
     const double r = __dmul_rn(x, 0x1.45F306DC9C883p+23);
     const int n = (__double2int_rz(r) + 0x800000) >> 24;
     x = __dsub_rn(x, __dmul_rn((double)n, 0x1.921FB54442D18p0));
     const double x2 = __dmul_rn(x, x);
-    const double s = ((n & 3) == 1 || (n & 3) == 2) ? -1.0 : 1.0;
-    const double tsg = (n & 2) ? -1.0 : 1.0;
-    if (n & 1) { *sn = cos_poly_d(x2, tsg); *cs = sin_poly_d(x * s, x2); }
-    else       { *sn = sin_poly_d(x * s, x2); *cs = cos_poly_d(x2, tsg); }
+    const float ps = sin_poly_d(x, x2), pc = cos_poly_d(x2);
+    const unsigned sneg = ((n & 3) == 1 || (n & 3) == 2) ? 0x80000000u : 0u;   // sign applied to the sine polynomial
+    const unsigned cneg = (n & 2) ? 0x80000000u : 0u;                          // ... to the cosine polynomial
+    const float s_ = __uint_as_float(__float_as_uint(ps) ^ sneg), c_ = __uint_as_float(__float_as_uint(pc) ^ cneg);
+    if (n & 1) { *sn = c_; *cs = s_; }
+    else       { *sn = s_; *cs = c_; }
 }
 
 // ------------------------------------------------------------------------------------------------ A.8 blur
@@ -787,8 +791,58 @@ __device__ __forceinline__ uint32_t ldg_u32_now(const void* p) { uint32_t v; asm
 
 __device__ __forceinline__ float u8f(uint32_t w, uint32_t sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f; }
 
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi)
+{
+    return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float f2_lo(unsigned long long v) { return __uint_as_float((unsigned)v); }
+__device__ __forceinline__ float f2_hi(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
+
+// Packed-FP32 version: Blackwell's FFMA2 / FMUL2 / FADD2 do two IEEE-rounded FP32 operations per issue slot, so the
+// thread's 8 columns are held as 4 packs (column m, column m + 4).  With that pairing every tap of the row pass reads
+// an aligned register pair P(i) = (p[i], p[i+4]), i = 0..9, built once per source row straight from the loaded words
+// (PRMT into the mantissa of 2^23, one FADD2 with -2^23 converts both halves exactly).  No mul feeds an add here (the
+// pattern ptxas would contract): products feed FMA addends, sums feed FMA multiplicands.
+constexpr int BLUR_DEPTH = 12;         // source rows in flight per thread (cp.async ring slots)
+__device__ __forceinline__ void cp_async_8(unsigned dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds_v4(unsigned addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u64_zero(unsigned addr) { asm volatile("st.shared.v2.u32 [%0], {%1, %1};" :: "r"(addr), "r"(0u) : "memory"); }
+// one source row of a thread: bytes x0-4 .. x0+11 -> 16 bytes of its ring slot (the second half may lie past the row)
+__device__ __forceinline__ void blur_cp_row(unsigned dst, const uint8_t* src, bool hi_ok)
+{
+    cp_async_8(dst, src);
+    if (hi_ok) cp_async_8(dst + 8u, src + 8);
+    else sts_u64_zero(dst + 8u);
+}
+
 __global__ void __launch_bounds__(BLUR_NT) k_blur(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur)
 {
+    __shared__ __align__(16) uint8_t s_ring[BLUR_DEPTH * BLUR_NT * 16];
     const int f = blockIdx.y;
     int l = 0;
 #pragma unroll 1
@@ -801,44 +855,68 @@ __global__ void __launch_bounds__(BLUR_NT) k_blur(const __grid_constant__ Geom g
     const int ye = min(ys + BLUR_RH, L.h - 13);
     if ((int)blockIdx.x - L.blur0 >= L.nblur || ys >= ye) return;
     const float k0 = __int_as_float(0x3d8fafb1), k1 = __int_as_float(0x3e06387e), k2 = __int_as_float(0x3e434a39), k3 = __int_as_float(0x3e5d4ae0);
+    const unsigned long long K0 = f2_pack(k0, k0), K1 = f2_pack(k1, k1), K2 = f2_pack(k2, k2), K3 = f2_pack(k3, k3);
+    const unsigned long long NEG23 = f2_pack(-8388608.0f, -8388608.0f), RND = f2_pack(12582912.0f, 12582912.0f);
     const uint8_t* src = pyr + (size_t)f * g.pyr_frame + L.img_off + (size_t)(ys - 3) * L.pitch + (x0 - 4);
     uint8_t* dst = blur + (size_t)f * g.pyr_frame + L.img_off + (size_t)ys * L.pitch + x0;
     const bool hi_ok = x0 + 4 < L.pitch;                                          // second 8-byte load inside the row
     const int nrows = (ye - ys) + 6;
-    float w[8][7];
+    unsigned long long w[4][7];
+    // Source rows stream through a thread-private shared-memory ring filled by cp.async (LDGSTS): BLUR_DEPTH rows are
+    // in flight per thread with no register and -- the point -- no scoreboard cost (a warp has six scoreboards, so 14
+    // register loads in flight end up sharing them and the oldest load waits for the youngest).  A thread reads back
+    // only the 16 bytes it copied itself, so cp.async.wait_group is all the synchronisation there is.
+    const unsigned ring = (unsigned)__cvta_generic_to_shared(s_ring) + threadIdx.x * 16u;
+#pragma unroll
+    for (int d = 0; d < BLUR_DEPTH; ++d) {
+        if (d < nrows) blur_cp_row(ring + d * (BLUR_NT * 16u), src + (size_t)d * L.pitch, hi_ok);
+        cp_async_commit();
+    }
+    src += (size_t)BLUR_DEPTH * L.pitch;
+    int slot = 0;                                                                  // ring slot of source row r
 #pragma unroll 1
     for (int r0 = 0; r0 < nrows; r0 += 7) {
 #pragma unroll
         for (int k = 0; k < 7; ++k) {
             const int r = r0 + k;
             if (r < nrows) {
-                const uint2 a = __ldg(reinterpret_cast<const uint2*>(src));
-                const uint2 b = hi_ok ? __ldg(reinterpret_cast<const uint2*>(src) + 1) : make_uint2(0u, 0u);
+                cp_async_wait<BLUR_DEPTH - 1>();                                   // row r has landed
+                const unsigned sa = ring + slot * (BLUR_NT * 16u);
+                const uint4 ab = lds_v4(sa);
+                const uint2 a = make_uint2(ab.x, ab.y), b = make_uint2(ab.z, ab.w);
+                if (r + BLUR_DEPTH < nrows) blur_cp_row(sa, src, hi_ok);           // refill the slot with row r + DEPTH
+                cp_async_commit();
                 src += L.pitch;
-                float p[14];                                                       // pixels x0-3 .. x0+10
-                p[0] = u8f(a.x, 0x7651); p[1] = u8f(a.x, 0x7652); p[2] = u8f(a.x, 0x7653);
-                p[3] = u8f(a.y, 0x7650); p[4] = u8f(a.y, 0x7651); p[5] = u8f(a.y, 0x7652); p[6] = u8f(a.y, 0x7653);
-                p[7] = u8f(b.x, 0x7650); p[8] = u8f(b.x, 0x7651); p[9] = u8f(b.x, 0x7652); p[10] = u8f(b.x, 0x7653);
-                p[11] = u8f(b.y, 0x7650); p[12] = u8f(b.y, 0x7651); p[13] = u8f(b.y, 0x7652);
+                slot = slot + 1 == BLUR_DEPTH ? 0 : slot + 1;
+                const uint32_t W[4] = {a.x, a.y, b.x, b.y};                        // bytes x0-4 .. x0+11; pixel i = x0-3+i is byte i+1
+                unsigned long long P[10];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float acc = __fmul_rn(k0, p[j]);
-                    acc = __fmaf_rn(p[j + 1], k1, acc); acc = __fmaf_rn(p[j + 2], k2, acc); acc = __fmaf_rn(p[j + 3], k3, acc);
-                    acc = __fmaf_rn(p[j + 4], k2, acc); acc = __fmaf_rn(p[j + 5], k1, acc); acc = __fmaf_rn(p[j + 6], k0, acc);
-                    w[j][k] = acc;                                                 // window slot of source row r is r % 7 == k
+                for (int i = 0; i < 10; ++i) {
+                    const uint32_t lo = __byte_perm(W[(i + 1) >> 2], 0x4B000000u, 0x7650u | ((i + 1) & 3));
+                    const uint32_t hi = __byte_perm(W[(i + 5) >> 2], 0x4B000000u, 0x7650u | ((i + 5) & 3));
+                    P[i] = f2_add((unsigned long long)lo | ((unsigned long long)hi << 32), NEG23);
+                }
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    unsigned long long acc = f2_mul(K0, P[m]);
+                    acc = f2_fma(P[m + 1], K1, acc); acc = f2_fma(P[m + 2], K2, acc); acc = f2_fma(P[m + 3], K3, acc);
+                    acc = f2_fma(P[m + 4], K2, acc); acc = f2_fma(P[m + 5], K1, acc); acc = f2_fma(P[m + 6], K0, acc);
+                    w[m][k] = acc;                                                 // window slot of source row r is r % 7 == k
                 }
                 if (r >= 6) {
-                    uint32_t o0 = 0, o1 = 0;
+                    uint32_t q[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float o = __fmul_rn(k3, w[j][(k + 4) % 7]);                                          // row r-3
-                        o = __fmaf_rn(__fadd_rn(w[j][(k + 5) % 7], w[j][(k + 3) % 7]), k2, o);              // r-2, r-4
-                        o = __fmaf_rn(__fadd_rn(w[j][(k + 6) % 7], w[j][(k + 2) % 7]), k1, o);              // r-1, r-5
-                        o = __fmaf_rn(__fadd_rn(w[j][k], w[j][(k + 1) % 7]), k0, o);                         // r,   r-6
-                        const uint32_t q = (uint32_t)(__float_as_int(__fadd_rn(o, 12582912.0f)) & 0xff);    // rint via 1.5 * 2^23
-                        if (j < 4) o0 |= q << (8 * j); else o1 |= q << (8 * (j - 4));
+                    for (int m = 0; m < 4; ++m) {
+                        unsigned long long o = f2_mul(K3, w[m][(k + 4) % 7]);                                   // row r-3
+                        o = f2_fma(f2_add(w[m][(k + 5) % 7], w[m][(k + 3) % 7]), K2, o);                        // r-2, r-4
+                        o = f2_fma(f2_add(w[m][(k + 6) % 7], w[m][(k + 2) % 7]), K1, o);                        // r-1, r-5
+                        o = f2_fma(f2_add(w[m][k], w[m][(k + 1) % 7]), K0, o);                                  // r,   r-6
+                        const unsigned long long rb = f2_add(o, RND);                                           // rint via 1.5 * 2^23
+                        q[m] = (uint32_t)rb; q[m + 4] = (uint32_t)(rb >> 32);
                     }
-                    reinterpret_cast<uint32_t*>(dst)[0] = o0;
+                    const uint32_t o0 = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+                    const uint32_t o1 = __byte_perm(__byte_perm(q[4], q[5], 0x0040), __byte_perm(q[6], q[7], 0x0040), 0x5410);
+                    reinterpret_cast<uint32_t*>(dst)[0] = o0;                                                   // x0 = 4 mod 8: two word stores
                     reinterpret_cast<uint32_t*>(dst)[1] = o1;
                     dst += L.pitch;
                 }
@@ -848,16 +926,33 @@ __global__ void __launch_bounds__(BLUR_NT) k_blur(const __grid_constant__ Geom g
 }
 
 // ------------------------------------------------------------------------------------------------ A.7 / A.9 / A.10 describe
-// One warp = one final keypoint (no block-level sync): IC moments over the radius-15 disc of the unblurred level
-// (lane = column, shuffle reduction), fastAtan2, glibc-exact sin/cos, then the 37x37 window of the blurred level is
-// staged in shared memory with aligned word loads and the 256 steered tests are sampled from it
-// (lane = descriptor byte).  cvRound of the rotated coordinates is the exact magic-number add (|v| < 2^22).
+// One warp = DESC_KPW final keypoints, one after the other (no block-level sync).  Per keypoint: IC moments over the
+// radius-15 disc of the unblurred level (lane = column, shuffle reduction), fastAtan2, glibc-exact sin/cos, then the
+// 37x37 window of the blurred level is staged in shared memory with aligned word loads and the 256 steered tests are
+// sampled from it (lane = descriptor byte).
+//   * the lane's 8 test pairs live in REGISTERS for the whole warp lifetime (pattern table transposed on the host to
+//     [t][lane], read once with fully coalesced 128-bit loads) -- a per-keypoint gather of 128-byte-strided float4s
+//     costs 32 L1 wavefronts per load and made the LSU the bound;
+//   * the products of the rotation are packed FMUL2 (fma/mul/add .f32x2 are IEEE per half); the subtraction / addition
+//     stays scalar because ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false;
+//   * cvRound of the rotated coordinates is the exact magic-number add (|v| < 2^22); the window origin (+18, +18: even,
+//     so ties-to-even is unchanged) rides in the magic constant, so the sample address is one IMAD + one IADD;
+//   * the level of a slot comes from a warp scan of the 8 per-level counts (ballot + popc).
 // Keypoint records and descriptors leave as coalesced stores.
-constexpr int DESC_KPB = 4;            // keypoints (warps) per CTA
+constexpr int DESC_KPB = 4;            // warps per CTA
+constexpr int DESC_KPW = 4;            // keypoints per warp
 constexpr int DESC_NT = DESC_KPB * 32;
 constexpr int DWIN = 37, DWORDS = 16;  // staged window: 37 rows x 16 words (12 used: 48 bytes >= 37 + 3 alignment slack)
 
-__global__ void __launch_bounds__(DESC_NT) k_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr,
+__device__ __forceinline__ int dp4a_us(unsigned a_u8x4, unsigned b_s8x4, int c)       // sum of u8 * s8 products + c
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
+    return d;
+}
+__device__ __forceinline__ unsigned lds_u8(unsigned addr) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+
+__global__ void __launch_bounds__(DESC_NT, 6) k_describe(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr,
                                                       const uint8_t* __restrict__ blur, const Elem* __restrict__ work,
                                                       const int* __restrict__ fincnt, const float4* __restrict__ pattern,
                                                       float* __restrict__ kps_out, uint8_t* __restrict__ desc_out,
@@ -865,99 +960,148 @@ __global__ void __launch_bounds__(DESC_NT) k_describe(const __grid_constant__ Ge
 {
     __shared__ uint32_t s_win[DESC_KPB][(DWIN + 1) * DWORDS];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, f = blockIdx.y;
-    const int slot = blockIdx.x * DESC_KPB + wid;
-    int total = 0, lvl = -1, idx = 0;
-    {
-        int s = slot;
-        for (int l = 0; l < g.nlevels; ++l) {
-            const int c = __ldg(fincnt + f * g.nlevels + l);
-            total += c;
-            if (lvl < 0) { if (s < c) { lvl = l; idx = s; } else s -= c; }
-        }
-    }
+    // ---- per-level counts -> inclusive prefix across lanes (lane l <-> level l)
+    int pre = lane < g.nlevels ? __ldg(fincnt + f * g.nlevels + lane) : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, pre, d); if (lane >= d) pre += o; }
+    const int total = __shfl_sync(0xffffffffu, pre, 31);
     if (blockIdx.x == 0 && threadIdx.x == 0) counts_out[f] = total;
-    if (slot >= min(total, cap) || lvl < 0) return;          // warp-uniform
-    const LevelGeom& L = g.L[lvl];
-    const Elem e = work[(size_t)f * g.ws_frame + L.ws_off + idx];
-    const int x = (int)(e.pos & 0xffffu), y = (int)(e.pos >> 16);
-    const int pitch = L.pitch;
-    const uint8_t* img = pyr + (size_t)f * g.pyr_frame + L.img_off;
-    const uint8_t* bimg = blur + (size_t)f * g.pyr_frame + L.img_off;
-
-    // ---- stage the blurred window rows y-18 .. y+18, bytes (x-18) .. (x+18), as aligned words; 2 rows per step
-    const int xa = (x - 18) & ~3, sh = (x - 18) & 3;
+    const int nkp = min(total, cap);
+    const int slot0 = blockIdx.x * (DESC_KPB * DESC_KPW) + wid;
+    if (slot0 >= nkp) return;                                // warp-uniform
+    // ---- this lane's 8 test pairs: (x0, x1) and (y0, y1) packs
+    unsigned long long PX[8], PY[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const float4 pt = __ldg(pattern + t * 32 + lane);
+        PX[t] = f2_pack(pt.x, pt.z);
+        PY[t] = f2_pack(pt.y, pt.w);
+    }
     uint32_t* win = s_win[wid];
+    const unsigned win_s = (unsigned)__cvta_generic_to_shared(win);
+    // IC disc: lane <-> column u = lane - 15 (lane 31 idle); icmask[j] keeps the rows 4j .. 4j+3 of that column inside it
+    const int icu = min(lane, 30) - 15;
+    uint32_t icmask[8];
     {
-        const int c = lane & 15, half = lane >> 4;
-        const bool on = c < 12 && xa + c * 4 < pitch;
-        const uint8_t* p = bimg + (size_t)(y - 18 + half) * pitch + xa + (on ? c * 4 : 0);
-        uint32_t* d = win + half * DWORDS + c;
-#pragma unroll
-        for (int it = 0; it < (DWIN + 1) / 2; ++it, p += 2 * pitch, d += 2 * DWORDS) {   // rows 2*it + half; row 37 is padding
-            uint32_t v = 0;
-            if (on && (2 * it + half) < DWIN) v = __ldg(reinterpret_cast<const uint32_t*>(p));
-            *d = v;
-        }
-    }
-    // ---- IC moments on the unblurred level: lane <-> column u = lane - 15.  All 31 rows are loaded first (every
-    //      address is inside the level: the disc radius 15 is below the 31-px border), so the loads are in flight
-    //      together; the disc shape umax[|v|] is applied afterwards with compile-time thresholds.
-    int m10 = 0, m01 = 0;
-    {
-        const int u = min(lane, 30) - 15, au = u < 0 ? -u : u;
-        const uint8_t* p = img + (size_t)(y - 15) * pitch + (x + u);
-        int I[31];
-#pragma unroll
-        for (int k = 0; k < 31; ++k) I[k] = (int)__ldg(p + (size_t)k * pitch);
         constexpr int UMAX[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-        int colsum = 0;
+        const int au = icu < 0 ? -icu : icu;
 #pragma unroll
-        for (int k = 0; k < 31; ++k) {
-            const int vv = k - 15;
-            const int Iv = (au <= UMAX[vv < 0 ? -vv : vv]) ? I[k] : 0;
-            colsum += Iv; m01 += vv * Iv;
-        }
-        m10 = u * colsum;
-        if (lane == 31) { m10 = 0; m01 = 0; }
-    }
+        for (int j = 0; j < 8; ++j) {
+            uint32_t m = 0;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, d); m01 += __shfl_xor_sync(0xffffffffu, m01, d); }
-    const float ang = fast_atan2_deg((float)m01, (float)m10);
-    float sn, cs;
-    glibc_sincosf(__fmul_rn(ang, __int_as_float(0x3c8efa35)), &sn, &cs);
-    __syncwarp();
-    // ---- steered rBRIEF: lane <-> descriptor byte
-    {
-        const uint8_t* B = reinterpret_cast<const uint8_t*>(win) + 18 * (DWORDS * 4) + 18 + sh;
-        constexpr float MAGIC = 12582912.0f;                 // 1.5 * 2^23: (v + MAGIC) holds rint(v) in its low mantissa bits
-        constexpr int MBITS = 0x4B400000;
-        unsigned byte = 0;
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            const float4 pt = __ldg(pattern + lane * 8 + t);
-            const float fx0 = __fsub_rn(__fmul_rn(pt.x, cs), __fmul_rn(pt.y, sn));
-            const float fy0 = __fadd_rn(__fmul_rn(pt.x, sn), __fmul_rn(pt.y, cs));
-            const float fx1 = __fsub_rn(__fmul_rn(pt.z, cs), __fmul_rn(pt.w, sn));
-            const float fy1 = __fadd_rn(__fmul_rn(pt.z, sn), __fmul_rn(pt.w, cs));
-            const int ix0 = __float_as_int(__fadd_rn(fx0, MAGIC)) - MBITS, iy0 = __float_as_int(__fadd_rn(fy0, MAGIC)) - MBITS;
-            const int ix1 = __float_as_int(__fadd_rn(fx1, MAGIC)) - MBITS, iy1 = __float_as_int(__fadd_rn(fy1, MAGIC)) - MBITS;
-            const int t0 = B[iy0 * (DWORDS * 4) + ix0], t1 = B[iy1 * (DWORDS * 4) + ix1];
-            byte |= (unsigned)(t0 < t1) << t;
-        }
-        const size_t o = (size_t)f * cap + slot;
-        desc_out[o * 32 + lane] = (uint8_t)byte;
-        if (lane < 7) {
-            float val;
-            switch (lane) {
-                case 0: val = __fmul_rn((float)x, L.scale); break;
-                case 1: val = __fmul_rn((float)y, L.scale); break;
-                case 2: val = __fmul_rn(31.0f, L.scale); break;
-                case 3: val = ang; break;
-                case 4: val = e.response; break;
-                case 5: val = __int_as_float(lvl); break;
-                default: val = __int_as_float(-1); break;
+            for (int b = 0; b < 4; ++b) {
+                const int k = 4 * j + b, vv = k - 15;
+                if (k < 31 && lane < 31 && au <= UMAX[vv < 0 ? -vv : vv]) m |= 0xFFu << (8 * b);
             }
-            kps_out[o * 7 + lane] = val;
+            icmask[j] = m;
+        }
+    }
+
+#pragma unroll 1
+    for (int it = 0; it < DESC_KPW; ++it) {
+        const int slot = slot0 + it * DESC_KPB;
+        if (slot >= nkp) break;                              // warp-uniform
+        const int lvl = __popc(__ballot_sync(0xffffffffu, pre <= slot) & ((1u << g.nlevels) - 1u));
+        const int before = __shfl_sync(0xffffffffu, pre, max(lvl - 1, 0));
+        const int idx = slot - (lvl > 0 ? before : 0);
+        const LevelGeom& L = g.L[lvl];
+        const Elem e = work[(size_t)f * g.ws_frame + L.ws_off + idx];
+        const int x = (int)(e.pos & 0xffffu), y = (int)(e.pos >> 16);
+        const int pitch = L.pitch;
+#ifdef ORBX_DEBUG
+        if (lane == 0 && (lvl >= g.nlevels || idx < 0 || x < 31 || y < 31 || x >= L.w - 31 || y >= L.h - 31))
+            printf("describe: bad keypoint f=%d slot=%d lvl=%d idx=%d x=%d y=%d total=%d\n", f, slot, lvl, idx, x, y, total);
+#endif
+        const uint8_t* img = pyr + (size_t)f * g.pyr_frame + L.img_off;
+        const uint8_t* bimg = blur + (size_t)f * g.pyr_frame + L.img_off;
+
+        // ---- stage the blurred window rows y-18 .. y+18, bytes (x-18) .. (x+18), as aligned words; 2 rows per step
+        const int xa = (x - 18) & ~3, sh = (x - 18) & 3;
+        __syncwarp();                                        // the previous keypoint's samples are done
+        {
+            const int c = lane & 15, half = lane >> 4;
+            const bool on = c < 12 && xa + c * 4 < pitch;
+            const uint8_t* p = bimg + (size_t)(y - 18 + half) * pitch + xa + (on ? c * 4 : 0);
+            uint32_t* d = win + half * DWORDS + c;
+            uint32_t v[(DWIN + 1) / 2];
+#pragma unroll
+            for (int r = 0; r < (DWIN + 1) / 2; ++r, p += 2 * pitch) {     // rows 2*r + half; row 37 is padding
+                v[r] = 0;
+                if (on && (2 * r + half) < DWIN) v[r] = ldg_u32_now(p);
+            }
+#pragma unroll
+            for (int r = 0; r < (DWIN + 1) / 2; ++r) d[r * 2 * DWORDS] = v[r];
+        }
+        // ---- IC moments on the unblurred level: lane <-> column u = lane - 15.  All 31 rows are loaded first (every
+        //      address is inside the level: the disc radius 15 is below the 31-px border), so the loads are in flight
+        //      together; the disc shape umax[|v|] is applied afterwards with compile-time thresholds.
+        int m10 = 0, m01 = 0;
+        {
+            const uint8_t* p = img + (size_t)(y - 15) * pitch + (x + icu);
+            uint32_t I[32];
+#pragma unroll
+            for (int k = 0; k < 31; ++k, p += pitch) I[k] = ldg_u8_now(p);
+            I[31] = 0;
+            int colsum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                // rows 4j .. 4j+3 of this column in one word; the disc mask and the row coefficients v = k - 15 are bytes
+                const uint32_t w = (I[4 * j] | (I[4 * j + 1] << 8) | (I[4 * j + 2] << 16) | (I[4 * j + 3] << 24)) & icmask[j];
+                constexpr int v0 = 4 * 0 - 15;
+                const int vj = v0 + 4 * j;
+                const uint32_t coef = (uint32_t)(vj & 255) | ((uint32_t)((vj + 1) & 255) << 8) | ((uint32_t)((vj + 2) & 255) << 16) | ((uint32_t)((vj + 3) & 255) << 24);
+                colsum = dp4a_us(w, 0x01010101u, colsum);
+                m01 = dp4a_us(w, coef, m01);
+            }
+            m10 = icu * colsum;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, d); m01 += __shfl_xor_sync(0xffffffffu, m01, d); }
+        const float ang = fast_atan2_deg((float)m01, (float)m10);
+        float sn, cs;
+        glibc_sincosf(__fmul_rn(ang, __int_as_float(0x3c8efa35)), &sn, &cs);
+        __syncwarp();                                        // window staged
+        // ---- steered rBRIEF: lane <-> descriptor byte
+        {
+            // (v + MAGIC) holds rint(v) in its low mantissa bits; MAGIC = 1.5 * 2^23 + 18 moves the origin to the
+            // window's corner.  addr = 64 * bits(y) + bits(x) + cbase  (mod 2^32)
+            const unsigned long long MAGIC2 = f2_pack(12582930.0f, 12582930.0f);
+            const unsigned long long cs2 = f2_pack(cs, cs), sn2 = f2_pack(sn, sn);
+            const unsigned cbase = win_s + (unsigned)sh - 65u * 0x4B400000u;   // the +18s stay: 64 * (iy + 18) + (ix + 18)
+            unsigned byte = 0;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                const unsigned long long xc = f2_mul(PX[t], cs2), ys = f2_mul(PY[t], sn2);
+                const unsigned long long xs = f2_mul(PX[t], sn2), yc = f2_mul(PY[t], cs2);
+                const float fx0 = __fsub_rn(f2_lo(xc), f2_lo(ys)), fx1 = __fsub_rn(f2_hi(xc), f2_hi(ys));
+                const float fy0 = __fadd_rn(f2_lo(xs), f2_lo(yc)), fy1 = __fadd_rn(f2_hi(xs), f2_hi(yc));
+                const unsigned long long bx = f2_add(f2_pack(fx0, fx1), MAGIC2), by = f2_add(f2_pack(fy0, fy1), MAGIC2);
+                const unsigned a0 = (unsigned)by * 64u + (unsigned)bx + cbase;
+                const unsigned a1 = (unsigned)(by >> 32) * 64u + (unsigned)(bx >> 32) + cbase;
+#ifdef ORBX_DEBUG
+                if (a0 - win_s >= (DWIN + 1) * DWORDS * 4 || a1 - win_s >= (DWIN + 1) * DWORDS * 4) {
+                    printf("describe: bad lds f=%d slot=%d lane=%d t=%d a0=%u a1=%u sn=%f cs=%f ang=%f m01=%d m10=%d\n", f, slot, lane, t, a0 - win_s, a1 - win_s, sn, cs, ang, m01, m10);
+                    continue;
+                }
+#endif
+                const unsigned t0 = lds_u8(a0), t1 = lds_u8(a1);
+                byte |= (unsigned)(t0 < t1) << t;
+            }
+            const size_t o = (size_t)f * cap + slot;
+            desc_out[o * 32 + lane] = (uint8_t)byte;
+            if (lane < 7) {
+                float val;
+                switch (lane) {
+                    case 0: val = __fmul_rn((float)x, L.scale); break;
+                    case 1: val = __fmul_rn((float)y, L.scale); break;
+                    case 2: val = __fmul_rn(31.0f, L.scale); break;
+                    case 3: val = ang; break;
+                    case 4: val = e.response; break;
+                    case 5: val = __int_as_float(lvl); break;
+                    default: val = __int_as_float(-1); break;
+                }
+                kps_out[o * 7 + lane] = val;
+            }
         }
     }
 }
