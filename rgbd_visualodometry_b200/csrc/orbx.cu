@@ -214,7 +214,7 @@ void stage_mark(orbx_ctx* c, int i)
 // The extraction pipeline on device-resident frames; everything asynchronous on c->stream.
 // The kernel sequence for frames [f0, f0 + nb) on stream `st`.  Every buffer is frame-major, so a frame range is
 // just a base-pointer offset.  `side` (may be null) is a second stream the blur is queued on behind FAST.
-int run_extract_range(orbx_ctx* c, cudaStream_t st, cudaStream_t side, cudaEvent_t ev_a, cudaEvent_t ev_b, bool marks, int f0, int nb,
+int run_extract_range(orbx_ctx* c, cudaStream_t st, cudaStream_t side, cudaEvent_t ev_a, cudaEvent_t ev_b, bool marks, bool fused, int f0, int nb,
                       const uint8_t* d_imgs, size_t step, size_t frame_stride, int channels, float* d_kps, uint8_t* d_desc, int cap,
                       int* d_counts)
 {
@@ -236,7 +236,7 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, cudaStream_t side, cudaEvent
 
     if (marks) stage_mark(c, 0);
     const int aligned4 = ((reinterpret_cast<uintptr_t>(d_imgs) | step | frame_stride) & 3) == 0;
-    if (nb >= FUSED_PYR_MIN_BATCH) {
+    if (fused) {
         // the batch alone fills the GPU: one CTA per frame runs gray + the whole level chain in a single launch
         if (channels == 3) k_gray_pyr<3><<<B, GP_NT, 0, st>>>(d_imgs, frame_stride, step, aligned4, g, pyr, tabs);
         else               k_gray_pyr<1><<<B, GP_NT, 0, st>>>(d_imgs, frame_stride, step, aligned4, g, pyr, tabs);
@@ -244,10 +244,11 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, cudaStream_t side, cudaEvent
         if (marks) stage_mark(c, 1);
     } else {
         {
-            const dim3 blk(64, 4);
-            const dim3 grd((unsigned)((g.L[0].pitch / 4 + 63) / 64), (unsigned)((g.L[0].h + 3) / 4), B);
-            if (channels == 3) k_gray<3><<<grd, blk, 0, st>>>(d_imgs, frame_stride, step, aligned4, g, pyr);
-            else               k_gray<1><<<grd, blk, 0, st>>>(d_imgs, frame_stride, step, aligned4, g, pyr);
+            const int aligned16 = ((reinterpret_cast<uintptr_t>(d_imgs) | step | frame_stride) & 15) == 0;
+            const dim3 blk(32, 8);
+            const dim3 grd((unsigned)((g.L[0].pitch / 16 + 31) / 32), (unsigned)((g.L[0].h + 7) / 8), B);
+            if (channels == 3) k_gray<3><<<grd, blk, 0, st>>>(d_imgs, frame_stride, step, aligned16, g, pyr);
+            else               k_gray<1><<<grd, blk, 0, st>>>(d_imgs, frame_stride, step, aligned16, g, pyr);
             ++c->launches;
         }
         if (marks) stage_mark(c, 1);
@@ -274,7 +275,7 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, cudaStream_t side, cudaEvent
         CU(cudaEventRecord(ev_b, side));
     }
     if (marks) stage_mark(c, 3);
-    k_select<<<dim3((unsigned)g.nlevels, B), SEL_NT, 0, st>>>(g, pyr, rowcnt, rowent, work, selpos, fincnt, status);
+    k_select<<<dim3(B, (unsigned)g.nlevels), SEL_NT, 0, st>>>(g, pyr, rowcnt, rowent, work, selpos, fincnt, status);
     ++c->launches;
     if (marks) stage_mark(c, 4);
     if (!side && g.total_blur > 0 && !(dbg_skip & 1)) {
@@ -303,9 +304,11 @@ int run_extract(orbx_ctx* c, const uint8_t* d_imgs, int batch, int w, int h, siz
     CU(cudaMemsetAsync(c->status.p, 0, sizeof(int) * (size_t)batch, c->stream));
     static const int env_lanes = getenv("ORBX_LANES") ? atoi(getenv("ORBX_LANES")) : 3;
     int lanes = std::max(1, std::min(env_lanes, MAX_LANES));
-    if (c->profiling || batch < lanes * LANE_MIN_FRAMES) lanes = 1;
+    if (batch < lanes * LANE_MIN_FRAMES) lanes = 1;
+    const bool fused = batch / lanes >= FUSED_PYR_MIN_BATCH;    // per-stage profiling (one lane) times the same kernels the lanes run
+    if (c->profiling) lanes = 1;
     if (lanes == 1) {
-        rc = run_extract_range(c, c->stream, c->profiling ? nullptr : c->stream2, c->ev_pyr, c->ev_blur, c->profiling, 0, batch, d_imgs, step,
+        rc = run_extract_range(c, c->stream, c->profiling ? nullptr : c->stream2, c->ev_pyr, c->ev_blur, c->profiling, fused, 0, batch, d_imgs, step,
                                frame_stride, channels, d_kps, d_desc, cap, d_counts);
         if (rc) return rc;
     } else {
@@ -314,7 +317,7 @@ int run_extract(orbx_ctx* c, const uint8_t* d_imgs, int batch, int w, int h, siz
             const int f0 = (int)((long)batch * k / lanes), f1 = (int)((long)batch * (k + 1) / lanes);
             cudaStream_t st = k == 0 ? c->stream : c->lane[k];
             if (k > 0) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
-            rc = run_extract_range(c, st, nullptr, nullptr, nullptr, false, f0, f1 - f0, d_imgs, step, frame_stride, channels, d_kps, d_desc, cap, d_counts);
+            rc = run_extract_range(c, st, nullptr, nullptr, nullptr, false, fused, f0, f1 - f0, d_imgs, step, frame_stride, channels, d_kps, d_desc, cap, d_counts);
             if (rc) return rc;
             if (k > 0) { CU(cudaEventRecord(c->ev_join[k], st)); CU(cudaStreamWaitEvent(c->stream, c->ev_join[k], 0)); }
         }
@@ -556,7 +559,7 @@ int orbx_detect_and_compute_batch(orbx_ctx* c, const uint8_t* const* imgs, int b
         for (int i = f0; i < f1; ++i)
             CU(cudaMemcpy2DAsync((uint8_t*)c->in.p + fstride * i, dstep, imgs[i], step, row, (size_t)h, cudaMemcpyHostToDevice, st));
         const bool side = lanes == 1 && !c->profiling;
-        if ((rc = run_extract_range(c, st, side ? c->stream2 : nullptr, c->ev_pyr, c->ev_blur, c->profiling, f0, f1 - f0, (const uint8_t*)c->in.p, dstep,
+        if ((rc = run_extract_range(c, st, side ? c->stream2 : nullptr, c->ev_pyr, c->ev_blur, c->profiling, f1 - f0 >= FUSED_PYR_MIN_BATCH, f0, f1 - f0, (const uint8_t*)c->in.p, dstep,
                                     fstride, channels, (float*)c->kps.p, (uint8_t*)c->desc.p, cap, (int*)c->counts.p)))
             return rc;
         const size_t n = (size_t)(f1 - f0);

@@ -26,46 +26,68 @@ __device__ __forceinline__ unsigned vmax2(unsigned a, unsigned b) { return __vma
 __device__ __forceinline__ unsigned vmax3(unsigned a, unsigned b, unsigned c) { return __vimax3_u16x2(a, b, c); }
 __device__ __forceinline__ unsigned vmin3(unsigned a, unsigned b, unsigned c) { return __vimin3_u16x2(a, b, c); }
 
+// cp.async (LDGSTS): global -> shared copies that cost neither registers nor scoreboards while in flight (a warp has six
+// scoreboards; a deep register-prefetch pipeline ends up sharing them and the oldest load waits for the youngest).
+__device__ __forceinline__ void cp_async_4(unsigned dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_8(unsigned dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds_v4(unsigned addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+
 // ------------------------------------------------------------------------------------------------ A.1 gray
-// g = (3735 B + 19235 G + 9798 R + 16384) >> 15.  One thread = 4 consecutive pixels of one row.
+// g = (3735 B + 19235 G + 9798 R + 16384) >> 15.
+// 4 gray pixels from 12 BGR bytes: coefficients split into high / low bytes so each pixel is two IDP.4A
+//   3735 B + 19235 G + 9798 R + 16384 = 256 (14 B + 75 G + 38 R) + (151 B + 35 G + 70 R) + 16384      (exact)
+__device__ __forceinline__ uint32_t gray4(uint32_t w0, uint32_t w1, uint32_t w2)
+{
+    constexpr uint32_t CH_ = 14u | (75u << 8) | (38u << 16), CL_ = 151u | (35u << 8) | (70u << 16);
+    const uint32_t p0 = w0, p1 = __byte_perm(w0, w1, 0x0543), p2 = __byte_perm(w1, w2, 0x0432), p3 = w2 >> 8;
+    const uint32_t g0 = (__dp4a(p0, CH_, 0u) * 256u + __dp4a(p0, CL_, 16384u)) >> 15;
+    const uint32_t g1 = (__dp4a(p1, CH_, 0u) * 256u + __dp4a(p1, CL_, 16384u)) >> 15;
+    const uint32_t g2 = (__dp4a(p2, CH_, 0u) * 256u + __dp4a(p2, CL_, 16384u)) >> 15;
+    const uint32_t g3 = (__dp4a(p3, CH_, 0u) * 256u + __dp4a(p3, CL_, 16384u)) >> 15;
+    return g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+}
+
+// One thread = 16 consecutive pixels of one row: three 128-bit loads (48 BGR bytes), one 128-bit store -- the kernel
+// is a pure HBM stream (3 bytes in, 1 byte out per pixel).  Unaligned inputs / row tails fall back to byte loads.
 template <int CH>
 __global__ void __launch_bounds__(256) k_gray(const uint8_t* __restrict__ in, unsigned long long frame_stride,
-                                              unsigned long long step, int aligned4, const __grid_constant__ Geom g,
+                                              unsigned long long step, int aligned16, const __grid_constant__ Geom g,
                                               uint8_t* __restrict__ pyr)
 {
     const LevelGeom& L = g.L[0];
-    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     const int f = blockIdx.z;
     if (y >= L.h || x >= L.pitch) return;
     const uint8_t* src = in + (size_t)f * frame_stride + (size_t)y * step + (size_t)x * CH;
-    uint32_t out = 0;
-    if (CH == 3) {
-        if (aligned4 && x + 3 < L.w) {
-            const uint32_t* s4 = reinterpret_cast<const uint32_t*>(src);
-            const uint32_t w0 = __ldg(s4), w1 = __ldg(s4 + 1), w2 = __ldg(s4 + 2);
-            // bytes: b0 g0 r0 b1 | g1 r1 b2 g2 | r2 b3 g3 r3
-            const uint32_t p0 = (3735u * (w0 & 255u) + 19235u * ((w0 >> 8) & 255u) + 9798u * ((w0 >> 16) & 255u) + 16384u) >> 15;
-            const uint32_t p1 = (3735u * (w0 >> 24) + 19235u * (w1 & 255u) + 9798u * ((w1 >> 8) & 255u) + 16384u) >> 15;
-            const uint32_t p2 = (3735u * ((w1 >> 16) & 255u) + 19235u * (w1 >> 24) + 9798u * (w2 & 255u) + 16384u) >> 15;
-            const uint32_t p3 = (3735u * ((w2 >> 8) & 255u) + 19235u * ((w2 >> 16) & 255u) + 9798u * (w2 >> 24) + 16384u) >> 15;
-            out = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+    uint4 out = make_uint4(0u, 0u, 0u, 0u);
+    if (aligned16 && x + 15 < L.w) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        if (CH == 3) {
+            const uint4 a = __ldg(s4), b = __ldg(s4 + 1), c = __ldg(s4 + 2);
+            out = make_uint4(gray4(a.x, a.y, a.z), gray4(a.w, b.x, b.y), gray4(b.z, b.w, c.x), gray4(c.y, c.z, c.w));
         } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (x + k < L.w) {
-                    const uint32_t p = (3735u * __ldg(src + 3 * k) + 19235u * __ldg(src + 3 * k + 1) + 9798u * __ldg(src + 3 * k + 2) + 16384u) >> 15;
-                    out |= p << (8 * k);
-                }
+            out = __ldg(s4);
         }
     } else {
-        if (aligned4 && x + 3 < L.w) out = __ldg(reinterpret_cast<const uint32_t*>(src));
-        else {
+        uint32_t o[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) if (x + k < L.w) out |= (uint32_t)__ldg(src + k) << (8 * k);
-        }
+        for (int k = 0; k < 16; ++k)
+            if (x + k < L.w) {
+                const uint8_t* s = src + (size_t)k * CH;
+                const uint32_t p = CH == 3 ? (3735u * __ldg(s) + 19235u * __ldg(s + 1) + 9798u * __ldg(s + 2) + 16384u) >> 15 : (uint32_t)__ldg(s);
+                o[k >> 2] |= p << (8 * (k & 3));
+            }
+        out = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    *reinterpret_cast<uint32_t*>(pyr + (size_t)f * g.pyr_frame + L.img_off + (size_t)y * L.pitch + x) = out;
+    *reinterpret_cast<uint4*>(pyr + (size_t)f * g.pyr_frame + L.img_off + (size_t)y * L.pitch + x) = out;   // pitch, offsets: multiples of 16
 }
 
 // ------------------------------------------------------------------------------------------------ A.2 pyramid
@@ -143,27 +165,109 @@ __device__ __forceinline__ void pyr_down_item(const Geom& g, int l, int f, int x
     }
 }
 
-// one level per launch (small batches / large frames: plenty of CTAs per level)
-__global__ void __launch_bounds__(128) k_pyr_down(const __grid_constant__ Geom g, int l, uint8_t* pyr, const uint32_t* __restrict__ tabs)
+// One level per launch (the path every lane of a batch takes unless the batch alone fills the GPU).  Same arithmetic
+// as pyr_down_item, restructured around the SOURCE rows: the thread streams the source rows it needs, in order,
+// through a private shared-memory ring filled by cp.async (PYR_DEPTH rows in flight), takes the horizontal pass of
+// each once, and emits an output row as soon as its lower source row has passed.  Load latency sits under the
+// arithmetic of the rows already there instead of in front of every output row.
+constexpr int PYR_DEPTH = 8;
+constexpr int PYR_NT = 32 * PYR_BY;
+__global__ void __launch_bounds__(PYR_NT) k_pyr_down(const __grid_constant__ Geom g, int l, uint8_t* pyr, const uint32_t* __restrict__ tabs)
 {
+    __shared__ __align__(16) uint8_t s_ring[PYR_DEPTH * PYR_NT * 16];
     const LevelGeom& D = g.L[l];
+    const LevelGeom& S = g.L[l - 1];
     const int x = (blockIdx.x * 32 + threadIdx.x) * 4;
     const int ys = (blockIdx.y * PYR_BY + threadIdx.y) * PYR_RH, ye = min(ys + PYR_RH, D.h);
+    const int f = blockIdx.z;
     if (x >= D.pitch || ys >= ye) return;
-    pyr_down_item(g, l, blockIdx.z, x, ys, ye, pyr, tabs);
-}
-
-// 4 gray pixels from 12 BGR bytes: coefficients split into high / low bytes so each pixel is two IDP.4A
-//   3735 B + 19235 G + 9798 R + 16384 = 256 (14 B + 75 G + 38 R) + (151 B + 35 G + 70 R) + 16384      (exact)
-__device__ __forceinline__ uint32_t gray4(uint32_t w0, uint32_t w1, uint32_t w2)
-{
-    constexpr uint32_t CH_ = 14u | (75u << 8) | (38u << 16), CL_ = 151u | (35u << 8) | (70u << 16);
-    const uint32_t p0 = w0, p1 = __byte_perm(w0, w1, 0x0543), p2 = __byte_perm(w1, w2, 0x0432), p3 = w2 >> 8;
-    const uint32_t g0 = (__dp4a(p0, CH_, 0u) * 256u + __dp4a(p0, CL_, 16384u)) >> 15;
-    const uint32_t g1 = (__dp4a(p1, CH_, 0u) * 256u + __dp4a(p1, CL_, 16384u)) >> 15;
-    const uint32_t g2 = (__dp4a(p2, CH_, 0u) * 256u + __dp4a(p2, CL_, 16384u)) >> 15;
-    const uint32_t g3 = (__dp4a(p3, CH_, 0u) * 256u + __dp4a(p3, CL_, 16384u)) >> 15;
-    return g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+    uint8_t* dst = pyr + (size_t)f * g.pyr_frame + D.img_off + (size_t)ys * D.pitch + x;
+    if (x >= D.w) {                                          // row padding: keep it zero
+        for (int y = ys; y < ye; ++y, dst += D.pitch) *reinterpret_cast<uint32_t*>(dst) = 0u;
+        return;
+    }
+    uint32_t coef[4], sh[4];
+    bool hi[4];
+    const int a = (int)(__ldg(tabs + D.xtab + x) & 0xffffu) & ~3;   // aligned source byte all four outputs are addressed from
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t t = (x + k < D.w) ? __ldg(tabs + D.xtab + x + k) : (uint32_t)a;  // padding columns: taps 0 -> output 0
+        const int off = (int)(t & 0xffffu) - a;              // 0 .. 7
+        const uint32_t c1 = t >> 16;
+        coef[k] = (x + k < D.w) ? ((256u - c1) | (c1 << 16)) : 0u;
+        hi[k] = off >= 4;
+        sh[k] = (uint32_t)(off & 3) * 8u;
+    }
+    const bool w2ok = a + 8 < S.pitch;
+    const uint32_t* ytab = tabs + D.ytab;
+    const int s0 = (int)(__ldg(ytab + ys) & 0xffffu);
+    const int s1 = min((int)(__ldg(ytab + ye - 1) & 0xffffu) + 1, S.h - 1);         // last source row needed
+    const uint8_t* src = pyr + (size_t)f * g.pyr_frame + S.img_off + (size_t)s0 * S.pitch + a;
+    const unsigned ring = (unsigned)__cvta_generic_to_shared(s_ring) + (threadIdx.y * 32 + threadIdx.x) * 16u;
+#pragma unroll
+    for (int d = 0; d < PYR_DEPTH; ++d) {
+        if (s0 + d <= s1) {
+            const uint8_t* p = src + (size_t)d * S.pitch;
+            const unsigned sa = ring + d * (PYR_NT * 16u);
+            cp_async_4(sa, p); cp_async_4(sa + 4u, p + 4);
+            if (w2ok) cp_async_4(sa + 8u, p + 8);
+        }
+        cp_async_commit();
+    }
+    src += (size_t)PYR_DEPTH * S.pitch;
+    // Output-row bookkeeping: `emit_at` is the source row at which the pending output row y can be produced
+    // (y1 = min(y0 + 1, S.h - 1)); the taps of row y + 1 are fetched one row ahead.
+    int y = ys;
+    uint32_t ty = __ldg(ytab + y), ty_next = y + 1 < ye ? __ldg(ytab + y + 1) : 0u;
+    int emit_at = min((int)(ty & 0xffffu) + 1, S.h - 1);
+    int to_fetch = (s1 - s0 + 1) - PYR_DEPTH;               // source rows not yet requested
+    unsigned sa = ring;
+    const unsigned ring_end = ring + PYR_DEPTH * (PYR_NT * 16u);
+    PyrRow hA, hB;                                           // horizontal passes of the last two source rows (ping-pong)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { hA.h[k] = 0; hB.h[k] = 0; }
+    // one source row: wait, read, refill the slot, horizontal pass into `hc`, emit what became complete
+    auto step = [&](int s, const PyrRow& hp, PyrRow& hc) {
+        cp_async_wait<PYR_DEPTH - 1>();
+        const uint4 w = lds_v4(sa);
+        if (to_fetch > 0) {
+            cp_async_4(sa, src); cp_async_4(sa + 4u, src + 4);
+            if (w2ok) cp_async_4(sa + 8u, src + 8);
+        }
+        cp_async_commit();
+        --to_fetch;
+        src += S.pitch;
+        sa += PYR_NT * 16u;
+        if (sa == ring_end) sa = ring;
+        const uint32_t w2 = w2ok ? w.z : 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t v = __funnelshift_r(hi[k] ? w.y : w.x, hi[k] ? w2 : w.y, sh[k]);
+            hc.h[k] = __dp2a_lo(coef[k], v, 0u);
+        }
+        while (emit_at == s && y < ye) {                     // (two outputs per source row only when the bottom row clamps)
+            const bool clamped = (int)(ty & 0xffffu) == s;   // y1 == y0: both taps read the last source row
+            const uint32_t cy1 = ty >> 16, cy0 = 256u - cy1;
+            uint32_t out = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t top = clamped ? hc.h[k] : hp.h[k];
+                const uint32_t v = (top * cy0 + hc.h[k] * cy1 + 32768u) >> 16;
+                out |= min(v, 255u) << (8 * k);
+            }
+            *reinterpret_cast<uint32_t*>(dst) = out;
+            dst += D.pitch;
+            ++y;
+            ty = ty_next;
+            emit_at = min((int)(ty & 0xffffu) + 1, S.h - 1);
+            if (y + 1 < ye) ty_next = __ldg(ytab + y + 1);
+        }
+    };
+#pragma unroll 1
+    for (int s = s0; s <= s1; s += 2) {
+        step(s, hA, hB);
+        if (s + 1 <= s1) step(s + 1, hB, hA);
+    }
 }
 
 // Fused gray + whole pyramid, ONE CTA PER FRAME: the level chain l-1 -> l is a dependency only inside a frame, so a
@@ -519,7 +623,7 @@ __device__ int partition_tail_warp(Elem* v, int m, int len, float thr, int lane)
 }
 
 constexpr int SEL_NT = 128;
-constexpr int SEL_SMEM_ELEMS = 3072;
+constexpr int SEL_SMEM_ELEMS = 2048;
 constexpr int SEL_PAR_MIN = 32;        // ranges up to this length are finished by one warp
 
 struct SelShared {
@@ -641,7 +745,7 @@ __device__ __forceinline__ float harris_response(const uint8_t* __restrict__ img
 // -> Harris on the survivors -> retainBest(n_l) on Harris.  The final list is left as the prefix of the level's
 // global workspace; its length goes to fincnt.  The working array (and the partition scratch) lives in shared
 // memory when the level's candidate count fits, else in global memory.
-__global__ void __launch_bounds__(SEL_NT) k_select(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr,
+__global__ void __launch_bounds__(SEL_NT, 8) k_select(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr,
                                                    const uint32_t* __restrict__ rowcnt, const uint32_t* __restrict__ rowent,
                                                    Elem* __restrict__ work, uint32_t* __restrict__ selpos, int* __restrict__ fincnt,
                                                    int* __restrict__ status)
@@ -649,7 +753,9 @@ __global__ void __launch_bounds__(SEL_NT) k_select(const __grid_constant__ Geom 
     __shared__ Elem s_v[SEL_SMEM_ELEMS];
     __shared__ uint16_t s_pos[2 * SEL_SMEM_ELEMS];
     __shared__ SelShared sh;
-    const int l = blockIdx.x, f = blockIdx.y;
+    // grid = (frames, levels): level-major dispatch, so the long level-0 CTAs of every frame start in the first wave and
+    // the short upper levels fill the tail
+    const int l = blockIdx.y, f = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const LevelGeom& L = g.L[l];
     Elem* gv = work + (size_t)f * g.ws_frame + L.ws_off;
@@ -822,15 +928,6 @@ __device__ __forceinline__ float f2_hi(unsigned long long v) { return __uint_as_
 // (PRMT into the mantissa of 2^23, one FADD2 with -2^23 converts both halves exactly).  No mul feeds an add here (the
 // pattern ptxas would contract): products feed FMA addends, sums feed FMA multiplicands.
 constexpr int BLUR_DEPTH = 12;         // source rows in flight per thread (cp.async ring slots)
-__device__ __forceinline__ void cp_async_8(unsigned dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src) : "memory"); }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
-__device__ __forceinline__ uint4 lds_v4(unsigned addr)
-{
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-    return v;
-}
 __device__ __forceinline__ void sts_u64_zero(unsigned addr) { asm volatile("st.shared.v2.u32 [%0], {%1, %1};" :: "r"(addr), "r"(0u) : "memory"); }
 // one source row of a thread: bytes x0-4 .. x0+11 -> 16 bytes of its ring slot (the second half may lie past the row)
 __device__ __forceinline__ void blur_cp_row(unsigned dst, const uint8_t* src, bool hi_ok)
@@ -960,7 +1057,6 @@ __device__ __forceinline__ int dp4a_us(unsigned a_u8x4, unsigned b_s8x4, int c) 
 }
 __device__ __forceinline__ unsigned lds_u8(unsigned addr) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
 __device__ __forceinline__ unsigned lds_u32(unsigned addr) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
-__device__ __forceinline__ void cp_async_4(unsigned dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory"); }
 
 struct DescKp { int x, y, lvl; float response; };
 
