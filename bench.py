@@ -235,17 +235,21 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
     pin_in = torch.from_numpy(frames_np).pin_memory()
     kps_h = torch.zeros((B, CAP, 7), dtype=torch.float32).pin_memory()
     desc_h = torch.zeros((B, CAP, 32), dtype=torch.uint8).pin_memory()
-    best_h = torch.zeros((B, MAP_M, 4), dtype=torch.int32).pin_memory()
     cnt_h = np.zeros(B, np.int32)
     import ctypes as C
     ptrs = (C.c_void_p * B)(*[pin_in[i].data_ptr() for i in range(B)])
 
+    map_pin = torch.from_numpy(map_np).pin_memory()
+    best_hs = [torch.zeros((B, MAP_M, 4), dtype=torch.int32).pin_memory() for _ in range(MATCHES_PER_FRAME)]
+    qptrs = (C.c_void_p * MATCHES_PER_FRAME)(*[map_pin.data_ptr()] * MATCHES_PER_FRAME)
+    nqs = (C.c_int * MATCHES_PER_FRAME)(*[MAP_M] * MATCHES_PER_FRAME)
+    bptrs = (C.c_void_p * MATCHES_PER_FRAME)(*[t.data_ptr() for t in best_hs])
+
     def e2e_step():
-        rc = ctx.lib.orbx_detect_and_compute_batch(ctx.h, ptrs, B, W, H, W * 3, 3, kps_h.data_ptr(), desc_h.data_ptr(), CAP, cnt_h.ctypes.data)
+        # one C-ABI call: frames (host, pinned) -> keypoints, descriptors and the front-end's matches (host, pinned)
+        rc = ctx.lib.orbx_extract_match_batch(ctx.h, ptrs, B, W, H, W * 3, 3, kps_h.data_ptr(), desc_h.data_ptr(), CAP, cnt_h.ctypes.data,
+                                              qptrs, nqs, MATCHES_PER_FRAME, bptrs)
         assert rc == 0, ctx.lib.orbx_last_error(ctx.h)
-        for _ in range(MATCHES_PER_FRAME):
-            rc = ctx.lib.orbx_match_hamming_sets(ctx.h, map_np.ctypes.data, MAP_M, desc_h.data_ptr(), CAP, cnt_h.ctypes.data, B, best_h.data_ptr(), None)
-            assert rc == 0, ctx.lib.orbx_last_error(ctx.h)
 
     for _ in range(3):
         e2e_step()
@@ -260,8 +264,8 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_fps = world * B * e2e_steps / float(te.item())
-    h2d = B * H * W * 3 + MATCHES_PER_FRAME * (MAP_M * 32 + B * CAP * 32 + B * 4)
-    d2h = B * CAP * 60 + 2 * B * 4 + MATCHES_PER_FRAME * (B * MAP_M * 16 + 4)
+    h2d = B * H * W * 3 + MATCHES_PER_FRAME * MAP_M * 32
+    d2h = B * CAP * 60 + 2 * B * 4 + MATCHES_PER_FRAME * B * MAP_M * 16 + 16
 
     if rank != 0:
         return
@@ -323,7 +327,7 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
                        "l2": f"inputs {B * H * W * 3 / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)", "mean_keypoints_per_frame": n_out},
             "clocks": clocks,
             "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": "orbx_detect_and_compute_batch + orbx_match_hamming_sets (host buffers, pinned), wall clock around synchronous calls"},
+                    "api": "orbx_extract_match_batch (one C-ABI call per step: host frames in, keypoints + descriptors + matches out; pinned host buffers), wall clock around the synchronous call"},
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_pipeline": {"achieved": pipe_ach, "peak": hbm_peak, "unit": "GB/s", "frac": pipe_ach / hbm_peak if pipe_ach else None,
                                                          "note": "same algorithmic bytes over the sum of all extraction kernels"},

@@ -120,6 +120,16 @@ int orbx_match_hamming_device_ragged(orbx_ctx* ctx, const uint8_t* d_query, int 
  * ([nsets][train_stride_rows][32] with train_counts[nsets]); best / second are [nsets][nq] (second may be NULL). */
 int orbx_match_hamming_sets(orbx_ctx* ctx, const uint8_t* query, int nq, const uint8_t* train, int train_stride_rows,
                             const int* train_counts, int nsets, orbx_match* best, orbx_match* second);
+/* The front-end's whole per-frame pattern on HOST frames in one call (src/frontend.cpp:98-108: one detectAndCompute,
+ * then match() of map-point candidates against the frame's descriptors, src/frontend.cpp:153 + :187), for a batch:
+ * extraction as orbx_detect_and_compute_batch, then for each of the `nmaps` query sets (queries[j]: nq[j] x 32 host
+ * rows = the map candidates) one exact Hamming match against every frame's own descriptors; best[j] receives
+ * [batch][nq[j]] records (trainIdx = -1 where a frame has no keypoints).  The batch is cut into frame ranges that
+ * run upload -> kernels -> download on their own streams, so the PCIe copies of one range sit under the kernels of
+ * the others and the descriptors never make a host round trip between extraction and matching. */
+int orbx_extract_match_batch(orbx_ctx* ctx, const uint8_t* const* imgs, int batch, int w, int h, size_t step, int channels,
+                             orbx_keypoint* kps, uint8_t* desc, int cap, int* n_out, const uint8_t* const* queries,
+                             const int* nq, int nmaps, orbx_match* const* best);
 /* The reference's host-side post-filter (src/frontend.cpp:190-211): keep distance <= max(min*ratio, 30).
  * Pure host helper for the shim; in place compaction, returns the kept count. */
 int orbx_filter_matches(orbx_match* matches, int n, float match_ratio);

@@ -66,6 +66,8 @@ SYMBOLS = {
     "orbx_match_hamming_device": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
     "orbx_match_hamming_device_ragged": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, C.c_int, _P, _P]),
     "orbx_match_hamming_sets": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, C.c_int, _P, _P]),
+    "orbx_extract_match_batch": (C.c_int, [_P, C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, _P, _P, C.c_int, _P,
+                                          C.POINTER(_P), C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
     "orbx_filter_matches": (C.c_int, [_P, C.c_int, C.c_float]),
     "orbx_level_geometry": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "orbx_debug_read_level": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_size_t]),

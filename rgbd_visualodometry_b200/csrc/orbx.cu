@@ -69,6 +69,8 @@ struct orbx_ctx {
     cudaStream_t stream2 = nullptr;      // blur runs here, concurrently with FAST + selection (unless profiling)
     cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
     cudaStream_t lane[4] = {};           // extra frame-range pipelines (lane 0 is `stream`)
+    cudaStream_t lane_side[4] = {};      // per-lane side stream: the lane's blur runs under its (latency-bound) selection kernel
+    cudaEvent_t lane_eva[4] = {}, lane_evb[4] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[4] = {};
     float stage_ms[N_STAGES] = {};
     bool stage_valid[N_STAGES] = {};
@@ -312,12 +314,13 @@ int run_extract(orbx_ctx* c, const uint8_t* d_imgs, int batch, int w, int h, siz
                                frame_stride, channels, d_kps, d_desc, cap, d_counts);
         if (rc) return rc;
     } else {
+        static const bool lane_sides = !(getenv("ORBX_LANE_SIDES") && atoi(getenv("ORBX_LANE_SIDES")) == 0);
         CU(cudaEventRecord(c->ev_fork, c->stream));
         for (int k = 0; k < lanes; ++k) {
             const int f0 = (int)((long)batch * k / lanes), f1 = (int)((long)batch * (k + 1) / lanes);
             cudaStream_t st = k == 0 ? c->stream : c->lane[k];
             if (k > 0) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
-            rc = run_extract_range(c, st, nullptr, nullptr, nullptr, false, fused, f0, f1 - f0, d_imgs, step, frame_stride, channels, d_kps, d_desc, cap, d_counts);
+            rc = run_extract_range(c, st, lane_sides ? c->lane_side[k] : nullptr, c->lane_eva[k], c->lane_evb[k], false, fused, f0, f1 - f0, d_imgs, step, frame_stride, channels, d_kps, d_desc, cap, d_counts);
             if (rc) return rc;
             if (k > 0) { CU(cudaEventRecord(c->ev_join[k], st)); CU(cudaStreamWaitEvent(c->stream, c->ev_join[k], 0)); }
         }
@@ -325,6 +328,26 @@ int run_extract(orbx_ctx* c, const uint8_t* d_imgs, int batch, int w, int h, siz
     CU(cudaGetLastError());
     c->last_batch = batch;
     if (c->profiling) for (int i = 0; i < 6; ++i) c->stage_valid[i] = true;
+    return ORBX_OK;
+}
+
+// Host frames [f0, f1) -> the context's staging buffer on stream `st`.  Tightly packed rows go as plain 1-D copies, and
+// frames that are also contiguous in host memory (a video buffer, a numpy batch) as ONE copy per range: large linear
+// transfers are what PCIe moves fastest.
+int upload_frames(orbx_ctx* c, cudaStream_t st, const uint8_t* const* imgs, int f0, int f1, size_t step, size_t row, int h, size_t dstep, size_t fstride)
+{
+    if (step == row && dstep == row) {
+        int i = f0;
+        while (i < f1) {
+            int j = i + 1;
+            while (j < f1 && imgs[j] == imgs[j - 1] + fstride) ++j;
+            CU(cudaMemcpyAsync((uint8_t*)c->in.p + fstride * i, imgs[i], fstride * (size_t)(j - i), cudaMemcpyHostToDevice, st));
+            i = j;
+        }
+        return ORBX_OK;
+    }
+    for (int i = f0; i < f1; ++i)
+        CU(cudaMemcpy2DAsync((uint8_t*)c->in.p + fstride * i, dstep, imgs[i], step, row, (size_t)h, cudaMemcpyHostToDevice, st));
     return ORBX_OK;
 }
 
@@ -338,9 +361,14 @@ int check_args_extract(orbx_ctx* c, int batch, int w, int h, int channels, int c
     return ORBX_OK;
 }
 
+// The matcher on device-resident operands, asynchronous on `st` (default: the context's stream).  `slot` selects the
+// status word (one per lane, so concurrent lanes never reset each other's); lanes never take the split-train path,
+// whose key scratch is shared.
 int run_match(orbx_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int stride_rows, const int* d_counts, int nsets,
-              int4* d_best, int4* d_second)
+              int4* d_best, int4* d_second, cudaStream_t st = nullptr, int slot = 0)
 {
+    const bool lane_call = st != nullptr;
+    if (!st) st = c->stream;
     if (nt >= MT_MAX_TRAIN) return fail(c, ORBX_E_UNSUPPORTED, "train set larger than 2^20 - 1 rows");
     const bool knn2 = d_second != nullptr;
     const int tiles_m = (nq + MT_QROWS - 1) / MT_QROWS;
@@ -348,7 +376,7 @@ int run_match(orbx_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int n
     constexpr int kSMs = 148;                                // one CTA per SM (163 KB of shared memory each)
     // Few (query tile, set) pairs: split the train rows across CTAs and merge with atomicMax on the packed key.
     int nsplit = 1;
-    if (!knn2) {
+    if (!knn2 && !lane_call) {
         const long base = (long)tiles_m * nsets;
         if (base < kSMs) nsplit = (int)std::min<long>(ntile_n, std::max<long>(1, (kSMs + base - 1) / base));
     }
@@ -370,27 +398,27 @@ int run_match(orbx_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int n
     int* keys = nullptr;
     const size_t nout = (size_t)nq * nsets;
     int rc;
-    if ((rc = ensure(c, c->mstatus, sizeof(int)))) return rc;
-    CU(cudaMemsetAsync(c->mstatus.p, 0, sizeof(int), c->stream));
-    stage_mark(c, 7);
+    if ((rc = ensure(c, c->mstatus, sizeof(int) * 8))) return rc;
+    int* d_status = (int*)c->mstatus.p + slot;
+    CU(cudaMemsetAsync(d_status, 0, sizeof(int), st));
+    if (!lane_call) stage_mark(c, 7);
     if (nsplit > 1) {
         if ((rc = ensure(c, c->mkeys, nout * sizeof(int)))) return rc;
         keys = (int*)c->mkeys.p;
-        k_match_keys_init<<<(unsigned)((nout + 255) / 256), 256, 0, c->stream>>>(keys, nout);
+        k_match_keys_init<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(keys, nout);
         ++c->launches;
     }
     const dim3 grd((unsigned)tiles_m, (unsigned)nsplit, (unsigned)zgroups);
     if (getenv("ORBX_MATCH_TRACE") && !c->mtrace.p) { if ((rc = ensure(c, c->mtrace, 16 * 16 * 8))) return rc; cudaMemset(c->mtrace.p, 0, 16 * 16 * 8); }
     static const int dbg = getenv("ORBX_MATCH_DBG") ? atoi(getenv("ORBX_MATCH_DBG")) : 0;   // perf experiments only: skips a role's work (wrong results)
-    if (knn2) k_hamming_umma<true><<<grd, MT_THREADS, MT_SMEM_BYTES, c->stream>>>(d_q, nq, d_t, nt, stride_rows, d_counts, nsets, rows_per_split, d_best, d_second, keys, (int*)c->mstatus.p, dbg, (long long*)c->mtrace.p);
-    else      k_hamming_umma<false><<<grd, MT_THREADS, MT_SMEM_BYTES, c->stream>>>(d_q, nq, d_t, nt, stride_rows, d_counts, nsets, rows_per_split, d_best, d_second, keys, (int*)c->mstatus.p, dbg, (long long*)c->mtrace.p);
+    if (knn2) k_hamming_umma<true><<<grd, MT_THREADS, MT_SMEM_BYTES, st>>>(d_q, nq, d_t, nt, stride_rows, d_counts, nsets, rows_per_split, d_best, d_second, keys, d_status, dbg, (long long*)c->mtrace.p);
+    else      k_hamming_umma<false><<<grd, MT_THREADS, MT_SMEM_BYTES, st>>>(d_q, nq, d_t, nt, stride_rows, d_counts, nsets, rows_per_split, d_best, d_second, keys, d_status, dbg, (long long*)c->mtrace.p);
     ++c->launches;
     if (nsplit > 1) {
-        k_match_finalize<<<(unsigned)((nout + 255) / 256), 256, 0, c->stream>>>(keys, nq, nout, d_best);
+        k_match_finalize<<<(unsigned)((nout + 255) / 256), 256, 0, st>>>(keys, nq, nout, d_best);
         ++c->launches;
     }
-    stage_mark(c, 8);
-    if (c->profiling) c->stage_valid[6] = true;
+    if (!lane_call) { stage_mark(c, 8); if (c->profiling) c->stage_valid[6] = true; }
     CU(cudaGetLastError());
     return ORBX_OK;
 }
@@ -453,6 +481,9 @@ int orbx_create(orbx_ctx** out, int device, int nfeatures, float scale_factor, i
     if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) return bail(ORBX_E_CUDA);
     for (int k = 1; k < 4; ++k)
         if (cudaStreamCreateWithFlags(&c->lane[k], cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming) != cudaSuccess) return bail(ORBX_E_CUDA);
+    for (int k = 0; k < 4; ++k)
+        if (cudaStreamCreateWithFlags(&c->lane_side[k], cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&c->lane_eva[k], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->lane_evb[k], cudaEventDisableTiming) != cudaSuccess) return bail(ORBX_E_CUDA);
     if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(ORBX_E_CUDA);
     if (cudaEventCreateWithFlags(&c->ev_pyr, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_blur, cudaEventDisableTiming) != cudaSuccess) return bail(ORBX_E_CUDA);
     for (int i = 0; i < N_STAGES + 2; ++i) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail(ORBX_E_CUDA);
@@ -471,7 +502,7 @@ int orbx_create(orbx_ctx** out, int device, int nfeatures, float scale_factor, i
         if (cudaMemcpy(c->pattern.p, pat, sizeof pat, cudaMemcpyHostToDevice) != cudaSuccess) return bail(ORBX_E_CUDA);
     }
     if (cudaMemset(c->status.p, 0, sizeof(int) * B) != cudaSuccess) return bail(ORBX_E_CUDA);
-    if (cudaMallocHost((void**)&c->h_small, sizeof(int) * (2 * B + 4)) != cudaSuccess) return bail(ORBX_E_NOMEM);
+    if (cudaMallocHost((void**)&c->h_small, sizeof(int) * (2 * B + 16)) != cudaSuccess) return bail(ORBX_E_NOMEM);
     if (cudaFuncSetAttribute(k_hamming_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(k_hamming_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES) != cudaSuccess)
         return bail(ORBX_E_CUDA);
@@ -491,6 +522,7 @@ void orbx_destroy(orbx_ctx* c)
     if (c->h_small) cudaFreeHost(c->h_small);
     for (int i = 0; i < N_STAGES + 2; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int k = 1; k < 4; ++k) { if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); if (c->lane[k]) { cudaStreamSynchronize(c->lane[k]); cudaStreamDestroy(c->lane[k]); } }
+    for (int k = 0; k < 4; ++k) { if (c->lane_eva[k]) cudaEventDestroy(c->lane_eva[k]); if (c->lane_evb[k]) cudaEventDestroy(c->lane_evb[k]); if (c->lane_side[k]) { cudaStreamSynchronize(c->lane_side[k]); cudaStreamDestroy(c->lane_side[k]); } }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_pyr) cudaEventDestroy(c->ev_pyr);
     if (c->ev_blur) cudaEventDestroy(c->ev_blur);
@@ -538,7 +570,7 @@ int orbx_detect_and_compute_batch(orbx_ctx* c, const uint8_t* const* imgs, int b
     if (!imgs || !n_out || (cap > 0 && (!kps || !desc))) return fail(c, ORBX_E_ARG, "null pointer");
     if (step < (size_t)w * channels) return fail(c, ORBX_E_ARG, "step smaller than a row");
     CU(cudaSetDevice(c->device));
-    const size_t row = (size_t)w * channels, dstep = round_up(row, 4), fstride = dstep * h;
+    const size_t row = (size_t)w * channels, dstep = round_up(row, 16), fstride = dstep * h;   // 16: k_gray takes 128-bit loads
     if ((rc = ensure(c, c->in, fstride * batch))) return rc;
     if ((rc = ensure(c, c->kps, sizeof(orbx_keypoint) * (size_t)std::max(cap, 1) * batch))) return rc;
     if ((rc = ensure(c, c->desc, (size_t)32 * std::max(cap, 1) * batch))) return rc;
@@ -556,8 +588,7 @@ int orbx_detect_and_compute_batch(orbx_ctx* c, const uint8_t* const* imgs, int b
         const int f0 = (int)((long)batch * k / lanes), f1 = (int)((long)batch * (k + 1) / lanes);
         cudaStream_t st = k == 0 ? c->stream : c->lane[k];
         if (k > 0) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
-        for (int i = f0; i < f1; ++i)
-            CU(cudaMemcpy2DAsync((uint8_t*)c->in.p + fstride * i, dstep, imgs[i], step, row, (size_t)h, cudaMemcpyHostToDevice, st));
+        if ((rc = upload_frames(c, st, imgs, f0, f1, step, row, h, dstep, fstride))) return rc;
         const bool side = lanes == 1 && !c->profiling;
         if ((rc = run_extract_range(c, st, side ? c->stream2 : nullptr, c->ev_pyr, c->ev_blur, c->profiling, f1 - f0 >= FUSED_PYR_MIN_BATCH, f0, f1 - f0, (const uint8_t*)c->in.p, dstep,
                                     fstride, channels, (float*)c->kps.p, (uint8_t*)c->desc.p, cap, (int*)c->counts.p)))
@@ -576,6 +607,90 @@ int orbx_detect_and_compute_batch(orbx_ctx* c, const uint8_t* const* imgs, int b
     c->last_batch = batch;
     if (c->profiling) for (int i = 0; i < 6; ++i) c->stage_valid[i] = true;
     CU(cudaStreamSynchronize(c->stream));
+    bool over = false;
+    for (int i = 0; i < batch; ++i) {
+        if (h_status[i] & 1) return fail(c, ORBX_E_ORDER, "introselect depth limit hit: libstdc++ heap-select order not reproduced");
+        n_out[i] = h_counts[i];
+        if (h_counts[i] > cap) over = true;
+    }
+    if (over) return fail(c, ORBX_E_CAPACITY, "output capacity too small; n_out holds the needed counts");
+    return ORBX_OK;
+}
+
+int orbx_extract_match_batch(orbx_ctx* c, const uint8_t* const* imgs, int batch, int w, int h, size_t step, int channels,
+                             orbx_keypoint* kps, uint8_t* desc, int cap, int* n_out, const uint8_t* const* queries, const int* nq,
+                             int nmaps, orbx_match* const* best)
+{
+    int rc = check_args_extract(c, batch, w, h, channels, cap);
+    if (rc) return rc;
+    if (nmaps < 0 || nmaps > 8) return fail(c, ORBX_E_ARG, "nmaps outside [0, 8]");
+    if (n_out) for (int i = 0; i < batch; ++i) n_out[i] = 0;
+    if (batch == 0) return ORBX_OK;
+    if (!imgs || !n_out || cap <= 0 || !kps || !desc) return fail(c, ORBX_E_ARG, "null pointer / zero capacity");
+    if (nmaps > 0 && (!queries || !nq || !best)) return fail(c, ORBX_E_ARG, "null map arguments");
+    for (int j = 0; j < nmaps; ++j) if (nq[j] < 0 || (nq[j] > 0 && (!queries[j] || !best[j]))) return fail(c, ORBX_E_ARG, "bad map");
+    if (w == 0 || h == 0) {                                  // cv: empty image -> no keypoints; a query against an empty train set -> no matches
+        return ORBX_OK;
+    }
+    if (step < (size_t)w * channels) return fail(c, ORBX_E_ARG, "step smaller than a row");
+    if (cap >= MT_MAX_TRAIN) return fail(c, ORBX_E_UNSUPPORTED, "capacity larger than 2^20 - 1 rows");
+    CU(cudaSetDevice(c->device));
+    const size_t row = (size_t)w * channels, dstep = round_up(row, 16), fstride = dstep * h;
+    size_t qrows = 0, mrows = 0;
+    for (int j = 0; j < nmaps; ++j) { qrows += (size_t)nq[j]; mrows += (size_t)nq[j] * batch; }
+    if ((rc = ensure(c, c->in, fstride * batch)) || (rc = ensure(c, c->kps, sizeof(orbx_keypoint) * (size_t)cap * batch)) ||
+        (rc = ensure(c, c->desc, (size_t)32 * cap * batch)) || (rc = ensure(c, c->counts, sizeof(int) * (size_t)batch)) ||
+        (rc = ensure(c, c->mq, std::max<size_t>(qrows, 1) * 32)) || (rc = ensure(c, c->mbest, std::max<size_t>(mrows, 1) * 16)) ||
+        (rc = ensure(c, c->mstatus, sizeof(int) * 8)))
+        return rc;
+    for (int i = 0; i < batch; ++i) if (!imgs[i]) return fail(c, ORBX_E_ARG, "null frame pointer");
+    if ((rc = set_geometry(c, w, h))) return rc;
+    CU(cudaMemsetAsync(c->status.p, 0, sizeof(int) * (size_t)batch, c->stream));
+    {
+        size_t off = 0;
+        for (int j = 0; j < nmaps; ++j) {
+            if (nq[j] > 0) CU(cudaMemcpyAsync((uint8_t*)c->mq.p + off * 32, queries[j], (size_t)nq[j] * 32, cudaMemcpyHostToDevice, c->stream));
+            off += (size_t)nq[j];
+        }
+    }
+    int* h_counts = c->h_small;
+    int* h_status = c->h_small + batch;
+    int* h_mstatus = c->h_small + 2 * batch;
+    const int lanes = c->profiling ? 1 : std::max(1, std::min(MAX_LANES, batch / HOST_LANE_MIN_FRAMES));
+    CU(cudaEventRecord(c->ev_fork, c->stream));
+    for (int k = 0; k < lanes; ++k) {
+        const int f0 = (int)((long)batch * k / lanes), f1 = (int)((long)batch * (k + 1) / lanes);
+        const size_t n = (size_t)(f1 - f0);
+        cudaStream_t st = k == 0 ? c->stream : c->lane[k];
+        if (k > 0) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
+        if ((rc = upload_frames(c, st, imgs, f0, f1, step, row, h, dstep, fstride))) return rc;
+        if ((rc = run_extract_range(c, st, nullptr, nullptr, nullptr, c->profiling, f1 - f0 >= FUSED_PYR_MIN_BATCH, f0, f1 - f0, (const uint8_t*)c->in.p, dstep,
+                                    fstride, channels, (float*)c->kps.p, (uint8_t*)c->desc.p, cap, (int*)c->counts.p)))
+            return rc;
+        CU(cudaMemcpyAsync(h_counts + f0, (int*)c->counts.p + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h_status + f0, (int*)c->status.p + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(kps + (size_t)f0 * cap, (orbx_keypoint*)c->kps.p + (size_t)f0 * cap, sizeof(orbx_keypoint) * (size_t)cap * n, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, (uint8_t*)c->desc.p + (size_t)f0 * cap * 32, (size_t)32 * cap * n, cudaMemcpyDeviceToHost, st));
+        size_t qoff = 0, moff = 0;
+        for (int j = 0; j < nmaps; ++j) {
+            if (nq[j] > 0) {
+                int4* d_best = (int4*)c->mbest.p + moff + (size_t)f0 * nq[j];
+                // train sets = this lane's frames, straight from the extraction outputs ([frame][cap][32] + counts)
+                if ((rc = run_match(c, (const uint8_t*)c->mq.p + qoff * 32, nq[j], (const uint8_t*)c->desc.p + (size_t)f0 * cap * 32, cap, cap,
+                                    (const int*)c->counts.p + f0, (int)n, d_best, nullptr, st, k)))
+                    return rc;
+                CU(cudaMemcpyAsync(best[j] + (size_t)f0 * nq[j], d_best, (size_t)16 * nq[j] * n, cudaMemcpyDeviceToHost, st));
+            }
+            qoff += (size_t)nq[j]; moff += (size_t)nq[j] * batch;
+        }
+        CU(cudaMemcpyAsync(h_mstatus + k, (int*)c->mstatus.p + k, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (k > 0) { CU(cudaEventRecord(c->ev_join[k], st)); CU(cudaStreamWaitEvent(c->stream, c->ev_join[k], 0)); }
+    }
+    CU(cudaGetLastError());
+    c->last_batch = batch;
+    if (c->profiling) for (int i = 0; i < 6; ++i) c->stage_valid[i] = true;
+    CU(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < lanes; ++k) if (nmaps > 0 && h_mstatus[k]) return fail(c, ORBX_E_INTERNAL, "matcher pipeline timed out on an mbarrier (device status set)");
     bool over = false;
     for (int i = 0; i < batch; ++i) {
         if (h_status[i] & 1) return fail(c, ORBX_E_ORDER, "introselect depth limit hit: libstdc++ heap-select order not reproduced");

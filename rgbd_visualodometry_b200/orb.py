@@ -94,6 +94,32 @@ class Context:
             self._check(rc)
             return kps, desc, n
 
+    def extract_match_batch(self, images, maps, cap: int | None = None):
+        """The front-end's per-frame pattern for a batch of HOST frames: extraction, then every map in `maps`
+        ([M_j, 32] uint8 each) matched against each frame's own descriptors.  Returns (kps, desc, counts, [best_j[B, M_j]])."""
+        imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in images]
+        b = len(imgs)
+        qs = [np.ascontiguousarray(m, np.uint8).reshape(-1, 32) for m in maps]
+        h, w = imgs[0].shape[:2]
+        ch = 1 if imgs[0].ndim == 2 else imgs[0].shape[2]
+        cap = int(cap) if cap is not None else max(2 * self.nfeatures, 64)
+        ptrs = (C.c_void_p * b)(*[im.ctypes.data for im in imgs])
+        qptrs = (C.c_void_p * max(len(qs), 1))(*[q.ctypes.data for q in qs])
+        nq = (C.c_int * max(len(qs), 1))(*[len(q) for q in qs])
+        while True:
+            kps = np.zeros((b, cap), KP_DTYPE)
+            desc = np.zeros((b, cap, 32), np.uint8)
+            n = np.zeros(b, np.int32)
+            best = [np.zeros((b, len(q)), DMATCH_DTYPE) for q in qs]
+            bptrs = (C.c_void_p * max(len(qs), 1))(*[x.ctypes.data for x in best])
+            rc = self.lib.orbx_extract_match_batch(self.h, ptrs, b, w, h, imgs[0].strides[0] if h else 0, ch, _ptr(kps), _ptr(desc), cap,
+                                                   _ptr(n), qptrs, nq, len(qs), bptrs)
+            if rc == E_CAPACITY:
+                cap = int(n.max())
+                continue
+            self._check(rc)
+            return kps, desc, n, best
+
     def detect_and_compute_device(self, d_imgs_ptr: int, batch: int, w: int, h: int, step: int, frame_stride: int, channels: int,
                                   d_kps_ptr: int, d_desc_ptr: int, cap: int, d_counts_ptr: int):
         """Asynchronous, device-resident batch (raw device pointers, e.g. torch .data_ptr())."""

@@ -280,3 +280,33 @@ def test_orb_large_batch_fused_pyramid(orbmod, oracle):
         ko, do = oracle.detect_and_compute(fr, 200)
         _assert_kp_equal(kps[i, :cnt[i]], desc[i, :cnt[i]], ko, do, f"fused batch frame {i}")
     ctx.close()
+
+
+@pytest.mark.gpu
+def test_fused_extract_match_batch_equals_separate_calls_and_oracle(orbmod):
+    """orbx_extract_match_batch (lanes: upload -> extraction -> matching -> download per frame range) must give exactly what
+    the separate drop-in calls give, and frame 0 must equal the oracle end to end."""
+    from oracle import oracle as O
+    from rgbd_visualodometry_b200.synth import synth_frame, synth_map_queries, synth_descriptors
+    B, n = 70, 300
+    frames = [synth_frame(240, 320, 4100 + i) for i in range(B)]
+    frames[5] = np.full((240, 320, 3), 77, np.uint8)                       # a frame without keypoints
+    ctx = orbmod.Context(n, 1.2, 8, 320, 240, B)
+    k0, d0 = ctx.detect_and_compute(frames[0])
+    maps = [synth_map_queries(d0, 777, 3), synth_descriptors(130, 9)]
+    kps, desc, cnt, best = ctx.extract_match_batch(frames, maps)
+    kps2, desc2, cnt2 = ctx.detect_and_compute_batch(frames)
+    assert np.array_equal(cnt, cnt2) and cnt[5] == 0
+    for i in range(B):
+        assert kps[i, :cnt[i]].tobytes() == kps2[i, :cnt[i]].tobytes()
+        assert np.array_equal(desc[i, :cnt[i]], desc2[i, :cnt[i]])
+    for j, q in enumerate(maps):
+        for i in (0, 1, 5, 17, 34, 35, 69):
+            if cnt[i] == 0:
+                assert (best[j][i]["trainIdx"] == -1).all()
+                continue
+            ref = ctx.match(q, desc[i, :cnt[i]])
+            assert best[j][i].tobytes() == ref.tobytes(), (j, i)
+    ko, do = O.detect_and_compute(frames[0], n)
+    assert kps[0, :cnt[0]].tobytes() == ko.tobytes() and np.array_equal(desc[0, :cnt[0]], do)
+    assert best[0][0].tobytes() == O.match_hamming(maps[0], do).tobytes()
