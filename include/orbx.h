@@ -134,6 +134,47 @@ int orbx_extract_match_batch(orbx_ctx* ctx, const uint8_t* const* imgs, int batc
  * Pure host helper for the shim; in place compaction, returns the kept count. */
 int orbx_filter_matches(orbx_match* matches, int n, float match_ratio);
 
+/* ---- the callers either side of the matcher: device-resident map table, candidate visibility
+ *      filter, match post-filter, depth back-projection ------------------------------------------------------
+ *
+ * The reference gathers the candidate descriptors on the host for EVERY match call: it walks trackingMap_, tests
+ * Frame::IsCouldObserveMappoint per point and push_back()s Mappoint::descriptor_ rows into a fresh cv::Mat
+ * (src/frontend.cpp:169-184), then thresholds the matches on the host (:190-211).  Here the map points live in a
+ * slot-addressed table in HBM keyed by the reference's map-point id (Mappoint::id_, size_t), and one call does
+ * filter -> gather -> match -> threshold on the device.  Poses are T_c_w as a row-major 3 x 4 [R | t]
+ * (Frame::T_c_w_, SE3::matrix3x4()); cam = {fx, fy, cx, cy} (src/camera.cpp:27-30).  Geometry is double precision in
+ * the reference's operation order (parity to 1e-9 relative: the reference binary is compiled with FMA contraction). */
+
+/* Pre-size the table (it grows on demand). */
+int orbx_map_reserve(orbx_ctx* ctx, int capacity);
+int orbx_map_size(const orbx_ctx* ctx);
+int orbx_map_clear(orbx_ctx* ctx);
+/* Insert or update `n` map points (MapManager::InsertMappoint, src/frontend.cpp:396-399; Mappoint::SetPosition after BA;
+ * Mappoint::outlier_ set by the backend).  desc: n x 32 rows, pos / norm: n x 3 doubles (Mappoint::pos_, norm_), outlier:
+ * n bytes.  A NULL column is left unchanged for known ids and zero for new ones.  Host buffers, borrowed for the call. */
+int orbx_map_upsert(orbx_ctx* ctx, const int64_t* ids, int n, const uint8_t* desc, const double* pos, const double* norm,
+                    const uint8_t* outlier);
+/* As above, but the descriptor rows are copied device -> device out of frame `frame` of the last host-API extraction
+ * (keypoint indices kp_index[n]): the device form of descriptorsCurr_.row(idx).clone(), src/frontend.cpp:392-394. */
+int orbx_map_upsert_from_frame(orbx_ctx* ctx, const int64_t* ids, int n, int frame, const int32_t* kp_index, const double* pos,
+                               const double* norm);
+int orbx_map_erase(orbx_ctx* ctx, const int64_t* ids, int n);
+/* FrontEnd::MatchKeyPointsInTrackingMap (src/frontend.cpp:156-215) for the tracking map `ids[m]` (in the caller's
+ * iteration order): candidates = points that are not outliers and pass Frame::IsCouldObserveMappoint (src/frame.cpp:70-91:
+ * in front of the camera, projects inside cols x rows, viewing angle <= pi/6); cand[] receives their positions in ids[]
+ * (*n_cand of them, order kept); they are matched against the train descriptors -- host rows `train` (nt_or_frame = row
+ * count) or, when train is NULL, frame `nt_or_frame` of the last host-API extraction -- and matches[] receives the
+ * DMatch records with distance <= max(min_distance * match_ratio, 30) (*n_matches, queryIdx = index into cand[]).
+ * An unknown id is ORBX_E_ARG.  Empty candidate or train set -> no matches (the reference dereferences end() there). */
+int orbx_track_match(orbx_ctx* ctx, const int64_t* ids, int m, const double* pose_Tcw, const double* cam, int cols, int rows,
+                     const uint8_t* train, int nt_or_frame, float match_ratio, int32_t* cand, int* n_cand, orbx_match* matches,
+                     int* n_matches, float* min_dis, float* max_dis);
+/* FrontEnd::CreateNewMappoints' geometry (src/frontend.cpp:372-389): Frame::GetDepth (src/frame.cpp:43-67: cvRound'ed
+ * pixel, else its left / up / right / down neighbour, depth = d / depth_scale) and Camera::Pixel2World
+ * (src/camera.cpp:56-86) for n keypoints.  depth: h rows of step_bytes, 16UC1.  pos_w: n x 3, valid: n (0 = no depth). */
+int orbx_backproject(orbx_ctx* ctx, const orbx_keypoint* kps, int n, const uint16_t* depth, int w, int h, size_t step_bytes,
+                     float depth_scale, const double* cam, const double* pose_Tcw, double* pos_w, uint8_t* valid);
+
 /* ---- introspection for stage-level parity tests (not needed by the shim) ------------------------- */
 
 /* Geometry of the pyramid the context would build for a w x h frame. */

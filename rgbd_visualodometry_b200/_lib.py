@@ -14,7 +14,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 SO = os.path.join(PKG, "liborbx.so")
-SOURCES = ["orbx.cu", "orbx_kernels.cuh", "orbx_match.cuh", "orbx_geom.h", "brief_pattern.inc"]
+SOURCES = ["orbx.cu", "orbx_kernels.cuh", "orbx_match.cuh", "orbx_map.cuh", "orbx_geom.h", "brief_pattern.inc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared"]
 
@@ -68,6 +68,15 @@ SYMBOLS = {
     "orbx_match_hamming_sets": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, C.c_int, _P, _P]),
     "orbx_extract_match_batch": (C.c_int, [_P, C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, _P, _P, C.c_int, _P,
                                           C.POINTER(_P), C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    "orbx_map_reserve": (C.c_int, [_P, C.c_int]),
+    "orbx_map_size": (C.c_int, [_P]),
+    "orbx_map_clear": (C.c_int, [_P]),
+    "orbx_map_upsert": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P]),
+    "orbx_map_upsert_from_frame": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P]),
+    "orbx_map_erase": (C.c_int, [_P, _P, C.c_int]),
+    "orbx_track_match": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_float, _P, C.POINTER(C.c_int), _P,
+                                  C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "orbx_backproject": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_size_t, C.c_float, _P, _P, _P, _P]),
     "orbx_filter_matches": (C.c_int, [_P, C.c_int, C.c_float]),
     "orbx_level_geometry": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "orbx_debug_read_level": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_size_t]),

@@ -19,6 +19,8 @@
 #include "orbx_geom.h"
 #include "orbx_kernels.cuh"
 #include "orbx_match.cuh"
+#include "orbx_map.cuh"
+#include <unordered_map>
 
 using namespace orbx;
 
@@ -63,6 +65,13 @@ struct orbx_ctx {
     Buf mq, mt, mbest, msecond, mkeys, mstatus, mcounts, mtrace;
     int* h_small = nullptr;                  // pinned: counts[max_batch] + status[max_batch] + 1
     int last_batch = 0;
+
+    // device-resident map-point table: slot-addressed columns + the host's id -> slot index
+    Buf t_desc, t_pos, t_nrm, t_outl, t_slots, t_cand, t_ncand, t_q, t_in, t_best, t_filtered, t_minmax, t_aux;
+    int map_capacity = 0;
+    std::unordered_map<long long, int> map_slot;
+    std::vector<int> map_free;
+    int map_next = 0;
 
     bool profiling = false;
     cudaEvent_t ev[N_STAGES + 2] = {};   // 0..6 bracket the six extraction stages, 7..8 the matcher
@@ -517,7 +526,9 @@ void orbx_destroy(orbx_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream2) cudaStreamSynchronize(c->stream2);
     Buf* bufs[] = {&c->pyr, &c->blur, &c->rowcnt, &c->rowent, &c->work, &c->selpos, &c->fincnt, &c->status, &c->tabs, &c->pattern, &c->in, &c->kps,
-                   &c->desc, &c->counts, &c->mq, &c->mt, &c->mbest, &c->msecond, &c->mkeys, &c->mstatus, &c->mcounts, &c->mtrace};
+                   &c->desc, &c->counts, &c->mq, &c->mt, &c->mbest, &c->msecond, &c->mkeys, &c->mstatus, &c->mcounts, &c->mtrace,
+                   &c->t_desc, &c->t_pos, &c->t_nrm, &c->t_outl, &c->t_slots, &c->t_cand, &c->t_ncand, &c->t_q, &c->t_in, &c->t_best, &c->t_filtered,
+                   &c->t_minmax, &c->t_aux};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     if (c->h_small) cudaFreeHost(c->h_small);
     for (int i = 0; i < N_STAGES + 2; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -605,6 +616,7 @@ int orbx_detect_and_compute_batch(orbx_ctx* c, const uint8_t* const* imgs, int b
     }
     CU(cudaGetLastError());
     c->last_batch = batch;
+    c->out_cap = cap;
     if (c->profiling) for (int i = 0; i < 6; ++i) c->stage_valid[i] = true;
     CU(cudaStreamSynchronize(c->stream));
     bool over = false;
@@ -688,6 +700,7 @@ int orbx_extract_match_batch(orbx_ctx* c, const uint8_t* const* imgs, int batch,
     }
     CU(cudaGetLastError());
     c->last_batch = batch;
+    c->out_cap = cap;
     if (c->profiling) for (int i = 0; i < 6; ++i) c->stage_valid[i] = true;
     CU(cudaStreamSynchronize(c->stream));
     for (int k = 0; k < lanes; ++k) if (nmaps > 0 && h_mstatus[k]) return fail(c, ORBX_E_INTERNAL, "matcher pipeline timed out on an mbarrier (device status set)");
@@ -868,6 +881,268 @@ int orbx_debug_stage_times(orbx_ctx* c, const char** names, float* ms, int cap)
         ++n;
     }
     return n;
+}
+
+}  // extern "C"
+
+// =================================================================================================== map table / tracking
+namespace {
+
+// grow a table column, keeping its contents
+int grow_keep(orbx_ctx* c, Buf& b, size_t old_bytes, size_t new_bytes)
+{
+    if (b.bytes >= new_bytes && b.p) return ORBX_OK;
+    void* np = nullptr;
+    if (cudaMalloc(&np, std::max<size_t>(new_bytes, 256)) != cudaSuccess) return fail(c, ORBX_E_NOMEM, "cudaMalloc failed (map table)");
+    if (cudaMemsetAsync(np, 0, std::max<size_t>(new_bytes, 256), c->stream) != cudaSuccess) { cudaFree(np); return fail(c, ORBX_E_CUDA, "memset failed"); }
+    if (b.p && old_bytes) {
+        if (cudaMemcpyAsync(np, b.p, old_bytes, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) { cudaFree(np); return fail(c, ORBX_E_CUDA, "copy failed"); }
+    }
+    cudaStreamSynchronize(c->stream);
+    if (b.p) cudaFree(b.p);
+    b.p = np; b.bytes = std::max<size_t>(new_bytes, 256);
+    return ORBX_OK;
+}
+
+int map_reserve(orbx_ctx* c, int capacity)
+{
+    if (capacity <= c->map_capacity) return ORBX_OK;
+    int ncap = std::max(capacity, std::max(1024, c->map_capacity * 2));
+    const size_t o = (size_t)c->map_capacity, n = (size_t)ncap;
+    int rc;
+    if ((rc = grow_keep(c, c->t_desc, o * 32, n * 32)) || (rc = grow_keep(c, c->t_pos, o * 24, n * 24)) || (rc = grow_keep(c, c->t_nrm, o * 24, n * 24)) ||
+        (rc = grow_keep(c, c->t_outl, o, n)))
+        return rc;
+    c->map_capacity = ncap;
+    return ORBX_OK;
+}
+
+// ids -> slots (allocating new slots when `create`); the slot list is left in c->t_slots on the device
+int map_slots(orbx_ctx* c, const int64_t* ids, int n, bool create, std::vector<int>* slots)
+{
+    slots->resize((size_t)n);
+    if (create) {
+        int fresh = 0;
+        for (int i = 0; i < n; ++i) if (!c->map_slot.count((long long)ids[i])) ++fresh;     // duplicates inside one call over-count: harmless
+        const int need = c->map_next - (int)c->map_free.size() + fresh;
+        int rc = map_reserve(c, std::max(need, c->map_next));
+        if (rc) return rc;
+    }
+    for (int i = 0; i < n; ++i) {
+        auto it = c->map_slot.find((long long)ids[i]);
+        if (it != c->map_slot.end()) { (*slots)[i] = it->second; continue; }
+        if (!create) return fail(c, ORBX_E_ARG, "unknown map-point id");
+        int s;
+        if (!c->map_free.empty()) { s = c->map_free.back(); c->map_free.pop_back(); }
+        else {
+            s = c->map_next++;
+            if (s >= c->map_capacity) { int rc = map_reserve(c, s + 1); if (rc) return rc; }
+        }
+        c->map_slot.emplace((long long)ids[i], s);
+        (*slots)[i] = s;
+    }
+    int rc = ensure(c, c->t_slots, sizeof(int) * (size_t)std::max(n, 1));
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->t_slots.p, slots->data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    return ORBX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orbx_map_reserve(orbx_ctx* c, int capacity)
+{
+    if (!c || capacity < 0) return ORBX_E_ARG;
+    CU(cudaSetDevice(c->device));
+    return map_reserve(c, capacity);
+}
+
+int orbx_map_size(const orbx_ctx* c) { return c ? (int)c->map_slot.size() : 0; }
+
+int orbx_map_clear(orbx_ctx* c)
+{
+    if (!c) return ORBX_E_ARG;
+    c->map_slot.clear(); c->map_free.clear(); c->map_next = 0;
+    return ORBX_OK;
+}
+
+int orbx_map_upsert(orbx_ctx* c, const int64_t* ids, int n, const uint8_t* desc, const double* pos, const double* norm, const uint8_t* outlier)
+{
+    if (!c || n < 0) return ORBX_E_ARG;
+    if (n == 0) return ORBX_OK;
+    if (!ids) return fail(c, ORBX_E_ARG, "null ids");
+    CU(cudaSetDevice(c->device));
+    std::vector<int> slots;
+    std::vector<char> is_new((size_t)n);
+    for (int i = 0; i < n; ++i) is_new[i] = !c->map_slot.count((long long)ids[i]);
+    int rc = map_slots(c, ids, n, true, &slots);
+    if (rc) return rc;
+    // staging: [desc n*32][pos n*24][norm n*24][outlier n]; a column the caller leaves NULL keeps its value for existing
+    // points and starts as zero for new ones (outlier_ = false, norm_ = 0: src/mappoint.cpp:35)
+    const size_t N = (size_t)n, o_pos = N * 32, o_nrm = o_pos + N * 24, o_out = o_nrm + N * 24, total = o_out + N;
+    if ((rc = ensure(c, c->t_in, total))) return rc;
+    uint8_t* st = (uint8_t*)c->t_in.p;
+    if (desc) CU(cudaMemcpyAsync(st, desc, N * 32, cudaMemcpyHostToDevice, c->stream));
+    if (pos) CU(cudaMemcpyAsync(st + o_pos, pos, N * 24, cudaMemcpyHostToDevice, c->stream));
+    if (norm) CU(cudaMemcpyAsync(st + o_nrm, norm, N * 24, cudaMemcpyHostToDevice, c->stream));
+    if (outlier) CU(cudaMemcpyAsync(st + o_out, outlier, N, cudaMemcpyHostToDevice, c->stream));
+    if (!desc || !pos || !norm || !outlier) {
+        // zero the columns of NEW points that were not supplied: one scatter of zeros for those slots
+        std::vector<int> ns;
+        for (int i = 0; i < n; ++i) if (is_new[i]) ns.push_back(slots[i]);
+        if (!ns.empty()) {
+            const size_t Z = ns.size();
+            if ((rc = ensure(c, c->t_aux, Z * 4 + Z * 32))) return rc;
+            CU(cudaMemcpyAsync(c->t_aux.p, ns.data(), Z * 4, cudaMemcpyHostToDevice, c->stream));
+            uint8_t* z = (uint8_t*)c->t_aux.p + Z * 4;
+            CU(cudaMemsetAsync(z, 0, Z * 32, c->stream));
+            k_map_scatter<<<(unsigned)((Z + 255) / 256), 256, 0, c->stream>>>((const int*)c->t_aux.p, (int)Z, desc ? nullptr : z, pos ? nullptr : (const double*)z,
+                                                                              norm ? nullptr : (const double*)z, outlier ? nullptr : z, (uint8_t*)c->t_desc.p,
+                                                                              (double*)c->t_pos.p, (double*)c->t_nrm.p, (uint8_t*)c->t_outl.p);
+            ++c->launches;
+            CU(cudaStreamSynchronize(c->stream));            // `ns` is a local
+        }
+    }
+    k_map_scatter<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const int*)c->t_slots.p, n, desc ? st : nullptr, pos ? (const double*)(st + o_pos) : nullptr,
+                                                                      norm ? (const double*)(st + o_nrm) : nullptr, outlier ? st + o_out : nullptr,
+                                                                      (uint8_t*)c->t_desc.p, (double*)c->t_pos.p, (double*)c->t_nrm.p, (uint8_t*)c->t_outl.p);
+    ++c->launches;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));                    // host sources are borrowed only for the duration of the call
+    return ORBX_OK;
+}
+
+int orbx_map_upsert_from_frame(orbx_ctx* c, const int64_t* ids, int n, int frame, const int32_t* kp_index, const double* pos, const double* norm)
+{
+    if (!c || n < 0) return ORBX_E_ARG;
+    if (n == 0) return ORBX_OK;
+    if (!ids || !kp_index) return fail(c, ORBX_E_ARG, "null pointer");
+    if (!c->desc.p || c->out_cap <= 0 || frame < 0 || frame >= c->last_batch) return fail(c, ORBX_E_ARG, "no host-API extraction holds that frame");
+    for (int i = 0; i < n; ++i) if (kp_index[i] < 0 || kp_index[i] >= c->out_cap) return fail(c, ORBX_E_ARG, "keypoint index out of range");
+    int rc = orbx_map_upsert(c, ids, n, nullptr, pos, norm, nullptr);
+    if (rc) return rc;
+    std::vector<int> slots;
+    if ((rc = map_slots(c, ids, n, false, &slots))) return rc;
+    if ((rc = ensure(c, c->t_aux, sizeof(int) * (size_t)n))) return rc;
+    CU(cudaMemcpyAsync(c->t_aux.p, kp_index, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    k_map_scatter_desc<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const int*)c->t_slots.p, (const int*)c->t_aux.p, n,
+                                                                           (const uint8_t*)c->desc.p + (size_t)frame * c->out_cap * 32, (uint8_t*)c->t_desc.p);
+    ++c->launches;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return ORBX_OK;
+}
+
+int orbx_map_erase(orbx_ctx* c, const int64_t* ids, int n)
+{
+    if (!c || n < 0 || (n > 0 && !ids)) return ORBX_E_ARG;
+    for (int i = 0; i < n; ++i) {
+        auto it = c->map_slot.find((long long)ids[i]);
+        if (it == c->map_slot.end()) continue;
+        c->map_free.push_back(it->second);
+        c->map_slot.erase(it);
+    }
+    return ORBX_OK;
+}
+
+int orbx_track_match(orbx_ctx* c, const int64_t* ids, int m, const double* pose_Tcw, const double* cam, int cols, int rows,
+                     const uint8_t* train, int nt_or_frame, float match_ratio, int32_t* cand, int* n_cand, orbx_match* matches, int* n_matches,
+                     float* min_dis, float* max_dis)
+{
+    if (!c) return ORBX_E_ARG;
+    if (n_cand) *n_cand = 0;
+    if (n_matches) *n_matches = 0;
+    if (m < 0 || !pose_Tcw || !cam || !n_cand || !n_matches) return fail(c, ORBX_E_ARG, "bad arguments");
+    if (m == 0) return ORBX_OK;
+    if (!ids || !cand || !matches) return fail(c, ORBX_E_ARG, "null pointer");
+    CU(cudaSetDevice(c->device));
+    // train set: host rows, or frame `nt_or_frame` of the last host-API extraction (still on the device)
+    const uint8_t* d_train = nullptr;
+    const int* d_tcount = nullptr;
+    int nt = 0, stride = 0;
+    int rc;
+    if (train) {
+        nt = nt_or_frame;
+        if (nt < 0) return fail(c, ORBX_E_ARG, "negative train count");
+        if (nt > 0) {
+            if ((rc = ensure(c, c->mt, (size_t)nt * 32))) return rc;
+            CU(cudaMemcpyAsync(c->mt.p, train, (size_t)nt * 32, cudaMemcpyHostToDevice, c->stream));
+            d_train = (const uint8_t*)c->mt.p;
+        }
+        stride = nt;
+    } else {
+        const int f = nt_or_frame;
+        if (!c->desc.p || c->out_cap <= 0 || f < 0 || f >= c->last_batch) return fail(c, ORBX_E_ARG, "no host-API extraction holds that frame");
+        d_train = (const uint8_t*)c->desc.p + (size_t)f * c->out_cap * 32;
+        d_tcount = (const int*)c->counts.p + f;
+        nt = stride = c->out_cap;
+    }
+    std::vector<int> slots;
+    if ((rc = map_slots(c, ids, m, false, &slots))) return rc;
+    if ((rc = ensure(c, c->t_cand, sizeof(int) * (size_t)m)) || (rc = ensure(c, c->t_ncand, 16)) || (rc = ensure(c, c->t_q, (size_t)m * 32)) ||
+        (rc = ensure(c, c->t_best, (size_t)m * 16)) || (rc = ensure(c, c->t_filtered, (size_t)m * 16)) || (rc = ensure(c, c->t_minmax, 16)))
+        return rc;
+    Pose T; Cam K;
+    for (int i = 0; i < 12; ++i) T.m[i] = pose_Tcw[i];
+    K.fx = cam[0]; K.fy = cam[1]; K.cx = cam[2]; K.cy = cam[3];
+    k_visibility<<<1, VIS_NT, 0, c->stream>>>((const int*)c->t_slots.p, m, T, K, cols, rows, (const double*)c->t_pos.p, (const double*)c->t_nrm.p,
+                                              (const uint8_t*)c->t_outl.p, (int*)c->t_cand.p, (int*)c->t_ncand.p);
+    ++c->launches;
+    int* h = c->h_small;
+    CU(cudaMemcpyAsync(h, c->t_ncand.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));                    // the candidate count sizes the matcher's grid
+    const int nc = h[0];
+    *n_cand = nc;
+    if (nc > 0) CU(cudaMemcpyAsync(cand, c->t_cand.p, sizeof(int) * (size_t)nc, cudaMemcpyDeviceToHost, c->stream));
+    if (nc == 0 || nt == 0) { CU(cudaStreamSynchronize(c->stream)); return ORBX_OK; }   // cv: empty query or train -> no matches
+    k_gather_desc<<<(unsigned)((nc + 255) / 256), 256, 0, c->stream>>>((const int*)c->t_slots.p, (const int*)c->t_cand.p, nc, (const uint8_t*)c->t_desc.p,
+                                                                       (uint8_t*)c->t_q.p);
+    ++c->launches;
+    if ((rc = run_match(c, (const uint8_t*)c->t_q.p, nc, d_train, nt, stride, d_tcount, 1, (int4*)c->t_best.p, nullptr))) return rc;
+    k_filter_matches<<<1, VIS_NT, 0, c->stream>>>((const int4*)c->t_best.p, nc, match_ratio, (int4*)c->t_filtered.p, (int*)c->t_ncand.p + 1,
+                                                  (float*)c->t_minmax.p);
+    ++c->launches;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(h, (int*)c->t_ncand.p + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(h + 1, c->t_minmax.p, 2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(h + 3, c->mstatus.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (h[3]) return fail(c, ORBX_E_INTERNAL, "matcher pipeline timed out on an mbarrier (device status set)");
+    const int nm = h[0];
+    if (nm > 0) CU(cudaMemcpy(matches, c->t_filtered.p, (size_t)nm * 16, cudaMemcpyDeviceToHost));
+    *n_matches = nm;
+    if (min_dis) memcpy(min_dis, h + 1, sizeof(float));
+    if (max_dis) memcpy(max_dis, h + 2, sizeof(float));
+    return ORBX_OK;
+}
+
+int orbx_backproject(orbx_ctx* c, const orbx_keypoint* kps, int n, const uint16_t* depth, int w, int h, size_t step_bytes, float depth_scale,
+                     const double* cam, const double* pose_Tcw, double* pos_w, uint8_t* valid)
+{
+    if (!c || n < 0) return ORBX_E_ARG;
+    if (n == 0) return ORBX_OK;
+    if (!kps || !depth || !cam || !pose_Tcw || !pos_w || !valid || w <= 0 || h <= 0 || step_bytes < (size_t)w * 2 || (step_bytes & 1))
+        return fail(c, ORBX_E_ARG, "bad arguments");
+    CU(cudaSetDevice(c->device));
+    const size_t N = (size_t)n, dbytes = step_bytes * (size_t)h;
+    const size_t o_depth = round_up(N * 28, 256), o_pos = round_up(o_depth + dbytes, 256), o_valid = o_pos + N * 24, total = o_valid + N;
+    int rc = ensure(c, c->t_in, total);
+    if (rc) return rc;
+    uint8_t* st = (uint8_t*)c->t_in.p;
+    CU(cudaMemcpyAsync(st, kps, N * 28, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(st + o_depth, depth, dbytes, cudaMemcpyHostToDevice, c->stream));
+    Pose T; Cam K;
+    for (int i = 0; i < 12; ++i) T.m[i] = pose_Tcw[i];
+    K.fx = cam[0]; K.fy = cam[1]; K.cx = cam[2]; K.cy = cam[3];
+    k_backproject<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>((const float*)st, n, (const uint16_t*)(st + o_depth), w, h, step_bytes / 2,
+                                                                      (double)depth_scale, K, T, (double*)(st + o_pos), st + o_valid);
+    ++c->launches;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(pos_w, st + o_pos, N * 24, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(valid, st + o_valid, N, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return ORBX_OK;
 }
 
 }  // extern "C"

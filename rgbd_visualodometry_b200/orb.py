@@ -163,6 +163,70 @@ class Context:
         self._check(self.lib.orbx_match_hamming_sets(self.h, _ptr(q), len(q), _ptr(t), cap, _ptr(cnt), s, _ptr(best), _ptr(second)))
         return (best, second) if knn2 else best
 
+    # ---- map table / tracking -------------------------------------------------------------------
+    def map_upsert(self, ids, desc=None, pos=None, norm=None, outlier=None):
+        ids = np.ascontiguousarray(ids, np.int64)
+        n = len(ids)
+        d = None if desc is None else np.ascontiguousarray(desc, np.uint8).reshape(n, 32)
+        p = None if pos is None else np.ascontiguousarray(pos, np.float64).reshape(n, 3)
+        nv = None if norm is None else np.ascontiguousarray(norm, np.float64).reshape(n, 3)
+        o = None if outlier is None else np.ascontiguousarray(outlier, np.uint8).reshape(n)
+        self._check(self.lib.orbx_map_upsert(self.h, _ptr(ids), n, _ptr(d), _ptr(p), _ptr(nv), _ptr(o)))
+
+    def map_upsert_from_frame(self, ids, frame: int, kp_index, pos=None, norm=None):
+        ids = np.ascontiguousarray(ids, np.int64)
+        n = len(ids)
+        ki = np.ascontiguousarray(kp_index, np.int32).reshape(n)
+        p = None if pos is None else np.ascontiguousarray(pos, np.float64).reshape(n, 3)
+        nv = None if norm is None else np.ascontiguousarray(norm, np.float64).reshape(n, 3)
+        self._check(self.lib.orbx_map_upsert_from_frame(self.h, _ptr(ids), n, frame, _ptr(ki), _ptr(p), _ptr(nv)))
+
+    def map_erase(self, ids):
+        ids = np.ascontiguousarray(ids, np.int64)
+        self._check(self.lib.orbx_map_erase(self.h, _ptr(ids), len(ids)))
+
+    def map_clear(self):
+        self._check(self.lib.orbx_map_clear(self.h))
+
+    @property
+    def map_size(self) -> int:
+        return int(self.lib.orbx_map_size(self.h))
+
+    def track_match(self, ids, pose_Tcw, cam, cols: int, rows: int, train=None, frame: int = 0, match_ratio: float = 2.0):
+        """FrontEnd::MatchKeyPointsInTrackingMap on the device.  Returns (cand, matches, min_dis, max_dis); matches'
+        queryIdx index `cand`, whose entries index `ids`."""
+        ids = np.ascontiguousarray(ids, np.int64)
+        m = len(ids)
+        T = np.ascontiguousarray(pose_Tcw, np.float64).reshape(12)
+        K = np.ascontiguousarray(cam, np.float64).reshape(4)
+        cand = np.zeros(max(m, 1), np.int32)
+        out = np.zeros(max(m, 1), DMATCH_DTYPE)
+        nc, nm = C.c_int(0), C.c_int(0)
+        mn, mx = C.c_float(0), C.c_float(0)
+        if train is not None:
+            t = np.ascontiguousarray(train, np.uint8).reshape(-1, 32)
+            tp, tn = _ptr(t), len(t)
+            if tn == 0:
+                tp = _ptr(np.zeros((1, 32), np.uint8))
+        else:
+            tp, tn = None, frame
+        self._check(self.lib.orbx_track_match(self.h, _ptr(ids), m, _ptr(T), _ptr(K), cols, rows, tp, tn, match_ratio, _ptr(cand), C.byref(nc),
+                                              _ptr(out), C.byref(nm), C.byref(mn), C.byref(mx)))
+        return cand[:nc.value].copy(), out[:nm.value].copy(), mn.value, mx.value
+
+    def backproject(self, kps: np.ndarray, depth: np.ndarray, depth_scale: float, cam, pose_Tcw):
+        """Frame::GetDepth + Camera::Pixel2World for KP_DTYPE keypoints.  Returns (pos_w[n, 3], valid[n])."""
+        k = np.ascontiguousarray(kps)
+        d = np.ascontiguousarray(depth, np.uint16)
+        n = len(k)
+        T = np.ascontiguousarray(pose_Tcw, np.float64).reshape(12)
+        K = np.ascontiguousarray(cam, np.float64).reshape(4)
+        pos = np.zeros((max(n, 1), 3), np.float64)
+        valid = np.zeros(max(n, 1), np.uint8)
+        self._check(self.lib.orbx_backproject(self.h, _ptr(k), n, _ptr(d), d.shape[1], d.shape[0], d.strides[0], depth_scale, _ptr(K), _ptr(T),
+                                              _ptr(pos), _ptr(valid)))
+        return pos[:n], valid[:n].astype(bool)
+
     # ---- misc -----------------------------------------------------------------------------------------------
     def synchronize(self):
         self._check(self.lib.orbx_synchronize(self.h))
