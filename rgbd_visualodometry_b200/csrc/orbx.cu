@@ -393,14 +393,16 @@ int run_match(orbx_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int n
     const int rows_per_split = tiles_per_split * MT_BN;
     nsplit = (nt + rows_per_split - 1) / rows_per_split;
     // Many sets: each CTA keeps its expanded query tile and walks sets z, z + zgroups, ... (persistent pipelines).
-    // zgroups: waves(z) * sets-per-CTA(z) is the time in units of one (query tile, set) pass; +1 per wave for the setup
+    // zgroups: waves(z) * sets-per-CTA(z) is the time in units of one (query tile, set) pass; a CTA's setup (TMEM
+    // allocation, query expansion, pipeline fill) costs about a third of such a pass for ~1000-row sets, less for longer ones
     int zgroups = 1;
     {
         const long per_z = (long)tiles_m * nsplit;
+        const long setup20 = std::max<long>(1, std::min<long>(20, 20L * 4 / std::max(1, tiles_per_split)));   // in 1/20 passes
         long best_cost = -1;
         for (int z = 1; z <= nsets; ++z) {
             const long waves = (per_z * z + kSMs - 1) / kSMs;
-            const long cost = waves * ((nsets + z - 1) / z + 1);
+            const long cost = waves * (20L * ((nsets + z - 1) / z) + setup20);
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; zgroups = z; }
         }
     }

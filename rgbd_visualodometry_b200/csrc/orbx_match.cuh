@@ -353,6 +353,11 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
                 tc_fence_after();
                 const uint32_t sb = sbu + MT_SMEM_B + s * MT_B_BYTES;
                 const uint64_t db0 = umma_desc_sw128(sb);
+                // A set's last tile usually holds fewer than MT_BN rows: issue it with the smallest UMMA N (multiple of 16)
+                // that covers them -- tensor time is proportional to N.  Columns beyond keep stale values the epilogue
+                // never reads (it bounds partial tiles by the row count).
+                const int rows_here = min(MT_BN, rg.n1 - (rg.n0 + i * MT_BN));
+                const uint32_t idesc = (MT_IDESC & ~(0x3Fu << 17)) | ((uint32_t)(((rows_here + 15) & ~15) >> 3) << 17);
                 // barriers of the NEXT tile (same pipelines, consecutive tile numbers even across set boundaries)
                 const int s1 = (t + 1) % MT_STAGES, b1 = (t + 1) & 1;
                 const uint32_t ph1 = (uint32_t)((t + 1) / MT_STAGES) & 1u, bph1 = (uint32_t)((t + 1) >> 1) & 1u;
@@ -364,12 +369,14 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks) {      // K = 256 = 8 x UMMA_K(32 int8): 8 TMEM columns of A, 4 k-steps per 128-B swizzle atom of B
                             const uint64_t db = db0 + (uint64_t)(((ks >> 2) * (MT_BN * 128) + (ks & 3) * 32) >> 4);   // start-address field, 16-byte units
-                            tc_mma_i8_ts(d, ta + (uint32_t)ks * 8u, db, MT_IDESC, ks > 0 ? 1u : 0u);
+                            tc_mma_i8_ts(d, ta + (uint32_t)ks * 8u, db, idesc, ks > 0 ? 1u : 0u);
                         }
-                        tc_mma_i8(d, dca, dcb, MT_IDESC, 1u);  // bias k-step: + (MT_BN-1 - jl) in every row
+                        tc_mma_i8(d, dca, dcb, idesc, 1u);  // bias k-step: + (MT_BN-1 - jl) in every row
                     }
-                    // while the queued MMAs execute, probe the next tile's barriers so its issue can start without a wait
-                    if (a == 0) ready_next = mbar_test(bar_tempty + 8 * b1, bph1 ^ 1u) && mbar_test(bar_full + 8 * s1, ph1);
+                    // While the queued MMAs execute, probe the next tile's barriers so its issue can start without a wait.
+                    // The probe sits AFTER the last MMA of the tile: issuing blocks on the MMA queue for most of the tile's
+                    // tensor time, so by now the epilogue of tile t - 1 has usually handed its accumulators back.
+                    if (a == 1) ready_next = mbar_test(bar_tempty + 8 * b1, bph1 ^ 1u) && mbar_test(bar_full + 8 * s1, ph1);
                 }
                 if (elect_one()) {
                     tc_commit(bar_empty + 8 * s);            // smem stage reusable once these MMAs retire
@@ -405,6 +412,11 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
                     for (int ch = 0; ch < NCH; ++ch) tc_ld32(tmem_base + lane_base + (uint32_t)((b * 2 + a) * MT_BN + ch * 32), r[ch]);
                     tc_wait_ld();
                     if (tr_on) trace[(t - 40) * 16 + 6] = clock64();
+                    // The accumulators now live in registers: hand the TMEM buffer back to the issuer BEFORE the max
+                    // reduction, so the epilogue's arithmetic overlaps the MMAs of tile t + 2 instead of gating them.
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
                     // accumulator = 127 * dot + (MT_BN-1 - jl): the raw integer maximum is (largest dot, lowest index)
                     int k1 = INT_MIN, k2 = INT_MIN;
                     if (!KNN2 && full) {
@@ -444,11 +456,12 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
                         }
                     }
                 }
+                else {                                       // (perf-experiment mode without TMEM loads: still release the buffer)
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+                }
                 if (tr_on) trace[(t - 40) * 16 + 11] = clock64() + (m1 & 1);
-                tc_fence_before();
-                if (tr_on) trace[(t - 40) * 16 + 12] = clock64();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
                 if (tr_on) trace[(t - 40) * 16 + 7] = clock64();
             }
             if (ok && qrow < nq) {
