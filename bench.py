@@ -284,9 +284,11 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
     ext_total = sum(ext_stages.values())
     roofline = None
     traffic = None                                       # DRAM bytes of the dominant kernel per launch, from the committed ncu --set full capture
+    traffic_file = "profiles/r1_v9_ncu_dram_traffic.json"
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_dram_traffic.json")))["kernels"]
-        kname = {"gray": "k_gray", "fast_nms": "k_fast_bands", "select_harris": "k_select", "blur": "k_blur", "describe": "k_describe"}.get(dom)
+        tj = json.load(open(os.path.join(ROOT, traffic_file)))["kernels"]
+        kname = {"gray": "k_gray", "pyramid": "k_pyr_down", "fast_nms": "k_fast_bands", "select_harris": "k_select", "blur": "k_blur",
+                 "describe": "k_describe"}.get(dom)
         if kname in tj and B == 256:
             last = tj[kname][-1]
             traffic = last["dram_read_bytes"] + last["dram_write_bytes"]
@@ -295,7 +297,7 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
     if dom:
         ach = b_alg * B / (ext_stages[dom] / 1e3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
-                    "traffic_source": "profiles/r1_ncu_dram_traffic.json (ncu --set full, same 256-frame launch)" if traffic else None,
+                    "traffic_source": f"{traffic_file} (ncu --set full, same 256-frame launch)" if traffic else None,
                     "peak_source": peak_src, "algorithmic_bytes_per_frame": b_alg, "frames_per_launch": B,
                     "kernel_ms": ext_stages[dom], "kernel_share_of_extraction": ext_stages[dom] / ext_total}
     pipe_ach = b_alg * B / (ext_total / 1e3) / 1e9 if ext_total else None
@@ -304,7 +306,8 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
     if "match" in stage_ms:
         tops = match_ops / (stage_ms["match"] / 1e3) / 1e12
         roof_match = {"bound": "tensor", "kernel": "k_hamming_umma (tcgen05 kind::i8)", "achieved": tops, "peak": 4500.0, "unit": "TOP/s",
-                      "frac": tops / 4500.0, "peak_source": "nominal dense int8 (no measured int8 peak available)", "kernel_ms": stage_ms["match"]}
+                      "frac": tops / 4500.0, "peak_source": "nominal dense int8 (no measured int8 peak available)", "kernel_ms": stage_ms["match"],
+                      "ncu_tensor_pipe_cycles_active_pct": 59.2, "ncu_source": "profiles/r1_v9_ncu_full_summary.csv (sm__pipe_tensor_cycles_active, same launch shape)"}
 
     # ---- CPU baseline: the reference's own operators (cv2) on this box's host cores, bounded sample
     cpu = None

@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""Summaries of an .ncu-rep for profiles/: per-kernel CSV (time, DRAM bytes, pipe / issue utilisation, top stalls) and a
+JSON of DRAM traffic per launch (source of bench.py's roofline.traffic).
+  python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r1_v9"""
+import csv, io, json, subprocess, sys
+rep, out = sys.argv[1], sys.argv[2]
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units, data = rows[0], rows[1], rows[2:]
+cols = ["Kernel Name", "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "gpu__time_duration.sum",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active"]
+idx = [hdr.index(c) for c in cols if c in hdr]
+st = [i for i, h in enumerate(hdr) if h.startswith("smsp__average_warp") and "issue_stalled" in h and h.endswith(".ratio")]
+with open(out + "_ncu_full_summary.csv", "w", newline="") as f:
+    w = csv.writer(f)
+    w.writerow([hdr[i] for i in idx] + ["top stalls (warps per issue-active cycle)"])
+    w.writerow([units[i] for i in idx] + [""])
+    for r in data:
+        vals = sorted([(float(r[i]), hdr[i].replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")) for i in st if r[i]], reverse=True)[:4]
+        w.writerow([r[i] for i in idx] + ["; ".join(f"{n}={v:.2f}" for v, n in vals)])
+ki, ti = hdr.index("Kernel Name"), hdr.index("gpu__time_duration.sum")
+ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+def to_bytes(v, u):
+    return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+kern = {}
+for r in data:
+    name = r[ki].split("(")[0].replace("void ", "").split("<")[0].strip()
+    kern.setdefault(name, []).append({"dram_read_bytes": to_bytes(r[ri], units[ri]), "dram_write_bytes": to_bytes(r[wi], units[wi]),
+                                      "time_us": float(r[ti]) * {"us": 1, "ms": 1e3, "ns": 1e-3}.get(units[ti], 1)})
+json.dump({"note": "dram__bytes_read.sum / dram__bytes_write.sum per launch from ncu --set full --clock-control none, "
+                   "ORBX_LANES=1 tools/prof_step.py 256 2 (256 VGA frames per launch)", "kernels": kern},
+          open(out + "_ncu_dram_traffic.json", "w"), indent=1)
+print(open(out + "_ncu_full_summary.csv").read())
