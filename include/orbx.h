@@ -55,7 +55,7 @@ typedef enum {
     ORBX_E_NOMEM = -4,       /* host or device allocation failed */
     ORBX_E_UNSUPPORTED = -5, /* valid OpenCV input this build does not cover (e.g. channels not 1 or 3) */
     ORBX_E_INTERNAL = -6,    /* an internal device-side bound was exceeded (never silently truncated) */
-    ORBX_E_ORDER = -7        /* libstdc++ introselect would have taken its heap-select fallback; order not reproduced */
+    ORBX_E_ORDER = -7        /* reserved (was: introselect depth-limit fallback not reproduced; the fallback is implemented now) */
 } orbx_status;
 
 /* ---- lifecycle ----------------------------------------------------------------------------------- */

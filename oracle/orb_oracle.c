@@ -178,8 +178,61 @@ void orbo_quotas(int nfeatures, float scale_factor, int nlevels, int* n_l)
 #define GT(p, q) (v[p].response > v[q].response)
 static inline void cswap(orbo_cand* v, int a, int b) { orbo_cand t = v[a]; v[a] = v[b]; v[b] = t; }
 
-/* std::nth_element (libstdc++ __introselect).  Returns -1 if the heap-select fallback would have
- * been taken (never observed; flagged rather than emulated), else 0. */
+/* libstdc++ heap primitives (bits/stl_heap.h) with comp(a, b) = a.response > b.response, on the range v[first ..):
+ * __push_heap, __adjust_heap, __make_heap, __pop_heap, __heap_select -- the depth-limit fallback of __introselect.
+ * Indices are relative to `first`, exactly as the iterator arithmetic of the library. */
+static void orbo_push_heap(orbo_cand* b, int hole, int top, orbo_cand value)
+{
+    int parent = (hole - 1) / 2;
+    while (hole > top && b[parent].response > value.response) {
+        b[hole] = b[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    b[hole] = value;
+}
+static void orbo_adjust_heap(orbo_cand* b, int hole, int len, orbo_cand value)
+{
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (b[child].response > b[child - 1].response) --child;
+        b[hole] = b[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        b[hole] = b[child - 1];
+        hole = child - 1;
+    }
+    orbo_push_heap(b, hole, top, value);
+}
+/* how often the fallback ran (tests assert that their tie-heavy cases really exercise it) */
+int orbo_heap_select_calls = 0;
+static void orbo_heap_select(orbo_cand* v, int first, int middle, int last)
+{
+    ++orbo_heap_select_calls;
+    orbo_cand* b = v + first;
+    const int len = middle - first;
+    if (len >= 2) {                                           /* __make_heap */
+        int parent = (len - 2) / 2;
+        for (;;) {
+            orbo_cand value = b[parent];
+            orbo_adjust_heap(b, parent, len, value);
+            if (parent == 0) break;
+            --parent;
+        }
+    }
+    for (int i = middle; i < last; ++i)
+        if (v[i].response > b[0].response) {                  /* __pop_heap(first, middle, i) */
+            orbo_cand value = v[i];
+            v[i] = b[0];
+            orbo_adjust_heap(b, 0, len, value);
+        }
+}
+
+/* std::nth_element (libstdc++ __introselect), including its depth-limit fallback (__heap_select + iter_swap). */
 static int orbo_nth_element(orbo_cand* v, int first, int nth, int last)
 {
     if (first == last || nth == last) return 0;
@@ -187,7 +240,11 @@ static int orbo_nth_element(orbo_cand* v, int first, int nth, int last)
     while ((len >> (lg + 1)) > 0) ++lg;
     int depth = 2 * lg;
     while (last - first > 3) {
-        if (depth == 0) return -1;
+        if (depth == 0) {
+            orbo_heap_select(v, first, nth + 1, last);
+            cswap(v, first, nth);
+            return 0;
+        }
         --depth;
         int mid = first + (last - first) / 2;
         int a = first + 1, b = mid, c = last - 1, pick;

@@ -570,11 +570,68 @@ __device__ __forceinline__ int median3_pick(const Elem* v, int a, int b, int c)
     return (ra > rc) ? a : ((rb > rc) ? c : b);
 }
 
-// warp-cooperative __introselect on [first, last) with the remaining depth budget; false = depth limit hit
+// libstdc++'s depth-limit fallback of __introselect (bits/stl_heap.h, comp(a, b) = a.response > b.response):
+// __heap_select(first, nth + 1, last) = __make_heap on [first, middle), then every later element that beats the heap's
+// top (the smallest kept response) is __pop_heap'ed in; finally iter_swap(first, nth).  Sequential by nature and rare
+// (about one frame in a hundred hits the depth limit on some level): one lane runs it verbatim.
+__device__ __forceinline__ void heap_push(Elem* b, int hole, int top, Elem value)
+{
+    int parent = (hole - 1) / 2;
+    while (hole > top && b[parent].response > value.response) {
+        b[hole] = b[parent];
+        hole = parent;
+        parent = (hole - 1) / 2;
+    }
+    b[hole] = value;
+}
+__device__ __forceinline__ void heap_adjust(Elem* b, int hole, int len, Elem value)
+{
+    const int top = hole;
+    int child = hole;
+    while (child < (len - 1) / 2) {
+        child = 2 * (child + 1);
+        if (b[child].response > b[child - 1].response) --child;
+        b[hole] = b[child];
+        hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2) {
+        child = 2 * (child + 1);
+        b[hole] = b[child - 1];
+        hole = child - 1;
+    }
+    heap_push(b, hole, top, value);
+}
+__device__ void heap_select_fallback(Elem* v, int first, int nth, int last, int lane)
+{
+    __syncwarp();
+    if (lane == 0) {
+        Elem* b = v + first;
+        const int middle = nth + 1, len = middle - first;
+        if (len >= 2) {
+            int parent = (len - 2) / 2;
+            for (;;) {
+                const Elem value = b[parent];
+                heap_adjust(b, parent, len, value);
+                if (parent == 0) break;
+                --parent;
+            }
+        }
+        for (int i = middle; i < last; ++i)
+            if (v[i].response > b[0].response) {
+                const Elem value = v[i];
+                v[i] = b[0];
+                heap_adjust(b, 0, len, value);
+            }
+        elem_swap(v, first, nth);
+    }
+    __syncwarp();
+}
+
+// warp-cooperative __introselect on [first, last) with the remaining depth budget (heap-select fallback included)
 __device__ bool introselect_warp(Elem* v, int first, int last, int nth, int depth, int lane)
 {
     while (last - first > 3) {
-        if (depth == 0) return false;
+        if (depth == 0) { heap_select_fallback(v, first, nth, last, lane); return true; }
         --depth;
         const int pick = median3_pick(v, first + 1, first + (last - first) / 2, last - 1);
         __syncwarp();
@@ -641,10 +698,10 @@ __device__ int retain_best_block(Elem* v, int len, int m, PosT* Lp, PosT* Rp, Se
     if (m == 0) return 0;
     const int nth = m - 1;
     int first = 0, last = len, depth = 2 * (31 - __clz(len));
-    bool ok = true;
+    bool ok = true, fallback = false;
     // ---- data-parallel Hoare passes while the range is long
     while (last - first > SEL_PAR_MIN) {
-        if (depth == 0) { ok = false; break; }
+        if (depth == 0) { fallback = true; break; }          // depth budget spent: libstdc++ switches to __heap_select
         --depth;
         if (tid == 0) elem_swap(v, first, median3_pick(v, first + 1, first + (last - first) / 2, last - 1));
         __syncthreads();
@@ -698,7 +755,8 @@ __device__ int retain_best_block(Elem* v, int len, int m, PosT* Lp, PosT* Rp, Se
     // ---- finish with one warp: short-range introselect + insertion sort, then the std::partition tail
     if (wid == 0) {
         int res = m;
-        if (ok) ok = introselect_warp(v, first, last, nth, depth, lane);
+        if (fallback) heap_select_fallback(v, first, nth, last, lane);
+        else ok = introselect_warp(v, first, last, nth, depth, lane);
         if (ok) res = partition_tail_warp(v, m, len, v[m - 1].response, lane);
         if (lane == 0) { sh->n = res; sh->ok = ok ? 1 : 0; }
     }

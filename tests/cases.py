@@ -15,6 +15,10 @@ def _tiled():
     return np.ascontiguousarray(np.tile(synth_frame(96, 128, 7, 1), (5, 5)))
 
 
+def _rolled(seed, dy, dx):
+    return np.ascontiguousarray(np.roll(synth_frame(480, 640, seed), (dy, dx), axis=(0, 1)))
+
+
 # name -> (factory, nfeatures).  Small enough for the C oracle to finish in well under a second each.
 ORB_CASES = {
     "vga500": (lambda: synth_frame(480, 640, 0), 500),
@@ -27,6 +31,10 @@ ORB_CASES = {
     "tiny500": (lambda: synth_frame(60, 70, 9), 500),      # every level <= 62 px: no keypoints
     "const500": (lambda: np.full((240, 320), 128, np.uint8), 500),
     "binary1000": (lambda: (np.random.default_rng(5).random((300, 400)) < 0.5).astype(np.uint8) * 255, 1000),
+    # libstdc++'s __introselect runs out of its depth budget on these two and takes the __heap_select fallback
+    # (found by tools/config_bench.py: about 1 synthetic frame in 100 does)
+    "heapsel_a1000": (lambda: _rolled(777 + 21, 7, 13), 1000),
+    "heapsel_b1000": (lambda: _rolled(777 + 16, 42, 78), 1000),
 }
 
 # larger cases: checked live against cv2 / between oracle and GPU, not stored as fixtures
