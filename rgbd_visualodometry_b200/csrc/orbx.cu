@@ -199,6 +199,13 @@ void build_geom(const orbx_ctx* c, int w, int h, Geom* g, std::vector<uint32_t>*
             if (L.w > 0 && L.h > 0 && S.w > 0 && S.h > 0) {
                 resize_taps(S.w, L.w, tabs->data() + L.xtab);
                 resize_taps(S.h, L.h, tabs->data() + L.ytab);
+                int span = 0;                                // how far a thread's 4 outputs reach from its aligned first source byte
+                for (int x = 0; x < L.w; x += 4) {
+                    const int a = (int)((*tabs)[L.xtab + x] & 0xffffu) & ~3;
+                    const int xl = std::min(x + 3, L.w - 1);
+                    span = std::max(span, (int)((*tabs)[L.xtab + xl] & 0xffffu) - a);
+                }
+                g->L[l].xspan = span;
             }
         }
     }
@@ -209,6 +216,8 @@ int set_geometry(orbx_ctx* c, int w, int h)
     if (c->geom_w == w && c->geom_h == h) return ORBX_OK;
     std::vector<uint32_t> tabs;
     build_geom(c, w, h, &c->geom, &tabs);
+    for (int l = 1; l < c->nlevels; ++l)
+        if (c->geom.L[l].xspan > 11) { c->geom_w = c->geom_h = -1; return fail(c, ORBX_E_UNSUPPORTED, "scale_factor too large for the pyramid kernels (4 outputs must span <= 12 source bytes: about 2.6)"); }
     int rc = ensure(c, c->tabs, tabs.size() * 4);
     if (rc) return rc;
     CU(cudaMemcpyAsync(c->tabs.p, tabs.data(), tabs.size() * 4, cudaMemcpyHostToDevice, c->stream));
@@ -247,7 +256,9 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, cudaStream_t side, cudaEvent
 
     if (marks) stage_mark(c, 0);
     const int aligned4 = ((reinterpret_cast<uintptr_t>(d_imgs) | step | frame_stride) & 3) == 0;
-    if (fused) {
+    bool narrow = true;                                      // every level within the 3-word window of the narrow pyramid kernels
+    for (int l = 1; l < g.nlevels; ++l) narrow = narrow && g.L[l].xspan <= 7;
+    if (fused && narrow) {
         // the batch alone fills the GPU: one CTA per frame runs gray + the whole level chain in a single launch
         if (channels == 3) k_gray_pyr<3><<<B, GP_NT, 0, st>>>(d_imgs, frame_stride, step, aligned4, g, pyr, tabs);
         else               k_gray_pyr<1><<<B, GP_NT, 0, st>>>(d_imgs, frame_stride, step, aligned4, g, pyr, tabs);
@@ -267,7 +278,8 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, cudaStream_t side, cudaEvent
             if (g.L[l].w <= 0 || g.L[l].h <= 0) continue;
             const dim3 blk(32, PYR_BY);
             const dim3 grd((unsigned)((g.L[l].pitch / 4 + 31) / 32), (unsigned)((g.L[l].h + PYR_RH * PYR_BY - 1) / (PYR_RH * PYR_BY)), B);
-            k_pyr_down<<<grd, blk, 0, st>>>(g, l, pyr, tabs);
+            if (g.L[l].xspan <= 7) k_pyr_down<false><<<grd, blk, 0, st>>>(g, l, pyr, tabs);
+            else                   k_pyr_down<true><<<grd, blk, 0, st>>>(g, l, pyr, tabs);
             ++c->launches;
         }
     }

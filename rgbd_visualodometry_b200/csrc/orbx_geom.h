@@ -34,6 +34,7 @@ struct LevelGeom {
     int nbands;
     int blur0, nblur, blur_cgs;  // blur tiles: first tile index, tile count (= column groups x strip groups), column groups
     uint32_t xtab, ytab;      // offsets (u32 units) of the INTER_LINEAR_EXACT tap tables: i0 | c1 << 16
+    int xspan;                // max over 4-column groups of (left tap of the group's last column) - (its aligned first byte): <= 7 narrow kernel, <= 11 wide
     unsigned long long img_off;   // bytes, inside the frame's pyr block
     unsigned long long cnt_off;   // u32 units, inside the frame's rowcnt block
     unsigned long long ent_off;   // u32 units, inside the frame's rowent block

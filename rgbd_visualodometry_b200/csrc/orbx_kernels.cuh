@@ -172,6 +172,10 @@ __device__ __forceinline__ void pyr_down_item(const Geom& g, int l, int f, int x
 // arithmetic of the rows already there instead of in front of every output row.
 constexpr int PYR_DEPTH = 8;
 constexpr int PYR_NT = 32 * PYR_BY;
+// WIDE = false: the 4 outputs of a thread reach at most 7 bytes past its aligned first source byte (scale factors up to
+// ~1.5, the reference's 1.2 included): 3 source words, one predicated select per operand.  WIDE = true: up to 11 bytes
+// (scale factors up to ~2.6): 4 source words, two selects per operand.
+template <bool WIDE>
 __global__ void __launch_bounds__(PYR_NT) k_pyr_down(const __grid_constant__ Geom g, int l, uint8_t* pyr, const uint32_t* __restrict__ tabs)
 {
     __shared__ __align__(16) uint8_t s_ring[PYR_DEPTH * PYR_NT * 16];
@@ -187,18 +191,19 @@ __global__ void __launch_bounds__(PYR_NT) k_pyr_down(const __grid_constant__ Geo
         return;
     }
     uint32_t coef[4], sh[4];
-    bool hi[4];
+    bool hi[4], hi2[4];
     const int a = (int)(__ldg(tabs + D.xtab + x) & 0xffffu) & ~3;   // aligned source byte all four outputs are addressed from
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const uint32_t t = (x + k < D.w) ? __ldg(tabs + D.xtab + x + k) : (uint32_t)a;  // padding columns: taps 0 -> output 0
-        const int off = (int)(t & 0xffffu) - a;              // 0 .. 7
+        const int off = (int)(t & 0xffffu) - a;              // 0 .. 7 (narrow), 0 .. 11 (wide)
         const uint32_t c1 = t >> 16;
         coef[k] = (x + k < D.w) ? ((256u - c1) | (c1 << 16)) : 0u;
         hi[k] = off >= 4;
+        hi2[k] = off >= 8;
         sh[k] = (uint32_t)(off & 3) * 8u;
     }
-    const bool w2ok = a + 8 < S.pitch;
+    const bool w2ok = a + 8 < S.pitch, w3ok = WIDE && a + 12 < S.pitch;
     const uint32_t* ytab = tabs + D.ytab;
     const int s0 = (int)(__ldg(ytab + ys) & 0xffffu);
     const int s1 = min((int)(__ldg(ytab + ye - 1) & 0xffffu) + 1, S.h - 1);         // last source row needed
@@ -211,6 +216,7 @@ __global__ void __launch_bounds__(PYR_NT) k_pyr_down(const __grid_constant__ Geo
             const unsigned sa = ring + d * (PYR_NT * 16u);
             cp_async_4(sa, p); cp_async_4(sa + 4u, p + 4);
             if (w2ok) cp_async_4(sa + 8u, p + 8);
+            if (w3ok) cp_async_4(sa + 12u, p + 12);
         }
         cp_async_commit();
     }
@@ -233,17 +239,19 @@ __global__ void __launch_bounds__(PYR_NT) k_pyr_down(const __grid_constant__ Geo
         if (to_fetch > 0) {
             cp_async_4(sa, src); cp_async_4(sa + 4u, src + 4);
             if (w2ok) cp_async_4(sa + 8u, src + 8);
+            if (w3ok) cp_async_4(sa + 12u, src + 12);
         }
         cp_async_commit();
         --to_fetch;
         src += S.pitch;
         sa += PYR_NT * 16u;
         if (sa == ring_end) sa = ring;
-        const uint32_t w2 = w2ok ? w.z : 0u;
+        const uint32_t w2 = w2ok ? w.z : 0u, w3 = w3ok ? w.w : 0u;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const uint32_t v = __funnelshift_r(hi[k] ? w.y : w.x, hi[k] ? w2 : w.y, sh[k]);
-            hc.h[k] = __dp2a_lo(coef[k], v, 0u);
+            uint32_t lo = hi[k] ? w.y : w.x, up = hi[k] ? w2 : w.y;
+            if (WIDE) { lo = hi2[k] ? w2 : lo; up = hi2[k] ? w3 : up; }
+            hc.h[k] = __dp2a_lo(coef[k], __funnelshift_r(lo, up, sh[k]), 0u);
         }
         while (emit_at == s && y < ye) {                     // (two outputs per source row only when the bottom row clamps)
             const bool clamped = (int)(ty & 0xffffu) == s;   // y1 == y0: both taps read the last source row

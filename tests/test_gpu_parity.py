@@ -310,3 +310,23 @@ def test_fused_extract_match_batch_equals_separate_calls_and_oracle(orbmod):
     ko, do = O.detect_and_compute(frames[0], n)
     assert kps[0, :cnt[0]].tobytes() == ko.tobytes() and np.array_equal(desc[0, :cnt[0]], do)
     assert best[0][0].tobytes() == O.match_hamming(maps[0], do).tobytes()
+
+
+@pytest.mark.parametrize("params", [(300, 1.5, 4), (400, 2.0, 3), (600, 1.1, 12), (500, 1.2, 1), (500, 1.3, 6), (250, 2.5, 2)])
+def test_orb_other_scale_factors_and_level_counts(orbmod, params):
+    """cv::ORB::create(nfeatures, scaleFactor, nlevels) with values other than the reference's yaml (1.2 / 8): the narrow
+    and the wide pyramid kernels, 1 .. 12 levels.  Oracle == cv2 for these is pinned on the CPU side (test_oracle.py)."""
+    from oracle import oracle as O
+    from rgbd_visualodometry_b200.synth import synth_frame
+    n, sf, nl = params
+    img = synth_frame(480, 640, 31)
+    k, d = orbmod.ORB_create(n, sf, nl).detectAndCompute(img, None)
+    ko, do = O.detect_and_compute(img, n, sf, nl)
+    _assert_kp_equal(k, d, ko, do, f"ORB({n}, {sf}, {nl})")
+
+
+def test_orb_rejects_scale_factor_beyond_the_pyramid_kernels(orbmod):
+    from rgbd_visualodometry_b200.synth import synth_frame
+    with pytest.raises(orbmod.OrbxError) as e:
+        orbmod.ORB_create(100, 3.5, 2).detectAndCompute(synth_frame(240, 320, 1), None)
+    assert e.value.code == -5                                # ORBX_E_UNSUPPORTED, never a silently wrong pyramid

@@ -150,3 +150,14 @@ class TestLiveCv2:
         q = synth_map_queries(t, 1500, 31)
         m = cv2.BFMatcher(cv2.NORM_HAMMING).match(q, t)
         assert oracle.match_hamming(q, t).tobytes() == oracle.cv2_matches_to_array(m).tobytes()
+
+
+@pytest.mark.skipif(cv2 is None, reason="cv2 not importable")
+@pytest.mark.parametrize("params", [(300, 1.5, 4), (400, 2.0, 3), (600, 1.1, 12), (500, 1.2, 1), (250, 2.5, 2)])
+def test_oracle_other_parameters_vs_cv2_live(oracle, params):
+    from rgbd_visualodometry_b200.synth import synth_frame
+    n, sf, nl = params
+    img = synth_frame(480, 640, 31)
+    k, d = oracle.detect_and_compute(img, n, sf, nl)
+    kc, dc = cv2.ORB_create(n, sf, nl).detectAndCompute(img, None)
+    assert k.tobytes() == oracle.cv2_keypoints_to_array(kc).tobytes() and np.array_equal(d, dc)
