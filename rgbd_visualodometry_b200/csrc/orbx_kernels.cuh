@@ -362,6 +362,7 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
     constexpr int ITEMS = (2 * SR + NWARP - 1) / NWARP;   // (row, half) items per warp
     constexpr int QCAP = ITEMS * 128;      // private queue capacity: every pixel of the warp's items
     static_assert(R * MW <= NT, "phase D needs one thread per mask word");
+    static_assert((R * MW) % 32 == 0, "phase D shuffles with a full-warp mask: its threads must be whole warps (R = 14 hangs)");
 
     __shared__ __align__(16) uint16_t s_img[TR * TP];
     __shared__ __align__(16) uint8_t s_score[SR * SP];
