@@ -288,25 +288,19 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, cudaStream_t side, cudaEvent
         k_fast_bands<FAST_R, FAST_NT><<<dim3((unsigned)g.total_bands, B), FAST_NT, 0, st>>>(g, pyr, rowcnt, rowent);
         ++c->launches;
     }
-    if (side && g.total_blur > 0 && !(dbg_skip & 1)) {
-        // The blur only needs the pyramid.  It is issue-bound while the selection kernel is latency-bound (serial
-        // introselect chains), so it is queued on a second stream BEHIND FAST and runs underneath k_select.
-        CU(cudaEventRecord(ev_a, st));
-        CU(cudaStreamWaitEvent(side, ev_a, 0));
-        k_blur<<<dim3((unsigned)g.total_blur, B), BLUR_NT, 0, side>>>(g, pyr, blur);
-        ++c->launches;
-        CU(cudaEventRecord(ev_b, side));
-    }
+    // (Selection and blur were also tried as interleaved CTAs of one launch and as concurrent kernels on a side stream:
+    //  neither beats running them back to back -- the selection kernel is bound by the latency of its longest CTA, not by
+    //  issue slots it could lend to the blur.)
+    (void)side; (void)ev_a; (void)ev_b;
     if (marks) stage_mark(c, 3);
     k_select<<<dim3(B, (unsigned)g.nlevels), SEL_NT, 0, st>>>(g, pyr, rowcnt, rowent, work, selpos, fincnt, status);
     ++c->launches;
     if (marks) stage_mark(c, 4);
-    if (!side && g.total_blur > 0 && !(dbg_skip & 1)) {
+    if (g.total_blur > 0 && !(dbg_skip & 1)) {
         k_blur<<<dim3((unsigned)g.total_blur, B), BLUR_NT, 0, st>>>(g, pyr, blur);
         ++c->launches;
     }
     if (marks) stage_mark(c, 5);
-    if (side && g.total_blur > 0 && !(dbg_skip & 1)) CU(cudaStreamWaitEvent(st, ev_b, 0));
     if (!(dbg_skip & 2)) k_describe<<<dim3((unsigned)((std::max(cap, 1) + DESC_KPB * DESC_KPW - 1) / (DESC_KPB * DESC_KPW)), B), DESC_NT, 0, st>>>(
         g, pyr, blur, work, fincnt, (const float4*)c->pattern.p, d_kps, d_desc, d_counts, cap);
     ++c->launches;

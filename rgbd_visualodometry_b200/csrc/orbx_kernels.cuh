@@ -26,6 +26,10 @@ __device__ __forceinline__ unsigned vmax2(unsigned a, unsigned b) { return __vma
 __device__ __forceinline__ unsigned vmax3(unsigned a, unsigned b, unsigned c) { return __vimax3_u16x2(a, b, c); }
 __device__ __forceinline__ unsigned vmin3(unsigned a, unsigned b, unsigned c) { return __vimin3_u16x2(a, b, c); }
 
+// Loads the compiler may not sink next to their first use: issued back to back, they are all in flight together.
+__device__ __forceinline__ uint32_t ldg_u8_now(const uint8_t* p) { uint32_t v; asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ uint32_t ldg_u32_now(const void* p) { uint32_t v; asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+
 // cp.async (LDGSTS): global -> shared copies that cost neither registers nor scoreboards while in flight (a warp has six
 // scoreboards; a deep register-prefetch pipeline ends up sharing them and the oldest load waits for the youngest).
 __device__ __forceinline__ void cp_async_4(unsigned dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory"); }
@@ -780,25 +784,41 @@ __device__ int retain_best_block(Elem* v, int len, int m, PosT* Lp, PosT* Rp, Se
 // ------------------------------------------------------------------------------------------------ A.5 Harris
 __device__ __forceinline__ float harris_response(const uint8_t* __restrict__ img, int pitch, int x, int y)
 {
+    // The 9 x 9 neighbourhood as 9 rows x 3 aligned words, ALL loaded before anything is used: the candidate's loads are
+    // in flight together (one L2 round trip per candidate instead of a chain of byte loads -- the selection kernel is
+    // latency-bound and Harris was a third of its critical path).  The Sobel sums are taken separably per row:
+    //   d[i] = p[i+1] - p[i-1],  s[i] = p[i-1] + 2 p[i] + p[i+1]   ->   Ix = d(r-1) + 2 d(r) + d(r+1),  Iy = s(r+1) - s(r-1)
+    const int xa = (x - 4) & ~3;
+    const unsigned shb = (unsigned)((x - 4) & 3) * 8u;
+    const uint8_t* p = img + (size_t)(y - 4) * pitch + xa;
+    uint32_t w[9][3];
+#pragma unroll
+    for (int r = 0; r < 9; ++r, p += pitch) {
+        w[r][0] = ldg_u32_now(p); w[r][1] = ldg_u32_now(p + 4); w[r][2] = ldg_u32_now(p + 8);
+    }
     int a = 0, b = 0, c = 0;
-    // 9x9 neighbourhood walked row by row with a 3-row register window
-    uint8_t r0[9], r1[9], r2[9];
-    const uint8_t* p = img + (size_t)(y - 4) * pitch + (x - 4);
+    int d0[7] = {}, d1[7] = {}, d2[7] = {}, s0[7] = {}, s1[7] = {}, s2[7] = {};   // rows r-2, r-1, r of the horizontal differences / sums
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { r0[i] = __ldg(p + i); r1[i] = __ldg(p + pitch + i); }
+    for (int r = 0; r < 9; ++r) {
+        const uint32_t v0 = __funnelshift_r(w[r][0], w[r][1], shb), v1 = __funnelshift_r(w[r][1], w[r][2], shb), v2 = w[r][2] >> shb;
+        int px[9];
 #pragma unroll
-    for (int row = 0; row < 7; ++row) {
-        const uint8_t* pr = p + (size_t)(row + 2) * pitch;
+        for (int i = 0; i < 4; ++i) { px[i] = (int)((v0 >> (8 * i)) & 255u); px[4 + i] = (int)((v1 >> (8 * i)) & 255u); }
+        px[8] = (int)(v2 & 255u);
 #pragma unroll
-        for (int i = 0; i < 9; ++i) r2[i] = __ldg(pr + i);
-#pragma unroll
-        for (int i = 1; i < 8; ++i) {
-            const int Ix = ((int)r1[i + 1] - (int)r1[i - 1]) * 2 + ((int)r0[i + 1] - (int)r0[i - 1]) + ((int)r2[i + 1] - (int)r2[i - 1]);
-            const int Iy = ((int)r2[i] - (int)r0[i]) * 2 + ((int)r2[i - 1] - (int)r0[i - 1]) + ((int)r2[i + 1] - (int)r0[i + 1]);
-            a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
+        for (int i = 0; i < 7; ++i) {
+            d0[i] = d1[i]; d1[i] = d2[i]; s0[i] = s1[i]; s1[i] = s2[i];
+            d2[i] = px[i + 2] - px[i];
+            s2[i] = px[i] + 2 * px[i + 1] + px[i + 2];
         }
+        if (r >= 2) {
 #pragma unroll
-        for (int i = 0; i < 9; ++i) { r0[i] = r1[i]; r1[i] = r2[i]; }
+            for (int i = 0; i < 7; ++i) {
+                const int Ix = d0[i] + 2 * d1[i] + d2[i];
+                const int Iy = s2[i] - s0[i];
+                a += Ix * Ix; b += Iy * Iy; c += Ix * Iy;
+            }
+        }
     }
     const float fa = (float)a, fb = (float)b, fc = (float)c;
     const float det = __fsub_rn(__fmul_rn(fa, fb), __fmul_rn(fc, fc));
@@ -812,17 +832,18 @@ __device__ __forceinline__ float harris_response(const uint8_t* __restrict__ img
 // -> Harris on the survivors -> retainBest(n_l) on Harris.  The final list is left as the prefix of the level's
 // global workspace; its length goes to fincnt.  The working array (and the partition scratch) lives in shared
 // memory when the level's candidate count fits, else in global memory.
-__global__ void __launch_bounds__(SEL_NT, 8) k_select(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr,
-                                                   const uint32_t* __restrict__ rowcnt, const uint32_t* __restrict__ rowent,
-                                                   Elem* __restrict__ work, uint32_t* __restrict__ selpos, int* __restrict__ fincnt,
-                                                   int* __restrict__ status)
+struct SelSmem {
+    Elem v[SEL_SMEM_ELEMS];
+    uint16_t pos[2 * SEL_SMEM_ELEMS];
+    SelShared sh;
+};
+__device__ __forceinline__ void select_body(const Geom& g, const uint8_t* __restrict__ pyr, const uint32_t* __restrict__ rowcnt,
+                                            const uint32_t* __restrict__ rowent, Elem* __restrict__ work, uint32_t* __restrict__ selpos,
+                                            int* __restrict__ fincnt, int* __restrict__ status, int l, int f, SelSmem& sm)
 {
-    __shared__ Elem s_v[SEL_SMEM_ELEMS];
-    __shared__ uint16_t s_pos[2 * SEL_SMEM_ELEMS];
-    __shared__ SelShared sh;
-    // grid = (frames, levels): level-major dispatch, so the long level-0 CTAs of every frame start in the first wave and
-    // the short upper levels fill the tail
-    const int l = blockIdx.y, f = blockIdx.x;
+    Elem* const s_v = sm.v;
+    uint16_t* const s_pos = sm.pos;
+    SelShared& sh = sm.sh;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const LevelGeom& L = g.L[l];
     Elem* gv = work + (size_t)f * g.ws_frame + L.ws_off;
@@ -847,16 +868,43 @@ __global__ void __launch_bounds__(SEL_NT, 8) k_select(const __grid_constant__ Ge
     const bool in_smem = N <= SEL_SMEM_ELEMS;
     Elem* v = in_smem ? s_v : gv;
     {
+        // Rows in groups of four: the first 128-bit chunk of each row's list (row lists are 32-byte aligned and most hold
+        // fewer than four survivors) is requested for all four rows before any is consumed, so a thread's gather costs
+        // about one memory round trip per group instead of one per entry.
         int o = woff + inc - mine;
-        for (int r = rb; r < re; ++r) {
-            const int c = (int)cnt[r];
-            const uint32_t* e = ent + (size_t)r * L.ent_pitch;
-            for (int i = 0; i < c; ++i) {
-                const uint32_t w = e[i];
-                Elem el;
-                el.response = (float)(w >> 16);
-                el.pos = ((uint32_t)(r + ORBX_EDGE) << 16) | (w & 0xffffu);
-                v[o++] = el;
+        for (int r0 = rb; r0 < re; r0 += 4) {
+            int cc[4];
+            uint4 w4[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) cc[k] = r0 + k < re ? (int)cnt[r0 + k] : 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                w4[k] = make_uint4(0u, 0u, 0u, 0u);
+                if (cc[k] > 0) w4[k] = __ldg(reinterpret_cast<const uint4*>(ent + (size_t)(r0 + k) * L.ent_pitch));
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int r = r0 + k, c = cc[k];
+                const uint32_t ypart = (uint32_t)(r + ORBX_EDGE) << 16;
+                const uint32_t first[4] = {w4[k].x, w4[k].y, w4[k].z, w4[k].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < c) {
+                        Elem el;
+                        el.response = (float)(first[i] >> 16);
+                        el.pos = ypart | (first[i] & 0xffffu);
+                        v[o++] = el;
+                    }
+                if (c > 4) {
+                    const uint32_t* e = ent + (size_t)r * L.ent_pitch;
+                    for (int i = 4; i < c; ++i) {
+                        const uint32_t w = e[i];
+                        Elem el;
+                        el.response = (float)(w >> 16);
+                        el.pos = ypart | (w & 0xffffu);
+                        v[o++] = el;
+                    }
+                }
             }
         }
     }
@@ -878,6 +926,17 @@ __global__ void __launch_bounds__(SEL_NT, 8) k_select(const __grid_constant__ Ge
                            : retain_best_block<uint32_t>(v, n1, L.quota, gpos, gpos + N, &sh, &flag);
     if (tid == 0) { fincnt[f * g.nlevels + l] = n2; if (flag) atomicOr(&status[f], flag); }
     if (v != gv) for (int i = tid; i < n2; i += SEL_NT) gv[i] = v[i];
+}
+
+// grid = (frames, levels): level-major dispatch, so the long level-0 CTAs of every frame start in the first wave and
+// the short upper levels fill the tail
+__global__ void __launch_bounds__(SEL_NT, 8) k_select(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr,
+                                                   const uint32_t* __restrict__ rowcnt, const uint32_t* __restrict__ rowent,
+                                                   Elem* __restrict__ work, uint32_t* __restrict__ selpos, int* __restrict__ fincnt,
+                                                   int* __restrict__ status)
+{
+    __shared__ SelSmem sm;
+    select_body(g, pyr, rowcnt, rowent, work, selpos, fincnt, status, blockIdx.y, blockIdx.x, sm);
 }
 
 
@@ -958,9 +1017,6 @@ constexpr int BLUR_RH = 64;            // output rows per thread
 constexpr int BLUR_NT = 128;           // work items per CTA
 constexpr int BLUR_LO = 12;            // first produced column (8-column groups start at 12 + 8q, so x0 - 4 is 8-byte aligned)
 
-// Loads the compiler may not sink next to their first use: issued back to back, they are all in flight together.
-__device__ __forceinline__ uint32_t ldg_u8_now(const uint8_t* p) { uint32_t v; asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
-__device__ __forceinline__ uint32_t ldg_u32_now(const void* p) { uint32_t v; asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 
 __device__ __forceinline__ float u8f(uint32_t w, uint32_t sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, sel)) - 8388608.0f; }
 
@@ -1004,20 +1060,20 @@ __device__ __forceinline__ void blur_cp_row(unsigned dst, const uint8_t* src, bo
     else sts_u64_zero(dst + 8u);
 }
 
-__global__ void __launch_bounds__(BLUR_NT) k_blur(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur)
+constexpr int BLUR_RING_BYTES = BLUR_DEPTH * BLUR_NT * 16;
+// tile = index of the CTA's work inside the frame's blur tile list, f = frame, s_ring = BLUR_RING_BYTES of shared memory
+__device__ __forceinline__ void blur_body(const Geom& g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, int tile, int f, uint8_t* s_ring)
 {
-    __shared__ __align__(16) uint8_t s_ring[BLUR_DEPTH * BLUR_NT * 16];
-    const int f = blockIdx.y;
     int l = 0;
 #pragma unroll 1
-    for (int i = 1; i < g.nlevels; ++i) if ((int)blockIdx.x >= g.L[i].blur0) l = i;
+    for (int i = 1; i < g.nlevels; ++i) if (tile >= g.L[i].blur0) l = i;
     const LevelGeom& L = g.L[l];
-    const int item = (blockIdx.x - L.blur0) * BLUR_NT + threadIdx.x;
+    const int item = (tile - L.blur0) * BLUR_NT + threadIdx.x;
     const int strip = item / L.blur_cgs, cg = item - strip * L.blur_cgs;
     const int x0 = BLUR_LO + cg * 8;                                              // first of this thread's 8 columns
     const int ys = 13 + strip * BLUR_RH;                                          // first output row
     const int ye = min(ys + BLUR_RH, L.h - 13);
-    if ((int)blockIdx.x - L.blur0 >= L.nblur || ys >= ye) return;
+    if (tile - L.blur0 >= L.nblur || ys >= ye) return;
     const float k0 = __int_as_float(0x3d8fafb1), k1 = __int_as_float(0x3e06387e), k2 = __int_as_float(0x3e434a39), k3 = __int_as_float(0x3e5d4ae0);
     const unsigned long long K0 = f2_pack(k0, k0), K1 = f2_pack(k1, k1), K2 = f2_pack(k2, k2), K3 = f2_pack(k3, k3);
     const unsigned long long NEG23 = f2_pack(-8388608.0f, -8388608.0f), RND = f2_pack(12582912.0f, 12582912.0f);
@@ -1087,6 +1143,12 @@ __global__ void __launch_bounds__(BLUR_NT) k_blur(const __grid_constant__ Geom g
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(BLUR_NT) k_blur(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur)
+{
+    __shared__ __align__(16) uint8_t s_ring[BLUR_RING_BYTES];
+    blur_body(g, pyr, blur, blockIdx.x, blockIdx.y, s_ring);
 }
 
 // ------------------------------------------------------------------------------------------------ A.7 / A.9 / A.10 describe
