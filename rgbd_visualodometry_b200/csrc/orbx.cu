@@ -75,11 +75,7 @@ struct orbx_ctx {
 
     bool profiling = false;
     cudaEvent_t ev[N_STAGES + 2] = {};   // 0..6 bracket the six extraction stages, 7..8 the matcher
-    cudaStream_t stream2 = nullptr;      // blur runs here, concurrently with FAST + selection (unless profiling)
-    cudaEvent_t ev_pyr = nullptr, ev_blur = nullptr;
     cudaStream_t lane[4] = {};           // extra frame-range pipelines (lane 0 is `stream`)
-    cudaStream_t lane_side[4] = {};      // per-lane side stream: the lane's blur runs under its (latency-bound) selection kernel
-    cudaEvent_t lane_eva[4] = {}, lane_evb[4] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[4] = {};
     float stage_ms[N_STAGES] = {};
     bool stage_valid[N_STAGES] = {};
@@ -233,8 +229,8 @@ void stage_mark(orbx_ctx* c, int i)
 
 // The extraction pipeline on device-resident frames; everything asynchronous on c->stream.
 // The kernel sequence for frames [f0, f0 + nb) on stream `st`.  Every buffer is frame-major, so a frame range is
-// just a base-pointer offset.  `side` (may be null) is a second stream the blur is queued on behind FAST.
-int run_extract_range(orbx_ctx* c, cudaStream_t st, cudaStream_t side, cudaEvent_t ev_a, cudaEvent_t ev_b, bool marks, bool fused, int f0, int nb,
+// just a base-pointer offset.
+int run_extract_range(orbx_ctx* c, cudaStream_t st, bool marks, bool fused, int f0, int nb,
                       const uint8_t* d_imgs, size_t step, size_t frame_stride, int channels, float* d_kps, uint8_t* d_desc, int cap,
                       int* d_counts)
 {
@@ -252,7 +248,6 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, cudaStream_t side, cudaEvent
     d_kps += F * cap * 7; d_desc += F * cap * 32; d_counts += F;
     const uint32_t* tabs = (const uint32_t*)c->tabs.p;
     const unsigned B = (unsigned)nb;
-    static const int dbg_skip = getenv("ORBX_SKIP") ? atoi(getenv("ORBX_SKIP")) : 0;   // debugging only: 1 = no blur, 2 = no describe
 
     if (marks) stage_mark(c, 0);
     const int aligned4 = ((reinterpret_cast<uintptr_t>(d_imgs) | step | frame_stride) & 3) == 0;
@@ -291,17 +286,16 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, cudaStream_t side, cudaEvent
     // (Selection and blur were also tried as interleaved CTAs of one launch and as concurrent kernels on a side stream:
     //  neither beats running them back to back -- the selection kernel is bound by the latency of its longest CTA, not by
     //  issue slots it could lend to the blur.)
-    (void)side; (void)ev_a; (void)ev_b;
     if (marks) stage_mark(c, 3);
     k_select<<<dim3(B, (unsigned)g.nlevels), SEL_NT, 0, st>>>(g, pyr, rowcnt, rowent, work, selpos, fincnt, status);
     ++c->launches;
     if (marks) stage_mark(c, 4);
-    if (g.total_blur > 0 && !(dbg_skip & 1)) {
+    if (g.total_blur > 0) {
         k_blur<<<dim3((unsigned)g.total_blur, B), BLUR_NT, 0, st>>>(g, pyr, blur);
         ++c->launches;
     }
     if (marks) stage_mark(c, 5);
-    if (!(dbg_skip & 2)) k_describe<<<dim3((unsigned)((std::max(cap, 1) + DESC_KPB * DESC_KPW - 1) / (DESC_KPB * DESC_KPW)), B), DESC_NT, 0, st>>>(
+    k_describe<<<dim3((unsigned)((std::max(cap, 1) + DESC_KPB * DESC_KPW - 1) / (DESC_KPB * DESC_KPW)), B), DESC_NT, 0, st>>>(
         g, pyr, blur, work, fincnt, (const float4*)c->pattern.p, d_kps, d_desc, d_counts, cap);
     ++c->launches;
     if (marks) stage_mark(c, 6);
@@ -325,17 +319,16 @@ int run_extract(orbx_ctx* c, const uint8_t* d_imgs, int batch, int w, int h, siz
     const bool fused = batch / lanes >= FUSED_PYR_MIN_BATCH;    // per-stage profiling (one lane) times the same kernels the lanes run
     if (c->profiling) lanes = 1;
     if (lanes == 1) {
-        rc = run_extract_range(c, c->stream, c->profiling ? nullptr : c->stream2, c->ev_pyr, c->ev_blur, c->profiling, fused, 0, batch, d_imgs, step,
+        rc = run_extract_range(c, c->stream, c->profiling, fused, 0, batch, d_imgs, step,
                                frame_stride, channels, d_kps, d_desc, cap, d_counts);
         if (rc) return rc;
     } else {
-        static const bool lane_sides = !(getenv("ORBX_LANE_SIDES") && atoi(getenv("ORBX_LANE_SIDES")) == 0);
         CU(cudaEventRecord(c->ev_fork, c->stream));
         for (int k = 0; k < lanes; ++k) {
             const int f0 = (int)((long)batch * k / lanes), f1 = (int)((long)batch * (k + 1) / lanes);
             cudaStream_t st = k == 0 ? c->stream : c->lane[k];
             if (k > 0) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
-            rc = run_extract_range(c, st, lane_sides ? c->lane_side[k] : nullptr, c->lane_eva[k], c->lane_evb[k], false, fused, f0, f1 - f0, d_imgs, step, frame_stride, channels, d_kps, d_desc, cap, d_counts);
+            rc = run_extract_range(c, st, false, fused, f0, f1 - f0, d_imgs, step, frame_stride, channels, d_kps, d_desc, cap, d_counts);
             if (rc) return rc;
             if (k > 0) { CU(cudaEventRecord(c->ev_join[k], st)); CU(cudaStreamWaitEvent(c->stream, c->ev_join[k], 0)); }
         }
@@ -495,14 +488,9 @@ int orbx_create(orbx_ctx** out, int device, int nfeatures, float scale_factor, i
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(ORBX_E_CUDA);
     if (prop.major != 10) return bail(ORBX_E_CUDA);          // sm_100a only: no other code path exists
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(ORBX_E_CUDA);
-    if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) return bail(ORBX_E_CUDA);
     for (int k = 1; k < 4; ++k)
         if (cudaStreamCreateWithFlags(&c->lane[k], cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming) != cudaSuccess) return bail(ORBX_E_CUDA);
-    for (int k = 0; k < 4; ++k)
-        if (cudaStreamCreateWithFlags(&c->lane_side[k], cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&c->lane_eva[k], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&c->lane_evb[k], cudaEventDisableTiming) != cudaSuccess) return bail(ORBX_E_CUDA);
     if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(ORBX_E_CUDA);
-    if (cudaEventCreateWithFlags(&c->ev_pyr, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_blur, cudaEventDisableTiming) != cudaSuccess) return bail(ORBX_E_CUDA);
     for (int i = 0; i < N_STAGES + 2; ++i) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail(ORBX_E_CUDA);
     build_geom(c, max_w, max_h, &c->geom_max, nullptr);
     const Geom& g = c->geom_max;
@@ -532,7 +520,6 @@ void orbx_destroy(orbx_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    if (c->stream2) cudaStreamSynchronize(c->stream2);
     Buf* bufs[] = {&c->pyr, &c->blur, &c->rowcnt, &c->rowent, &c->work, &c->selpos, &c->fincnt, &c->status, &c->tabs, &c->pattern, &c->in, &c->kps,
                    &c->desc, &c->counts, &c->mq, &c->mt, &c->mbest, &c->msecond, &c->mkeys, &c->mstatus, &c->mcounts, &c->mtrace,
                    &c->t_desc, &c->t_pos, &c->t_nrm, &c->t_outl, &c->t_slots, &c->t_cand, &c->t_ncand, &c->t_q, &c->t_in, &c->t_best, &c->t_filtered,
@@ -541,11 +528,7 @@ void orbx_destroy(orbx_ctx* c)
     if (c->h_small) cudaFreeHost(c->h_small);
     for (int i = 0; i < N_STAGES + 2; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int k = 1; k < 4; ++k) { if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); if (c->lane[k]) { cudaStreamSynchronize(c->lane[k]); cudaStreamDestroy(c->lane[k]); } }
-    for (int k = 0; k < 4; ++k) { if (c->lane_eva[k]) cudaEventDestroy(c->lane_eva[k]); if (c->lane_evb[k]) cudaEventDestroy(c->lane_evb[k]); if (c->lane_side[k]) { cudaStreamSynchronize(c->lane_side[k]); cudaStreamDestroy(c->lane_side[k]); } }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-    if (c->ev_pyr) cudaEventDestroy(c->ev_pyr);
-    if (c->ev_blur) cudaEventDestroy(c->ev_blur);
-    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -608,8 +591,7 @@ int orbx_detect_and_compute_batch(orbx_ctx* c, const uint8_t* const* imgs, int b
         cudaStream_t st = k == 0 ? c->stream : c->lane[k];
         if (k > 0) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
         if ((rc = upload_frames(c, st, imgs, f0, f1, step, row, h, dstep, fstride))) return rc;
-        const bool side = lanes == 1 && !c->profiling;
-        if ((rc = run_extract_range(c, st, side ? c->stream2 : nullptr, c->ev_pyr, c->ev_blur, c->profiling, f1 - f0 >= FUSED_PYR_MIN_BATCH, f0, f1 - f0, (const uint8_t*)c->in.p, dstep,
+        if ((rc = run_extract_range(c, st, c->profiling, f1 - f0 >= FUSED_PYR_MIN_BATCH, f0, f1 - f0, (const uint8_t*)c->in.p, dstep,
                                     fstride, channels, (float*)c->kps.p, (uint8_t*)c->desc.p, cap, (int*)c->counts.p)))
             return rc;
         const size_t n = (size_t)(f1 - f0);
@@ -684,7 +666,7 @@ int orbx_extract_match_batch(orbx_ctx* c, const uint8_t* const* imgs, int batch,
         cudaStream_t st = k == 0 ? c->stream : c->lane[k];
         if (k > 0) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
         if ((rc = upload_frames(c, st, imgs, f0, f1, step, row, h, dstep, fstride))) return rc;
-        if ((rc = run_extract_range(c, st, nullptr, nullptr, nullptr, c->profiling, f1 - f0 >= FUSED_PYR_MIN_BATCH, f0, f1 - f0, (const uint8_t*)c->in.p, dstep,
+        if ((rc = run_extract_range(c, st, c->profiling, f1 - f0 >= FUSED_PYR_MIN_BATCH, f0, f1 - f0, (const uint8_t*)c->in.p, dstep,
                                     fstride, channels, (float*)c->kps.p, (uint8_t*)c->desc.p, cap, (int*)c->counts.p)))
             return rc;
         CU(cudaMemcpyAsync(h_counts + f0, (int*)c->counts.p + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
