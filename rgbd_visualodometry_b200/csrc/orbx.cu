@@ -31,7 +31,8 @@ const int8_t k_pattern_host[256 * 4] = {
 };
 
 constexpr int FAST_R = 16, FAST_NT = 256;
-constexpr int MAX_LANES = 4;               // concurrent frame-range pipelines of one extraction call
+constexpr int MAX_LANES = 4;               // concurrent frame-range pipelines of one device-resident extraction call
+constexpr int HOST_MAX_LANES = 8;          // host-buffer calls: more, shorter ranges shrink the un-overlapped head (first upload) and tail
 constexpr int LANE_MIN_FRAMES = 64;        // a lane must still fill the GPU on its own
 constexpr int HOST_LANE_MIN_FRAMES = 16;   // host-buffer batches: lanes mainly overlap PCIe copies with kernels
 constexpr int FUSED_PYR_MIN_BATCH = 128;   // from this batch size on, one CTA per frame (k_gray_pyr) fills the GPU
@@ -75,8 +76,8 @@ struct orbx_ctx {
 
     bool profiling = false;
     cudaEvent_t ev[N_STAGES + 2] = {};   // 0..6 bracket the six extraction stages, 7..8 the matcher
-    cudaStream_t lane[4] = {};           // extra frame-range pipelines (lane 0 is `stream`)
-    cudaEvent_t ev_fork = nullptr, ev_join[4] = {};
+    cudaStream_t lane[HOST_MAX_LANES] = {};   // extra frame-range pipelines (lane 0 is `stream`)
+    cudaEvent_t ev_fork = nullptr, ev_join[HOST_MAX_LANES] = {};
     float stage_ms[N_STAGES] = {};
     bool stage_valid[N_STAGES] = {};
 };
@@ -488,7 +489,7 @@ int orbx_create(orbx_ctx** out, int device, int nfeatures, float scale_factor, i
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(ORBX_E_CUDA);
     if (prop.major != 10) return bail(ORBX_E_CUDA);          // sm_100a only: no other code path exists
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(ORBX_E_CUDA);
-    for (int k = 1; k < 4; ++k)
+    for (int k = 1; k < HOST_MAX_LANES; ++k)
         if (cudaStreamCreateWithFlags(&c->lane[k], cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming) != cudaSuccess) return bail(ORBX_E_CUDA);
     if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(ORBX_E_CUDA);
     for (int i = 0; i < N_STAGES + 2; ++i) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail(ORBX_E_CUDA);
@@ -527,7 +528,7 @@ void orbx_destroy(orbx_ctx* c)
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     if (c->h_small) cudaFreeHost(c->h_small);
     for (int i = 0; i < N_STAGES + 2; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-    for (int k = 1; k < 4; ++k) { if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); if (c->lane[k]) { cudaStreamSynchronize(c->lane[k]); cudaStreamDestroy(c->lane[k]); } }
+    for (int k = 1; k < HOST_MAX_LANES; ++k) { if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); if (c->lane[k]) { cudaStreamSynchronize(c->lane[k]); cudaStreamDestroy(c->lane[k]); } }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -580,11 +581,12 @@ int orbx_detect_and_compute_batch(orbx_ctx* c, const uint8_t* const* imgs, int b
     for (int i = 0; i < batch; ++i) if (!imgs[i]) return fail(c, ORBX_E_ARG, "null frame pointer");
     if ((rc = set_geometry(c, w, h))) return rc;
     CU(cudaMemsetAsync(c->status.p, 0, sizeof(int) * (size_t)batch, c->stream));
+    static const int host_lanes_max = std::max(1, std::min(HOST_MAX_LANES, getenv("ORBX_HOST_LANES") ? atoi(getenv("ORBX_HOST_LANES")) : HOST_MAX_LANES));
     int* h_counts = c->h_small;
     int* h_status = c->h_small + batch;
     // Frame ranges ("lanes") on their own streams: upload -> kernels -> download per lane, so the H2D copy of lane k+1
     // runs under the kernels of lane k and the D2H of lane k under the kernels of lane k+1 (PCIe is the bound here).
-    const int lanes = c->profiling ? 1 : std::max(1, std::min(MAX_LANES, batch / HOST_LANE_MIN_FRAMES));
+    const int lanes = c->profiling ? 1 : std::max(1, std::min(host_lanes_max, batch / HOST_LANE_MIN_FRAMES));
     if (lanes > 1) CU(cudaEventRecord(c->ev_fork, c->stream));
     for (int k = 0; k < lanes; ++k) {
         const int f0 = (int)((long)batch * k / lanes), f1 = (int)((long)batch * (k + 1) / lanes);
@@ -655,10 +657,11 @@ int orbx_extract_match_batch(orbx_ctx* c, const uint8_t* const* imgs, int batch,
             off += (size_t)nq[j];
         }
     }
+    static const int host_lanes_max = std::max(1, std::min(HOST_MAX_LANES, getenv("ORBX_HOST_LANES") ? atoi(getenv("ORBX_HOST_LANES")) : HOST_MAX_LANES));
     int* h_counts = c->h_small;
     int* h_status = c->h_small + batch;
     int* h_mstatus = c->h_small + 2 * batch;
-    const int lanes = c->profiling ? 1 : std::max(1, std::min(MAX_LANES, batch / HOST_LANE_MIN_FRAMES));
+    const int lanes = c->profiling ? 1 : std::max(1, std::min(host_lanes_max, batch / HOST_LANE_MIN_FRAMES));
     CU(cudaEventRecord(c->ev_fork, c->stream));
     for (int k = 0; k < lanes; ++k) {
         const int f0 = (int)((long)batch * k / lanes), f1 = (int)((long)batch * (k + 1) / lanes);
