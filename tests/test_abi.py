@@ -78,3 +78,32 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 s = open(os.path.join(dp, f)).read()
                 assert "import cv2" not in s and "from oracle" not in s and "import oracle" not in s and "orb_oracle" not in s, f
+
+
+def test_header_is_plain_c_and_a_c_caller_links(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 and as C++11 (the reference is C++11, CMakeLists.txt:8), and a
+    plain C translation unit using it must link against liborbx.so (no C++ / torch types in the signatures)."""
+    import shutil
+    import subprocess
+    from rgbd_visualodometry_b200 import _lib
+    _lib.load()
+    hdr = os.path.join(ROOT, "include", "orbx.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr])
+    src = tmp_path / "caller.c"
+    src.write_text('''#include "orbx.h"
+#include <stdio.h>
+int main(void) {
+    orbx_ctx* c = 0;
+    int rc = orbx_create(&c, 0, 500, 1.2f, 8, 640, 480, 1);      /* no GPU in the build container: must fail, not fall back */
+    printf("%s rc=%d sizeof(kp)=%d sizeof(m)=%d\\n", orbx_version(), rc, (int)sizeof(orbx_keypoint), (int)sizeof(orbx_match));
+    if (c) orbx_destroy(c);
+    return (sizeof(orbx_keypoint) == 28 && sizeof(orbx_match) == 16) ? 0 : 1;
+}
+''')
+    exe = tmp_path / "caller"
+    libdir = os.path.dirname(_lib.SO)
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir, "-lorbx",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "sm_100a" in out.stdout, out.stdout + out.stderr
