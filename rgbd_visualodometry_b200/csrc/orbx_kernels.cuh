@@ -370,8 +370,9 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
 
     __shared__ __align__(16) uint16_t s_img[TR * TP];
     __shared__ __align__(16) uint8_t s_score[SR * SP];
-    __shared__ uint16_t s_q[NWARP][QCAP];  // pass queues:   sy << 8 | sx
-    __shared__ uint16_t s_cq[NWARP][QCAP]; // corner queues (NMS candidates inside the output region)
+    __shared__ uint16_t s_q[NWARP][QCAP];  // pass queues:   sy << 8 | sx; compacted IN PLACE to the corner queues (NMS candidates
+                                           // inside the output region) as phase B consumes them: a corner's slot index never
+                                           // passes the entries still to be read, so no second queue is needed
     __shared__ uint32_t s_mask[R * MW];
     __shared__ uint32_t s_rowcnt[R];
 
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
 
     if (tid < R) s_rowcnt[tid] = 0;
     uint16_t* myq = s_q[wid];
-    uint16_t* mycq = s_cq[wid];
+    uint16_t* mycq = s_q[wid];
 
     for (int ox0 = 28; ox0 < xend; ox0 += CWO) {
         const int ox1 = min(ox0 + CWO, xend);
@@ -492,6 +493,7 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
                 }
             }
             const unsigned bc = __ballot_sync(0xffffffffu, corner);
+            __syncwarp();                                    // every lane has read its entry of this batch before slots <= i0 + 31 are rewritten
             if (corner) mycq[cn + __popc(bc & lt)] = (uint16_t)e;
             cn += __popc(bc);
         }
