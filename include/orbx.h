@@ -55,6 +55,7 @@ typedef enum {
     ORBX_E_NOMEM = -4,       /* host or device allocation failed */
     ORBX_E_UNSUPPORTED = -5, /* valid OpenCV input this build does not cover (e.g. channels not 1 or 3) */
     ORBX_E_INTERNAL = -6,    /* an internal device-side bound was exceeded (never silently truncated) */
+    ORBX_E_BUSY = -8,        /* orbx_submit_frame: two frames are already in flight */
     ORBX_E_ORDER = -7        /* reserved (was: introselect depth-limit fallback not reproduced; the fallback is implemented now) */
 } orbx_status;
 
@@ -93,6 +94,14 @@ int orbx_detect_and_compute_batch(orbx_ctx* ctx, const uint8_t* const* imgs, int
 int orbx_detect_and_compute_device(orbx_ctx* ctx, const uint8_t* d_imgs, int batch, int w, int h, size_t step,
                                    size_t frame_stride, int channels, orbx_keypoint* d_kps, uint8_t* d_desc,
                                    int cap, int* d_counts);
+
+/* Asynchronous form of the one-frame call for the sequential VO loop (app/run_vo.cpp:66-110): submit copies
+ * the image into pinned staging and queues upload, kernels and download, returning at once, so the host can run PnP / BA
+ * of frame i (or decode frame i+2) while the GPU extracts frame i+1; collect blocks until the OLDEST submitted frame is
+ * done and hands out its keypoints and descriptors (same results as orbx_detect_and_compute).  At most two frames in
+ * flight (ORBX_E_BUSY beyond).  The collected frame also becomes "frame 0 of the last extraction" for orbx_track_match. */
+int orbx_submit_frame(orbx_ctx* ctx, const uint8_t* img, int w, int h, size_t step, int channels);
+int orbx_collect_frame(orbx_ctx* ctx, orbx_keypoint* kps, uint8_t* desc, int cap, int* n_out);
 
 /* ---- matching: replaces cv::DescriptorMatcher::match(query, train, matches) as exact
  *      BFMatcher(NORM_HAMMING): one DMatch per query row, ties -> lowest trainIdx, distance = (float)hamming,

@@ -77,6 +77,8 @@ SYMBOLS = {
     "orbx_track_match": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_float, _P, C.POINTER(C.c_int), _P,
                                   C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "orbx_backproject": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_size_t, C.c_float, _P, _P, _P, _P]),
+    "orbx_submit_frame": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_size_t, C.c_int]),
+    "orbx_collect_frame": (C.c_int, [_P, _P, _P, C.c_int, C.POINTER(C.c_int)]),
     "orbx_filter_matches": (C.c_int, [_P, C.c_int, C.c_float]),
     "orbx_level_geometry": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "orbx_debug_read_level": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_size_t]),

@@ -63,6 +63,9 @@ struct orbx_ctx {
     Buf pyr, blur, rowcnt, rowent, work, selpos, fincnt, status, tabs, pattern;
     Buf in, kps, desc, counts;               // host-path staging on the device
     int out_cap = 0;
+    const uint8_t* view_desc = nullptr;      // device descriptors / counts of the frames the last host call (or collect) produced
+    const int* view_counts = nullptr;
+    int view_frames = 0;
     Buf mq, mt, mbest, msecond, mkeys, mstatus, mcounts, mtrace;
     int* h_small = nullptr;                  // pinned: counts[max_batch] + status[max_batch] + 1
     int last_batch = 0;
@@ -73,6 +76,18 @@ struct orbx_ctx {
     std::unordered_map<long long, int> map_slot;
     std::vector<int> map_free;
     int map_next = 0;
+
+    // asynchronous single-frame pipeline (orbx_submit_frame / orbx_collect_frame): two slots of pinned host staging and
+    // device outputs, so the host can prepare / consume one frame while the GPU works on the other
+    struct AsyncSlot {
+        uint8_t* h_in = nullptr; size_t h_in_bytes = 0;
+        uint8_t* h_out = nullptr; size_t h_out_bytes = 0;   // [counts 16 B][status 16 B][kps cap*28][desc cap*32]
+        Buf d_kps, d_desc, d_counts;
+        cudaEvent_t done = nullptr;
+        int cap = 0;
+        bool busy = false;
+    } aslot[2];
+    int a_head = 0, a_inflight = 0;          // oldest in-flight slot, number in flight
 
     bool profiling = false;
     cudaEvent_t ev[N_STAGES + 2] = {};   // 0..6 bracket the six extraction stages, 7..8 the matcher
@@ -527,6 +542,13 @@ void orbx_destroy(orbx_ctx* c)
                    &c->t_minmax, &c->t_aux};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     if (c->h_small) cudaFreeHost(c->h_small);
+    for (auto& a : c->aslot) {
+        if (a.h_in) cudaFreeHost(a.h_in);
+        if (a.h_out) cudaFreeHost(a.h_out);
+        Buf* ab[] = {&a.d_kps, &a.d_desc, &a.d_counts};
+        for (Buf* b : ab) if (b->p) cudaFree(b->p);
+        if (a.done) cudaEventDestroy(a.done);
+    }
     for (int i = 0; i < N_STAGES + 2; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int k = 1; k < HOST_MAX_LANES; ++k) { if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); if (c->lane[k]) { cudaStreamSynchronize(c->lane[k]); cudaStreamDestroy(c->lane[k]); } }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
@@ -609,6 +631,7 @@ int orbx_detect_and_compute_batch(orbx_ctx* c, const uint8_t* const* imgs, int b
     CU(cudaGetLastError());
     c->last_batch = batch;
     c->out_cap = cap;
+    c->view_desc = (const uint8_t*)c->desc.p; c->view_counts = (const int*)c->counts.p; c->view_frames = batch;
     if (c->profiling) for (int i = 0; i < 6; ++i) c->stage_valid[i] = true;
     CU(cudaStreamSynchronize(c->stream));
     bool over = false;
@@ -694,6 +717,7 @@ int orbx_extract_match_batch(orbx_ctx* c, const uint8_t* const* imgs, int batch,
     CU(cudaGetLastError());
     c->last_batch = batch;
     c->out_cap = cap;
+    c->view_desc = (const uint8_t*)c->desc.p; c->view_counts = (const int*)c->counts.p; c->view_frames = batch;
     if (c->profiling) for (int i = 0; i < 6; ++i) c->stage_valid[i] = true;
     CU(cudaStreamSynchronize(c->stream));
     for (int k = 0; k < lanes; ++k) if (nmaps > 0 && h_mstatus[k]) return fail(c, ORBX_E_INTERNAL, "matcher pipeline timed out on an mbarrier (device status set)");
@@ -1011,7 +1035,7 @@ int orbx_map_upsert_from_frame(orbx_ctx* c, const int64_t* ids, int n, int frame
     if (!c || n < 0) return ORBX_E_ARG;
     if (n == 0) return ORBX_OK;
     if (!ids || !kp_index) return fail(c, ORBX_E_ARG, "null pointer");
-    if (!c->desc.p || c->out_cap <= 0 || frame < 0 || frame >= c->last_batch) return fail(c, ORBX_E_ARG, "no host-API extraction holds that frame");
+    if (!c->view_desc || c->out_cap <= 0 || frame < 0 || frame >= c->view_frames) return fail(c, ORBX_E_ARG, "no host-API extraction holds that frame");
     for (int i = 0; i < n; ++i) if (kp_index[i] < 0 || kp_index[i] >= c->out_cap) return fail(c, ORBX_E_ARG, "keypoint index out of range");
     int rc = orbx_map_upsert(c, ids, n, nullptr, pos, norm, nullptr);
     if (rc) return rc;
@@ -1020,7 +1044,7 @@ int orbx_map_upsert_from_frame(orbx_ctx* c, const int64_t* ids, int n, int frame
     if ((rc = ensure(c, c->t_aux, sizeof(int) * (size_t)n))) return rc;
     CU(cudaMemcpyAsync(c->t_aux.p, kp_index, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     k_map_scatter_desc<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const int*)c->t_slots.p, (const int*)c->t_aux.p, n,
-                                                                           (const uint8_t*)c->desc.p + (size_t)frame * c->out_cap * 32, (uint8_t*)c->t_desc.p);
+                                                                           c->view_desc + (size_t)frame * c->out_cap * 32, (uint8_t*)c->t_desc.p);
     ++c->launches;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
@@ -1066,9 +1090,9 @@ int orbx_track_match(orbx_ctx* c, const int64_t* ids, int m, const double* pose_
         stride = nt;
     } else {
         const int f = nt_or_frame;
-        if (!c->desc.p || c->out_cap <= 0 || f < 0 || f >= c->last_batch) return fail(c, ORBX_E_ARG, "no host-API extraction holds that frame");
-        d_train = (const uint8_t*)c->desc.p + (size_t)f * c->out_cap * 32;
-        d_tcount = (const int*)c->counts.p + f;
+        if (!c->view_desc || c->out_cap <= 0 || f < 0 || f >= c->view_frames) return fail(c, ORBX_E_ARG, "no host-API extraction holds that frame");
+        d_train = c->view_desc + (size_t)f * c->out_cap * 32;
+        d_tcount = c->view_counts + f;
         nt = stride = c->out_cap;
     }
     std::vector<int> slots;
@@ -1135,6 +1159,90 @@ int orbx_backproject(orbx_ctx* c, const orbx_keypoint* kps, int n, const uint16_
     CU(cudaMemcpyAsync(pos_w, st + o_pos, N * 24, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(valid, st + o_valid, N, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return ORBX_OK;
+}
+
+}  // extern "C"
+
+// =================================================================================================== async single-frame pipeline
+extern "C" {
+
+int orbx_submit_frame(orbx_ctx* c, const uint8_t* img, int w, int h, size_t step, int channels)
+{
+    if (!c) return ORBX_E_ARG;
+    if (!img || w <= 0 || h <= 0) return fail(c, ORBX_E_ARG, "empty or null image (use the synchronous call for empty frames)");
+    if (w > c->max_w || h > c->max_h) return fail(c, ORBX_E_ARG, "frame larger than the context maximum");
+    if (channels != 1 && channels != 3) return fail(c, ORBX_E_UNSUPPORTED, "channels must be 1 (gray) or 3 (BGR)");
+    if (step < (size_t)w * channels) return fail(c, ORBX_E_ARG, "step smaller than a row");
+    if (c->a_inflight >= 2) return fail(c, ORBX_E_BUSY, "two frames already in flight: collect one first");
+    CU(cudaSetDevice(c->device));
+    orbx_ctx::AsyncSlot& a = c->aslot[(c->a_head + c->a_inflight) & 1];
+    const int cap = std::max(2 * c->nfeatures, 64);
+    const size_t row = (size_t)w * channels, dstep = round_up(row, 16), fstride = dstep * h;
+    const size_t out_bytes = 32 + (size_t)cap * 60;
+    int rc;
+    if (a.h_in_bytes < fstride) {
+        if (a.h_in) cudaFreeHost(a.h_in);
+        a.h_in = nullptr; a.h_in_bytes = 0;
+        if (cudaMallocHost((void**)&a.h_in, fstride) != cudaSuccess) return fail(c, ORBX_E_NOMEM, "pinned allocation failed");
+        a.h_in_bytes = fstride;
+    }
+    if (a.h_out_bytes < out_bytes) {
+        if (a.h_out) cudaFreeHost(a.h_out);
+        a.h_out = nullptr; a.h_out_bytes = 0;
+        if (cudaMallocHost((void**)&a.h_out, out_bytes) != cudaSuccess) return fail(c, ORBX_E_NOMEM, "pinned allocation failed");
+        a.h_out_bytes = out_bytes;
+    }
+    if (!a.done && cudaEventCreateWithFlags(&a.done, cudaEventDisableTiming) != cudaSuccess) return fail(c, ORBX_E_CUDA, "event creation failed");
+    if ((rc = ensure(c, c->in, fstride)) || (rc = ensure(c, a.d_kps, sizeof(orbx_keypoint) * (size_t)cap)) || (rc = ensure(c, a.d_desc, (size_t)32 * cap)) ||
+        (rc = ensure(c, a.d_counts, 32)))
+        return rc;
+    a.cap = cap;
+    if ((rc = set_geometry(c, w, h))) return rc;
+    for (int y = 0; y < h; ++y) memcpy(a.h_in + (size_t)y * dstep, img + (size_t)y * step, row);     // the caller's buffer is free on return
+    // everything below is stream-ordered behind the previous frame: the shared per-frame workspace is reused safely
+    CU(cudaMemcpyAsync(c->in.p, a.h_in, fstride, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->status.p, 0, sizeof(int), c->stream));
+    if ((rc = run_extract_range(c, c->stream, false, false, 0, 1, (const uint8_t*)c->in.p, dstep, fstride, channels, (float*)a.d_kps.p,
+                                (uint8_t*)a.d_desc.p, cap, (int*)a.d_counts.p)))
+        return rc;
+    CU(cudaMemcpyAsync(a.h_out, a.d_counts.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(a.h_out + 16, c->status.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(a.h_out + 32, a.d_kps.p, sizeof(orbx_keypoint) * (size_t)cap, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(a.h_out + 32 + (size_t)cap * 28, a.d_desc.p, (size_t)32 * cap, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaEventRecord(a.done, c->stream));
+    CU(cudaGetLastError());
+    a.busy = true;
+    ++c->a_inflight;
+    return ORBX_OK;
+}
+
+int orbx_collect_frame(orbx_ctx* c, orbx_keypoint* kps, uint8_t* desc, int cap, int* n_out)
+{
+    if (!c || !n_out) return ORBX_E_ARG;
+    *n_out = 0;
+    if (c->a_inflight <= 0) return fail(c, ORBX_E_ARG, "no frame in flight");
+    if (cap < 0 || (cap > 0 && (!kps || !desc))) return fail(c, ORBX_E_ARG, "null output");
+    CU(cudaSetDevice(c->device));
+    orbx_ctx::AsyncSlot& a = c->aslot[c->a_head];
+    CU(cudaEventSynchronize(a.done));
+    int n, status;
+    memcpy(&n, a.h_out, sizeof n);
+    memcpy(&status, a.h_out + 16, sizeof status);
+    *n_out = n;
+    if (n > a.cap) {                                          // more ties than the internal capacity: redo synchronously is the caller's fallback
+        a.busy = false; c->a_head ^= 1; --c->a_inflight;
+        return fail(c, ORBX_E_CAPACITY, "internal capacity exceeded; use orbx_detect_and_compute for this frame");
+    }
+    if (n > cap) return fail(c, ORBX_E_CAPACITY, "output capacity too small; n_out holds the needed count (frame still in flight)");
+    memcpy(kps, a.h_out + 32, sizeof(orbx_keypoint) * (size_t)n);
+    memcpy(desc, a.h_out + 32 + (size_t)a.cap * 28, (size_t)32 * n);
+    // the collected frame becomes "frame 0 of the last extraction" for orbx_track_match / orbx_map_upsert_from_frame
+    c->view_desc = (const uint8_t*)a.d_desc.p; c->view_counts = (const int*)a.d_counts.p; c->view_frames = 1; c->out_cap = a.cap;
+    a.busy = false;
+    c->a_head ^= 1;
+    --c->a_inflight;
+    (void)status;
     return ORBX_OK;
 }
 

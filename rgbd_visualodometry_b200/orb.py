@@ -94,6 +94,22 @@ class Context:
             self._check(rc)
             return kps, desc, n
 
+    def submit_frame(self, image: np.ndarray):
+        """Queue one HOST frame (returns at once; at most two in flight)."""
+        im = np.ascontiguousarray(image, dtype=np.uint8)
+        h, w = im.shape[:2]
+        ch = 1 if im.ndim == 2 else im.shape[2]
+        self._check(self.lib.orbx_submit_frame(self.h, _ptr(im), w, h, im.strides[0], ch))
+
+    def collect_frame(self, cap: int | None = None):
+        """Wait for the oldest submitted frame -> (keypoints, descriptors)."""
+        cap = int(cap) if cap is not None else max(2 * self.nfeatures, 64)
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        self._check(self.lib.orbx_collect_frame(self.h, _ptr(kps), _ptr(desc), cap, C.byref(n)))
+        return kps[:n.value].copy(), desc[:n.value].copy()
+
     def extract_match_batch(self, images, maps, cap: int | None = None):
         """The front-end's per-frame pattern for a batch of HOST frames: extraction, then every map in `maps`
         ([M_j, 32] uint8 each) matched against each frame's own descriptors.  Returns (kps, desc, counts, [best_j[B, M_j]])."""

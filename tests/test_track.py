@@ -136,3 +136,36 @@ def test_backproject_vs_oracle(orbmod):
     assert np.array_equal(valid, ovalid) and 0 < valid.sum() < len(valid)
     assert np.allclose(pos[valid], opos[valid], rtol=1e-9, atol=1e-12)
     assert (pos[~valid] == 0).all()
+
+
+@pytest.mark.gpu
+def test_async_submit_collect_equals_sync_and_feeds_tracking(orbmod):
+    """two frames in flight, results identical to the synchronous drop-in call; the collected frame is the
+    train set of the next orbx_track_match without leaving the device."""
+    from oracle import oracle as O
+    from rgbd_visualodometry_b200.synth import synth_frame
+    frames = [synth_frame(480, 640, 6100 + i) for i in range(5)]
+    ctx = orbmod.Context(500, 1.2, 8, 640, 480, 1)
+    sync = [ctx.detect_and_compute(f) for f in frames]
+    ctx.submit_frame(frames[0])
+    ctx.submit_frame(frames[1])
+    with pytest.raises(orbmod.OrbxError) as e:
+        ctx.submit_frame(frames[2])
+    assert e.value.code == -8                                 # ORBX_E_BUSY
+    for i in range(5):
+        k, d = ctx.collect_frame()
+        assert k.tobytes() == sync[i][0].tobytes() and np.array_equal(d, sync[i][1]), i
+        if i + 2 < 5:
+            ctx.submit_frame(frames[i + 2])
+    with pytest.raises(orbmod.OrbxError):
+        ctx.collect_frame()                                   # nothing in flight
+    ko, do = O.detect_and_compute(frames[4], 500)
+    assert k.tobytes() == ko.tobytes() and np.array_equal(d, do)
+    # the last collected frame (4) is the resident train set
+    m = len(sync[3][1])
+    pose, cam, pos, norm, outlier = _scene(21, m)
+    ids = np.arange(m, dtype=np.int64)
+    ctx.map_upsert(ids, sync[3][1], pos, norm, np.zeros(m, np.uint8))
+    cand, matches, mn, mx = ctx.track_match(ids, pose, cam, 640, 480, train=None, frame=0)
+    oc, om, omn, omx = T.track_match(pose, cam, 640, 480, pos, norm, np.zeros(m, bool), sync[3][1], sync[4][1], 2.0, O.match_hamming)
+    assert np.array_equal(cand, oc) and matches.tobytes() == om.tobytes() and (mn, mx) == (omn, omx)
