@@ -1010,9 +1010,10 @@ int orbx_map_upsert(orbx_ctx* c, const int64_t* ids, int n, const uint8_t* desc,
         for (int i = 0; i < n; ++i) if (is_new[i]) ns.push_back(slots[i]);
         if (!ns.empty()) {
             const size_t Z = ns.size();
-            if ((rc = ensure(c, c->t_aux, Z * 4 + Z * 32))) return rc;
+            const size_t zoff = round_up(Z * 4, 16);        // the zero block is read as uint4 / double: keep it 16-byte aligned
+            if ((rc = ensure(c, c->t_aux, zoff + Z * 32))) return rc;
             CU(cudaMemcpyAsync(c->t_aux.p, ns.data(), Z * 4, cudaMemcpyHostToDevice, c->stream));
-            uint8_t* z = (uint8_t*)c->t_aux.p + Z * 4;
+            uint8_t* z = (uint8_t*)c->t_aux.p + zoff;
             CU(cudaMemsetAsync(z, 0, Z * 32, c->stream));
             k_map_scatter<<<(unsigned)((Z + 255) / 256), 256, 0, c->stream>>>((const int*)c->t_aux.p, (int)Z, desc ? nullptr : z, pos ? nullptr : (const double*)z,
                                                                               norm ? nullptr : (const double*)z, outlier ? nullptr : z, (uint8_t*)c->t_desc.p,

@@ -169,3 +169,25 @@ def test_async_submit_collect_equals_sync_and_feeds_tracking(orbmod):
     cand, matches, mn, mx = ctx.track_match(ids, pose, cam, 640, 480, train=None, frame=0)
     oc, om, omn, omx = T.track_match(pose, cam, 640, 480, pos, norm, np.zeros(m, bool), sync[3][1], sync[4][1], 2.0, O.match_hamming)
     assert np.array_equal(cand, oc) and matches.tobytes() == om.tobytes() and (mn, mx) == (omn, omx)
+
+
+@pytest.mark.gpu
+def test_tracking_loop_orbx_equals_cv2_frontend():
+    """BASELINE config 1 in miniature (tools/run_vo_synth.py): the reference's tracking loop on a synthetic RGB-D sequence with
+    the hot path behind the orbx C-ABI vs the same loop with cv2's operators: identical keypoint / match / inlier counts and
+    poses frame by frame, and the trajectory within millimetres of the ground truth."""
+    cv2 = pytest.importorskip("cv2")
+    import importlib.util, os
+    spec = importlib.util.spec_from_file_location("run_vo_synth", os.path.join(os.path.dirname(__file__), "..", "tools", "run_vo_synth.py"))
+    vo = importlib.util.module_from_spec(spec); spec.loader.exec_module(vo)
+    seq = vo.make_sequence(16)
+    vo.run.pos = {}
+    a, _ = vo.run("orbx", seq)
+    vo.run.pos = {}
+    b, _ = vo.run("cv2", seq)
+    for x, y in zip(a, b):
+        assert x[1:4] == y[1:4], (x[:4], y[:4])
+        assert np.allclose(x[4], y[4], atol=1e-9)
+    err = max(np.linalg.norm(x[4] - x[5]) for x in a)
+    assert err < 0.01, err                                   # metres; 1 px at 2 m is ~3.9 mm
+    assert min(x[3] for x in a[1:]) >= 30                    # PnP inliers
