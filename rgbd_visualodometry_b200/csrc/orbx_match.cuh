@@ -38,9 +38,10 @@ constexpr int MT_STAGES = 4;
 constexpr int MT_EXP_GROUPS = 2;                  // expander groups take alternate B tiles, so a group has two tile periods per tile
 constexpr int MT_EXP_WARPS = MT_EXP_GROUPS * MT_BN / 32;
 // Warp ids: the SM's warp arbiter favours HIGHER warp ids, so the latency-critical roles sit on top:
-//   0 .. 5 expanders (run ahead, not critical) | 6 idle | 7 .. 14 epilogue | 15 MMA issuer
+//   0 .. 5 expanders (run ahead, not critical) | 6 MMA issuer of the odd tiles | 7 .. 14 epilogue | 15 MMA issuer of the even tiles
 constexpr int MT_EPI_WARP0 = 7;
 constexpr int MT_ISSUER_WARP = 15;
+constexpr int MT_ISSUER2_WARP = 6;      // second issuer (odd tiles): its barrier waits / commits run under the other issuer's MMAs
 constexpr int MT_THREADS = 16 * 32;
 static_assert(MT_EXP_WARPS <= MT_EPI_WARP0, "role layout");
 constexpr int MT_B_BYTES = MT_BN * 256;
@@ -326,10 +327,15 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
             ++n;
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-    } else if (warp == MT_ISSUER_WARP) {
-        // ================= MMA issuer =================
+    } else if (warp == MT_ISSUER_WARP || warp == MT_ISSUER2_WARP) {
+        // ================= MMA issuers =================
         // The whole warp runs the loop so that every operand is computed in warp-uniform code (uniform registers, no
         // per-instruction ELECT / R2UR waterfall); one elected lane issues the tcgen05 instructions.
+        // TWO issuer warps take alternate tiles (issuer g <-> tiles t = g mod 2 <-> accumulator buffer g): issuing blocks on
+        // the short MMA queue for the whole tensor time of a tile, so a single issuer exposes its per-tile barrier waits,
+        // commits and loop latency (~200 cycles of a ~1200-cycle tile period) as tensor-pipe idle time; with two, the next
+        // tile's MMAs are already queued behind the current one's.
+        const int issuer = warp == MT_ISSUER_WARP ? 0 : 1;
         const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t sbu = __shfl_sync(0xffffffffu, sbase, 0);
         const uint64_t dca = umma_desc_sw128(sbu + MT_SMEM_CA), dcb = umma_desc_sw128(sbu + MT_SMEM_CB);
@@ -338,6 +344,7 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
         for (int set = blockIdx.z; set < nsets && ok; set += gridDim.z) {
             const MatchSetRange rg = match_set_range(train_counts, set, nt, split, rows_per_split);
             for (int i = 0; i < rg.ntiles; ++i, ++t) {
+                if ((t & 1) != issuer) continue;              // the other issuer's tile
                 const int s = t % MT_STAGES;
                 const uint32_t ph = (uint32_t)(t / MT_STAGES) & 1u;
                 const int b = t & 1;
@@ -358,9 +365,9 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
                 // never reads (it bounds partial tiles by the row count).
                 const int rows_here = min(MT_BN, rg.n1 - (rg.n0 + i * MT_BN));
                 const uint32_t idesc = (MT_IDESC & ~(0x3Fu << 17)) | ((uint32_t)(((rows_here + 15) & ~15) >> 3) << 17);
-                // barriers of the NEXT tile (same pipelines, consecutive tile numbers even across set boundaries)
-                const int s1 = (t + 1) % MT_STAGES, b1 = (t + 1) & 1;
-                const uint32_t ph1 = (uint32_t)((t + 1) / MT_STAGES) & 1u, bph1 = (uint32_t)((t + 1) >> 1) & 1u;
+                // barriers of this issuer's NEXT tile, t + 2 (same pipelines, consecutive tile numbers even across set boundaries)
+                const int s1 = (t + 2) % MT_STAGES, b1 = b;
+                const uint32_t ph1 = (uint32_t)((t + 2) / MT_STAGES) & 1u, bph1 = (uint32_t)((t + 2) >> 1) & 1u;
 #pragma unroll
                 for (int a = 0; a < 2; ++a) {
                     if (elect_one() && !(dbg & 2)) {
