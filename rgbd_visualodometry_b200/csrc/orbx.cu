@@ -568,7 +568,7 @@ int orbx_synchronize(orbx_ctx* c)
     if (b > 0) CU(cudaMemcpyAsync(c->h_small, c->status.p, sizeof(int) * (size_t)b, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < b; ++i)
-        if (c->h_small[i] & 1) return fail(c, ORBX_E_ORDER, "introselect depth limit hit: libstdc++ heap-select order not reproduced");
+        if (c->h_small[i]) return fail(c, ORBX_E_INTERNAL, "device-side status set for a frame");
     return ORBX_OK;
 }
 
@@ -636,7 +636,7 @@ int orbx_detect_and_compute_batch(orbx_ctx* c, const uint8_t* const* imgs, int b
     CU(cudaStreamSynchronize(c->stream));
     bool over = false;
     for (int i = 0; i < batch; ++i) {
-        if (h_status[i] & 1) return fail(c, ORBX_E_ORDER, "introselect depth limit hit: libstdc++ heap-select order not reproduced");
+        if (h_status[i]) return fail(c, ORBX_E_INTERNAL, "device-side status set for a frame");
         n_out[i] = h_counts[i];
         if (h_counts[i] > cap) over = true;
     }
@@ -723,7 +723,7 @@ int orbx_extract_match_batch(orbx_ctx* c, const uint8_t* const* imgs, int batch,
     for (int k = 0; k < lanes; ++k) if (nmaps > 0 && h_mstatus[k]) return fail(c, ORBX_E_INTERNAL, "matcher pipeline timed out on an mbarrier (device status set)");
     bool over = false;
     for (int i = 0; i < batch; ++i) {
-        if (h_status[i] & 1) return fail(c, ORBX_E_ORDER, "introselect depth limit hit: libstdc++ heap-select order not reproduced");
+        if (h_status[i]) return fail(c, ORBX_E_INTERNAL, "device-side status set for a frame");
         n_out[i] = h_counts[i];
         if (h_counts[i] > cap) over = true;
     }
