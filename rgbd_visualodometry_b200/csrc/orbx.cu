@@ -287,10 +287,10 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, bool marks, bool fused, int 
         if (marks) stage_mark(c, 1);
         for (int l = 1; l < g.nlevels; ++l) {
             if (g.L[l].w <= 0 || g.L[l].h <= 0) continue;
-            const dim3 blk(32, PYR_BY);
-            const dim3 grd((unsigned)((g.L[l].pitch / 4 + 31) / 32), (unsigned)((g.L[l].h + PYR_RH * PYR_BY - 1) / (PYR_RH * PYR_BY)), B);
-            if (g.L[l].xspan <= 7) k_pyr_down<false><<<grd, blk, 0, st>>>(g, l, pyr, tabs);
-            else                   k_pyr_down<true><<<grd, blk, 0, st>>>(g, l, pyr, tabs);
+            const int nitems = (g.L[l].pitch / 8) * ((g.L[l].h + PYR_RH - 1) / PYR_RH);     // (column octet, row strip) work items
+            const dim3 grd((unsigned)((nitems + PYR_NT - 1) / PYR_NT), B);
+            if (g.L[l].xspan <= 7) k_pyr_down<false><<<grd, PYR_NT, 0, st>>>(g, l, pyr, tabs);
+            else                   k_pyr_down<true><<<grd, PYR_NT, 0, st>>>(g, l, pyr, tabs);
             ++c->launches;
         }
     }

@@ -174,54 +174,75 @@ __device__ __forceinline__ void pyr_down_item(const Geom& g, int l, int f, int x
 // through a private shared-memory ring filled by cp.async (PYR_DEPTH rows in flight), takes the horizontal pass of
 // each once, and emits an output row as soon as its lower source row has passed.  Load latency sits under the
 // arithmetic of the rows already there instead of in front of every output row.
+// A thread owns PYR_NQ = 2 adjacent column quads (8 output columns) of a strip of PYR_RH rows: the per-row control work
+// (ring slot, emission test, tap prefetch, pointer updates -- more than half of the instructions of a one-quad thread) is
+// shared by both quads, each of which keeps its own 3- or 4-word source window.  Work items (column octet, strip) of a
+// level are flattened over the CTAs, so warps stay full on narrow levels.
 constexpr int PYR_DEPTH = 8;
-constexpr int PYR_NT = 32 * PYR_BY;
-// WIDE = false: the 4 outputs of a thread reach at most 7 bytes past its aligned first source byte (scale factors up to
+constexpr int PYR_NT = 128;
+constexpr int PYR_NQ = 2;
+// WIDE = false: the 4 outputs of a quad reach at most 7 bytes past its aligned first source byte (scale factors up to
 // ~1.5, the reference's 1.2 included): 3 source words, one predicated select per operand.  WIDE = true: up to 11 bytes
 // (scale factors up to ~2.6): 4 source words, two selects per operand.
 template <bool WIDE>
 __global__ void __launch_bounds__(PYR_NT) k_pyr_down(const __grid_constant__ Geom g, int l, uint8_t* pyr, const uint32_t* __restrict__ tabs)
 {
-    __shared__ __align__(16) uint8_t s_ring[PYR_DEPTH * PYR_NT * 16];
+    __shared__ __align__(16) uint8_t s_ring[PYR_DEPTH * PYR_NQ * PYR_NT * 16];
     const LevelGeom& D = g.L[l];
     const LevelGeom& S = g.L[l - 1];
-    const int x = (blockIdx.x * 32 + threadIdx.x) * 4;
-    const int ys = (blockIdx.y * PYR_BY + threadIdx.y) * PYR_RH, ye = min(ys + PYR_RH, D.h);
-    const int f = blockIdx.z;
-    if (x >= D.pitch || ys >= ye) return;
+    const int noct = D.pitch >> 3;                           // column octets per row (pitch is a multiple of 16)
+    const int item = blockIdx.x * PYR_NT + threadIdx.x;
+    const int strip = item / noct, oct = item - strip * noct;
+    const int x = oct * 8;
+    const int ys = strip * PYR_RH, ye = min(ys + PYR_RH, D.h);
+    const int f = blockIdx.y;
+    if (ys >= ye) return;
     uint8_t* dst = pyr + (size_t)f * g.pyr_frame + D.img_off + (size_t)ys * D.pitch + x;
     if (x >= D.w) {                                          // row padding: keep it zero
-        for (int y = ys; y < ye; ++y, dst += D.pitch) *reinterpret_cast<uint32_t*>(dst) = 0u;
+        for (int y = ys; y < ye; ++y, dst += D.pitch) *reinterpret_cast<uint2*>(dst) = make_uint2(0u, 0u);
         return;
     }
-    uint32_t coef[4], sh[4];
-    bool hi[4], hi2[4];
-    const int a = (int)(__ldg(tabs + D.xtab + x) & 0xffffu) & ~3;   // aligned source byte all four outputs are addressed from
+    uint32_t coef[PYR_NQ][4], sh[PYR_NQ][4];
+    bool hi[PYR_NQ][4], hi2[PYR_NQ][4];
+    int a[PYR_NQ];                                           // aligned source byte each quad is addressed from
+    bool w2ok[PYR_NQ], w3ok[PYR_NQ];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t t = (x + k < D.w) ? __ldg(tabs + D.xtab + x + k) : (uint32_t)a;  // padding columns: taps 0 -> output 0
-        const int off = (int)(t & 0xffffu) - a;              // 0 .. 7 (narrow), 0 .. 11 (wide)
-        const uint32_t c1 = t >> 16;
-        coef[k] = (x + k < D.w) ? ((256u - c1) | (c1 << 16)) : 0u;
-        hi[k] = off >= 4;
-        hi2[k] = off >= 8;
-        sh[k] = (uint32_t)(off & 3) * 8u;
+    for (int q = 0; q < PYR_NQ; ++q) {
+        const int xq = x + 4 * q;
+        a[q] = xq < D.w ? ((int)(__ldg(tabs + D.xtab + xq) & 0xffffu) & ~3) : a[0];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t t = (xq + k < D.w) ? __ldg(tabs + D.xtab + xq + k) : (uint32_t)a[q];   // padding columns: taps 0 -> output 0
+            const int off = (int)(t & 0xffffu) - a[q];       // 0 .. 7 (narrow), 0 .. 11 (wide)
+            const uint32_t c1 = t >> 16;
+            coef[q][k] = (xq + k < D.w) ? ((256u - c1) | (c1 << 16)) : 0u;
+            hi[q][k] = off >= 4;
+            hi2[q][k] = off >= 8;
+            sh[q][k] = (uint32_t)(off & 3) * 8u;
+        }
+        w2ok[q] = a[q] + 8 < S.pitch;
+        w3ok[q] = WIDE && a[q] + 12 < S.pitch;
     }
-    const bool w2ok = a + 8 < S.pitch, w3ok = WIDE && a + 12 < S.pitch;
     const uint32_t* ytab = tabs + D.ytab;
     const int s0 = (int)(__ldg(ytab + ys) & 0xffffu);
     const int s1 = min((int)(__ldg(ytab + ye - 1) & 0xffffu) + 1, S.h - 1);         // last source row needed
-    const uint8_t* src = pyr + (size_t)f * g.pyr_frame + S.img_off + (size_t)s0 * S.pitch + a;
-    const unsigned ring = (unsigned)__cvta_generic_to_shared(s_ring) + (threadIdx.y * 32 + threadIdx.x) * 16u;
+    const uint8_t* src = pyr + (size_t)f * g.pyr_frame + S.img_off + (size_t)s0 * S.pitch;
+    // ring slot d: [quad 0: 16 B x PYR_NT threads][quad 1: 16 B x PYR_NT threads]  (each LDS.128 conflict-free)
+    const unsigned ring = (unsigned)__cvta_generic_to_shared(s_ring) + threadIdx.x * 16u;
+    constexpr unsigned SLOT = PYR_NQ * PYR_NT * 16u;
+    auto fetch = [&](unsigned slot_addr, const uint8_t* row) {
+#pragma unroll
+        for (int q = 0; q < PYR_NQ; ++q) {
+            const unsigned sa = slot_addr + q * (PYR_NT * 16u);
+            const uint8_t* p = row + a[q];
+            cp_async_4(sa, p); cp_async_4(sa + 4u, p + 4);
+            if (w2ok[q]) cp_async_4(sa + 8u, p + 8);
+            if (w3ok[q]) cp_async_4(sa + 12u, p + 12);
+        }
+    };
 #pragma unroll
     for (int d = 0; d < PYR_DEPTH; ++d) {
-        if (s0 + d <= s1) {
-            const uint8_t* p = src + (size_t)d * S.pitch;
-            const unsigned sa = ring + d * (PYR_NT * 16u);
-            cp_async_4(sa, p); cp_async_4(sa + 4u, p + 4);
-            if (w2ok) cp_async_4(sa + 8u, p + 8);
-            if (w3ok) cp_async_4(sa + 12u, p + 12);
-        }
+        if (s0 + d <= s1) fetch(ring + d * SLOT, src + (size_t)d * S.pitch);
         cp_async_commit();
     }
     src += (size_t)PYR_DEPTH * S.pitch;
@@ -232,42 +253,49 @@ __global__ void __launch_bounds__(PYR_NT) k_pyr_down(const __grid_constant__ Geo
     int emit_at = min((int)(ty & 0xffffu) + 1, S.h - 1);
     int to_fetch = (s1 - s0 + 1) - PYR_DEPTH;               // source rows not yet requested
     unsigned sa = ring;
-    const unsigned ring_end = ring + PYR_DEPTH * (PYR_NT * 16u);
-    PyrRow hA, hB;                                           // horizontal passes of the last two source rows (ping-pong)
+    const unsigned ring_end = ring + PYR_DEPTH * SLOT;
+    PyrRow hA[PYR_NQ], hB[PYR_NQ];                           // horizontal passes of the last two source rows (ping-pong)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { hA.h[k] = 0; hB.h[k] = 0; }
+    for (int q = 0; q < PYR_NQ; ++q)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { hA[q].h[k] = 0; hB[q].h[k] = 0; }
     // one source row: wait, read, refill the slot, horizontal pass into `hc`, emit what became complete
-    auto step = [&](int s, const PyrRow& hp, PyrRow& hc) {
+    auto step = [&](int s, const PyrRow* hp, PyrRow* hc) {
         cp_async_wait<PYR_DEPTH - 1>();
-        const uint4 w = lds_v4(sa);
-        if (to_fetch > 0) {
-            cp_async_4(sa, src); cp_async_4(sa + 4u, src + 4);
-            if (w2ok) cp_async_4(sa + 8u, src + 8);
-            if (w3ok) cp_async_4(sa + 12u, src + 12);
-        }
+        uint4 w[PYR_NQ];
+#pragma unroll
+        for (int q = 0; q < PYR_NQ; ++q) w[q] = lds_v4(sa + q * (PYR_NT * 16u));
+        if (to_fetch > 0) fetch(sa, src);
         cp_async_commit();
         --to_fetch;
         src += S.pitch;
-        sa += PYR_NT * 16u;
+        sa += SLOT;
         if (sa == ring_end) sa = ring;
-        const uint32_t w2 = w2ok ? w.z : 0u, w3 = w3ok ? w.w : 0u;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            uint32_t lo = hi[k] ? w.y : w.x, up = hi[k] ? w2 : w.y;
-            if (WIDE) { lo = hi2[k] ? w2 : lo; up = hi2[k] ? w3 : up; }
-            hc.h[k] = __dp2a_lo(coef[k], __funnelshift_r(lo, up, sh[k]), 0u);
+        for (int q = 0; q < PYR_NQ; ++q) {
+            const uint32_t w2 = w2ok[q] ? w[q].z : 0u, w3 = w3ok[q] ? w[q].w : 0u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t lo = hi[q][k] ? w[q].y : w[q].x, up = hi[q][k] ? w2 : w[q].y;
+                if (WIDE) { lo = hi2[q][k] ? w2 : lo; up = hi2[q][k] ? w3 : up; }
+                hc[q].h[k] = __dp2a_lo(coef[q][k], __funnelshift_r(lo, up, sh[q][k]), 0u);
+            }
         }
         while (emit_at == s && y < ye) {                     // (two outputs per source row only when the bottom row clamps)
             const bool clamped = (int)(ty & 0xffffu) == s;   // y1 == y0: both taps read the last source row
             const uint32_t cy1 = ty >> 16, cy0 = 256u - cy1;
-            uint32_t out = 0;
+            uint32_t out[PYR_NQ];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t top = clamped ? hc.h[k] : hp.h[k];
-                const uint32_t v = (top * cy0 + hc.h[k] * cy1 + 32768u) >> 16;
-                out |= min(v, 255u) << (8 * k);
+            for (int q = 0; q < PYR_NQ; ++q) {
+                out[q] = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t top = clamped ? hc[q].h[k] : hp[q].h[k];
+                    const uint32_t v = (top * cy0 + hc[q].h[k] * cy1 + 32768u) >> 16;
+                    out[q] |= min(v, 255u) << (8 * k);
+                }
             }
-            *reinterpret_cast<uint32_t*>(dst) = out;
+            *reinterpret_cast<uint2*>(dst) = make_uint2(out[0], out[1]);
             dst += D.pitch;
             ++y;
             ty = ty_next;
