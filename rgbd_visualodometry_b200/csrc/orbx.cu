@@ -190,9 +190,16 @@ void build_geom(const orbx_ctx* c, int w, int h, Geom* g, std::vector<uint32_t>*
         L.ent_pitch = (int)round_up((size_t)(L.in_w + 1) / 2 + 1, 8);
         L.ws_cap = std::max(((L.in_w + 1) / 2) * ((L.in_h + 1) / 2), 1);
         L.band0 = bands; L.nbands = (L.in_h + FAST_R - 1) / FAST_R; bands += L.nbands;
-        if (L.in_w > 0) {                                    // blur work items: 8-column groups x strips of BLUR_RH rows, BLUR_NT per CTA
+        if (L.in_w > 0) {                                    // blur work items: 8-column groups x strips of blur_rh rows, BLUR_NT per CTA
             L.blur_cgs = (L.w - 13 - BLUR_LO + 7) / 8;
-            L.nblur = (L.blur_cgs * ((L.h - 26 + BLUR_RH - 1) / BLUR_RH) + BLUR_NT - 1) / BLUR_NT;
+            // strip height: a multiple of 7 (the kernel's unrolled row window) that wastes the fewest rows on this level
+            const int rows = L.h - 26;
+            long best = -1;
+            for (int rh = 35; rh <= 84; rh += 7) {
+                const long cost = (long)((rows + rh - 1) / rh) * (rh + 6);
+                if (best < 0 || cost < best) { best = cost; L.blur_rh = rh; }
+            }
+            L.nblur = (L.blur_cgs * ((rows + L.blur_rh - 1) / L.blur_rh) + BLUR_NT - 1) / BLUR_NT;
         }
         L.blur0 = blurs; blurs += L.nblur;
         L.img_off = pyr; pyr += round_up((size_t)L.pitch * std::max(L.h, 1), 256);
@@ -511,7 +518,8 @@ int orbx_create(orbx_ctx** out, int device, int nfeatures, float scale_factor, i
     build_geom(c, max_w, max_h, &c->geom_max, nullptr);
     const Geom& g = c->geom_max;
     const size_t B = (size_t)max_batch;
-    if (ensure(c, c->pyr, g.pyr_frame * B) || ensure(c, c->blur, g.pyr_frame * B) || ensure(c, c->rowcnt, g.cnt_frame * 4 * B) || ensure(c, c->rowent, g.ent_frame * 4 * B) ||
+    if (ensure(c, c->pyr, g.pyr_frame * B + (size_t)(96 + 8) * g.L[0].pitch) ||   // + slack: the blur streams up to ~100 rows past a level's end (masked outputs)
+        ensure(c, c->blur, g.pyr_frame * B) || ensure(c, c->rowcnt, g.cnt_frame * 4 * B) || ensure(c, c->rowent, g.ent_frame * 4 * B) ||
         ensure(c, c->work, g.ws_frame * sizeof(Elem) * B) || ensure(c, c->selpos, g.ws_frame * 8 * B) || ensure(c, c->fincnt, sizeof(int) * ORBX_LEVELS_MAX * B) ||
         ensure(c, c->status, sizeof(int) * B) || ensure(c, c->pattern, sizeof(float) * 1024))
         return bail(ORBX_E_NOMEM);

@@ -33,6 +33,7 @@ struct LevelGeom {
     int band0;                // index of this level's first band in the per-frame band list
     int nbands;
     int blur0, nblur, blur_cgs;  // blur tiles: first tile index, tile count (= column groups x strip groups), column groups
+    int blur_rh;              // output rows per blur strip: a multiple of 7 chosen per level so the strips fit the level tightly
     uint32_t xtab, ytab;      // offsets (u32 units) of the INTER_LINEAR_EXACT tap tables: i0 | c1 << 16
     int xspan;                // max over 4-column groups of (left tap of the group's last column) - (its aligned first byte): <= 7 narrow kernel, <= 11 wide
     unsigned long long img_off;   // bytes, inside the frame's pyr block

@@ -1039,11 +1039,10 @@ __device__ __forceinline__ void glibc_sincosf(float ang, float* sn, float* cs)
 //   row pass   acc = F(k0*p[x-3]); acc = fma(p[x-3+i], k_i, acc), i = 1..6
 //   col pass   acc = F(k3*r[y]);   acc = fma(F(r[y+j] + r[y-j]), k_{3+j}, acc), j = 1..3;  out = rint(acc)
 // Only the region a descriptor can sample is produced: [12, w-13) x [13, h-13) (keypoints keep 31 px from the
-// border, rBRIEF reaches 18).  One thread = 8 adjacent columns walked down BLUR_RH rows with a 7-deep register
+// border, rBRIEF reaches 18).  One thread = 8 adjacent columns walked down a strip of rows with a 7-deep register
 // window of row-pass values (rotated by unrolling, no moves), so every input byte is loaded once per thread and
 // converted to float once (exactly: PRMT into the mantissa of 2^23, one FADD).  Work items (column group, strip)
 // of a level are flattened so warps stay full on narrow levels.  No clamp is needed: the taps sum to < 1.
-constexpr int BLUR_RH = 64;            // output rows per thread
 constexpr int BLUR_NT = 128;           // work items per CTA
 constexpr int BLUR_LO = 12;            // first produced column (8-column groups start at 12 + 8q, so x0 - 4 is 8-byte aligned)
 
@@ -1080,16 +1079,8 @@ __device__ __forceinline__ float f2_hi(unsigned long long v) { return __uint_as_
 // an aligned register pair P(i) = (p[i], p[i+4]), i = 0..9, built once per source row straight from the loaded words
 // (PRMT into the mantissa of 2^23, one FADD2 with -2^23 converts both halves exactly).  No mul feeds an add here (the
 // pattern ptxas would contract): products feed FMA addends, sums feed FMA multiplicands.
-constexpr int BLUR_DEPTH = 12;         // source rows in flight per thread (cp.async ring slots)
-__device__ __forceinline__ void sts_u64_zero(unsigned addr) { asm volatile("st.shared.v2.u32 [%0], {%1, %1};" :: "r"(addr), "r"(0u) : "memory"); }
-// one source row of a thread: bytes x0-4 .. x0+11 -> 16 bytes of its ring slot (the second half may lie past the row)
-__device__ __forceinline__ void blur_cp_row(unsigned dst, const uint8_t* src, bool hi_ok)
-{
-    cp_async_8(dst, src);
-    if (hi_ok) cp_async_8(dst + 8u, src + 8);
-    else sts_u64_zero(dst + 8u);
-}
-
+constexpr int BLUR_DEPTH = 7;          // source rows in flight per thread (cp.async ring slots = the 7-row window)
+template <int N> struct ic { static constexpr int value = N; };   // compile-time window slot
 constexpr int BLUR_RING_BYTES = BLUR_DEPTH * BLUR_NT * 16;
 // tile = index of the CTA's work inside the frame's blur tile list, f = frame, s_ring = BLUR_RING_BYTES of shared memory
 __device__ __forceinline__ void blur_body(const Geom& g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur, int tile, int f, uint8_t* s_ring)
@@ -1101,78 +1092,92 @@ __device__ __forceinline__ void blur_body(const Geom& g, const uint8_t* __restri
     const int item = (tile - L.blur0) * BLUR_NT + threadIdx.x;
     const int strip = item / L.blur_cgs, cg = item - strip * L.blur_cgs;
     const int x0 = BLUR_LO + cg * 8;                                              // first of this thread's 8 columns
-    const int ys = 13 + strip * BLUR_RH;                                          // first output row
-    const int ye = min(ys + BLUR_RH, L.h - 13);
-    if (tile - L.blur0 >= L.nblur || ys >= ye) return;
+    const int rh = L.blur_rh;                                                     // strip height, a multiple of 7
+    const int ys = 13 + strip * rh;                                               // first output row
+    const int nout = min(rh, L.h - 13 - ys);                                      // output rows this strip really has
+    if (tile - L.blur0 >= L.nblur || nout <= 0) return;
     const float k0 = __int_as_float(0x3d8fafb1), k1 = __int_as_float(0x3e06387e), k2 = __int_as_float(0x3e434a39), k3 = __int_as_float(0x3e5d4ae0);
     const unsigned long long K0 = f2_pack(k0, k0), K1 = f2_pack(k1, k1), K2 = f2_pack(k2, k2), K3 = f2_pack(k3, k3);
     const unsigned long long NEG23 = f2_pack(-8388608.0f, -8388608.0f), RND = f2_pack(12582912.0f, 12582912.0f);
     const uint8_t* src = pyr + (size_t)f * g.pyr_frame + L.img_off + (size_t)(ys - 3) * L.pitch + (x0 - 4);
     uint8_t* dst = blur + (size_t)f * g.pyr_frame + L.img_off + (size_t)ys * L.pitch + x0;
-    const bool hi_ok = x0 + 4 < L.pitch;                                          // second 8-byte load inside the row
-    const int nrows = (ye - ys) + 6;
     unsigned long long w[4][7];
-    // Source rows stream through a thread-private shared-memory ring filled by cp.async (LDGSTS): BLUR_DEPTH rows are
-    // in flight per thread with no register and -- the point -- no scoreboard cost (a warp has six scoreboards, so 14
-    // register loads in flight end up sharing them and the oldest load waits for the youngest).  A thread reads back
-    // only the 16 bytes it copied itself, so cp.async.wait_group is all the synchronisation there is.
+    // Source rows stream through a thread-private shared-memory ring filled by cp.async (LDGSTS): 7 rows are in flight
+    // per thread with no register and -- the point -- no scoreboard cost (a warp has six scoreboards, so 14 register
+    // loads in flight end up sharing them and the oldest load waits for the youngest).  A thread reads back only the
+    // 16 bytes it copied itself, so cp.async.wait_group is all the synchronisation there is.  The ring has as many
+    // slots as the row window (slot of source row r = r % 7, a compile-time index in the unrolled loop), every strip
+    // runs the same rh + 6 source rows (rows past a short last strip only feed outputs whose stores are masked; the
+    // pyramid buffer carries slack for them), and the first 6 rows -- which produce no output yet -- are a prologue: the
+    // steady-state body has no per-row bounds checks at all.
     const unsigned ring = (unsigned)__cvta_generic_to_shared(s_ring) + threadIdx.x * 16u;
 #pragma unroll
-    for (int d = 0; d < BLUR_DEPTH; ++d) {
-        if (d < nrows) blur_cp_row(ring + d * (BLUR_NT * 16u), src + (size_t)d * L.pitch, hi_ok);
+    for (int d = 0; d < 7; ++d) {
+        cp_async_8(ring + d * (BLUR_NT * 16u), src + (size_t)d * L.pitch);
+        cp_async_8(ring + d * (BLUR_NT * 16u) + 8u, src + (size_t)d * L.pitch + 8);
         cp_async_commit();
     }
-    src += (size_t)BLUR_DEPTH * L.pitch;
-    int slot = 0;                                                                  // ring slot of source row r
-#pragma unroll 1
-    for (int r0 = 0; r0 < nrows; r0 += 7) {
+    src += (size_t)7 * L.pitch;
+    // one source row in window slot K: wait, read it back, refill the slot with the row 7 further down, row pass
+    auto row_pass = [&](auto kc) {
+        constexpr int K = decltype(kc)::value;
+        cp_async_wait<6>();
+        const unsigned sa = ring + K * (BLUR_NT * 16u);
+        const uint4 ab = lds_v4(sa);
+        cp_async_8(sa, src); cp_async_8(sa + 8u, src + 8);
+        cp_async_commit();
+        src += L.pitch;
+        const uint32_t W[4] = {ab.x, ab.y, ab.z, ab.w};                            // bytes x0-4 .. x0+11; pixel i = x0-3+i is byte i+1
+        unsigned long long P[10];
 #pragma unroll
-        for (int k = 0; k < 7; ++k) {
-            const int r = r0 + k;
-            if (r < nrows) {
-                cp_async_wait<BLUR_DEPTH - 1>();                                   // row r has landed
-                const unsigned sa = ring + slot * (BLUR_NT * 16u);
-                const uint4 ab = lds_v4(sa);
-                const uint2 a = make_uint2(ab.x, ab.y), b = make_uint2(ab.z, ab.w);
-                if (r + BLUR_DEPTH < nrows) blur_cp_row(sa, src, hi_ok);           // refill the slot with row r + DEPTH
-                cp_async_commit();
-                src += L.pitch;
-                slot = slot + 1 == BLUR_DEPTH ? 0 : slot + 1;
-                const uint32_t W[4] = {a.x, a.y, b.x, b.y};                        // bytes x0-4 .. x0+11; pixel i = x0-3+i is byte i+1
-                unsigned long long P[10];
-#pragma unroll
-                for (int i = 0; i < 10; ++i) {
-                    const uint32_t lo = __byte_perm(W[(i + 1) >> 2], 0x4B000000u, 0x7650u | ((i + 1) & 3));
-                    const uint32_t hi = __byte_perm(W[(i + 5) >> 2], 0x4B000000u, 0x7650u | ((i + 5) & 3));
-                    P[i] = f2_add((unsigned long long)lo | ((unsigned long long)hi << 32), NEG23);
-                }
-#pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                    unsigned long long acc = f2_mul(K0, P[m]);
-                    acc = f2_fma(P[m + 1], K1, acc); acc = f2_fma(P[m + 2], K2, acc); acc = f2_fma(P[m + 3], K3, acc);
-                    acc = f2_fma(P[m + 4], K2, acc); acc = f2_fma(P[m + 5], K1, acc); acc = f2_fma(P[m + 6], K0, acc);
-                    w[m][k] = acc;                                                 // window slot of source row r is r % 7 == k
-                }
-                if (r >= 6) {
-                    uint32_t q[8];
-#pragma unroll
-                    for (int m = 0; m < 4; ++m) {
-                        unsigned long long o = f2_mul(K3, w[m][(k + 4) % 7]);                                   // row r-3
-                        o = f2_fma(f2_add(w[m][(k + 5) % 7], w[m][(k + 3) % 7]), K2, o);                        // r-2, r-4
-                        o = f2_fma(f2_add(w[m][(k + 6) % 7], w[m][(k + 2) % 7]), K1, o);                        // r-1, r-5
-                        o = f2_fma(f2_add(w[m][k], w[m][(k + 1) % 7]), K0, o);                                  // r,   r-6
-                        const unsigned long long rb = f2_add(o, RND);                                           // rint via 1.5 * 2^23
-                        q[m] = (uint32_t)rb; q[m + 4] = (uint32_t)(rb >> 32);
-                    }
-                    const uint32_t o0 = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
-                    const uint32_t o1 = __byte_perm(__byte_perm(q[4], q[5], 0x0040), __byte_perm(q[6], q[7], 0x0040), 0x5410);
-                    reinterpret_cast<uint32_t*>(dst)[0] = o0;                                                   // x0 = 4 mod 8: two word stores
-                    reinterpret_cast<uint32_t*>(dst)[1] = o1;
-                    dst += L.pitch;
-                }
-            }
+        for (int i = 0; i < 10; ++i) {
+            const uint32_t lo = __byte_perm(W[(i + 1) >> 2], 0x4B000000u, 0x7650u | ((i + 1) & 3));
+            const uint32_t hi = __byte_perm(W[(i + 5) >> 2], 0x4B000000u, 0x7650u | ((i + 5) & 3));
+            P[i] = f2_add((unsigned long long)lo | ((unsigned long long)hi << 32), NEG23);
         }
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            unsigned long long acc = f2_mul(K0, P[m]);
+            acc = f2_fma(P[m + 1], K1, acc); acc = f2_fma(P[m + 2], K2, acc); acc = f2_fma(P[m + 3], K3, acc);
+            acc = f2_fma(P[m + 4], K2, acc); acc = f2_fma(P[m + 5], K1, acc); acc = f2_fma(P[m + 6], K0, acc);
+            w[m][K] = acc;
+        }
+    };
+    // output row centred 3 rows above the newest source row (window slot K)
+    auto col_pass = [&](auto kc, bool store) {
+        constexpr int K = decltype(kc)::value;
+        uint32_t q[8];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            unsigned long long o = f2_mul(K3, w[m][(K + 4) % 7]);                                   // row r-3
+            o = f2_fma(f2_add(w[m][(K + 5) % 7], w[m][(K + 3) % 7]), K2, o);                        // r-2, r-4
+            o = f2_fma(f2_add(w[m][(K + 6) % 7], w[m][(K + 2) % 7]), K1, o);                        // r-1, r-5
+            o = f2_fma(f2_add(w[m][K], w[m][(K + 1) % 7]), K0, o);                                  // r,   r-6
+            const unsigned long long rb = f2_add(o, RND);                                           // rint via 1.5 * 2^23
+            q[m] = (uint32_t)rb; q[m + 4] = (uint32_t)(rb >> 32);
+        }
+        const uint32_t o0 = __byte_perm(__byte_perm(q[0], q[1], 0x0040), __byte_perm(q[2], q[3], 0x0040), 0x5410);
+        const uint32_t o1 = __byte_perm(__byte_perm(q[4], q[5], 0x0040), __byte_perm(q[6], q[7], 0x0040), 0x5410);
+        if (store) {
+            reinterpret_cast<uint32_t*>(dst)[0] = o0;                                               // x0 = 4 mod 8: two word stores
+            reinterpret_cast<uint32_t*>(dst)[1] = o1;
+        }
+        dst += L.pitch;
+    };
+    row_pass(ic<0>{}); row_pass(ic<1>{}); row_pass(ic<2>{}); row_pass(ic<3>{}); row_pass(ic<4>{}); row_pass(ic<5>{});
+    int j = 0;                                                                     // output row inside the strip
+#pragma unroll 1
+    for (int grp = 0; grp < rh; grp += 7) {                                       // source rows 6 + grp .. 12 + grp: window slots 6, 0, 1, .., 5
+        row_pass(ic<6>{}); col_pass(ic<6>{}, j + 0 < nout);
+        row_pass(ic<0>{}); col_pass(ic<0>{}, j + 1 < nout);
+        row_pass(ic<1>{}); col_pass(ic<1>{}, j + 2 < nout);
+        row_pass(ic<2>{}); col_pass(ic<2>{}, j + 3 < nout);
+        row_pass(ic<3>{}); col_pass(ic<3>{}, j + 4 < nout);
+        row_pass(ic<4>{}); col_pass(ic<4>{}, j + 5 < nout);
+        row_pass(ic<5>{}); col_pass(ic<5>{}, j + 6 < nout);
+        j += 7;
     }
+    cp_async_wait<0>();                                                            // nothing of this thread may still land in shared memory after it exits
 }
 
 __global__ void __launch_bounds__(BLUR_NT) k_blur(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr, uint8_t* __restrict__ blur)
