@@ -36,6 +36,13 @@ __device__ __forceinline__ void cp_async_4(unsigned dst, const void* src) { asm 
 __device__ __forceinline__ void cp_async_8(unsigned dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ uint2 lds_v2(unsigned addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u16(unsigned addr, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(addr), "h"((unsigned short)v) : "memory"); }
 __device__ __forceinline__ uint4 lds_v4(unsigned addr)
 {
     uint4 v;
@@ -451,18 +458,24 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
         }
         __syncthreads();
         // ---- phase A (per warp): compass rejection on (row, 128-pixel half) items -> private queue
+        // Shared memory is addressed through one precomputed 32-bit base per chunk (LDS with immediate offsets), and the
+        // survivors of an item are compacted with ONE warp prefix: each lane counts its 0..4 passing pixels, the counts'
+        // three bit planes go through three ballots (prefix = popc of the lower lanes' bits, weighted 1 / 2 / 4), and the
+        // lane writes its entries back to back.  (Queue order is free: phase B scores every entry, the NMS works on bits.)
         int qn = 0;
         {
             constexpr unsigned K = ((511u - T) << 16) | (511u - T);
+            const unsigned q_s = (unsigned)__cvta_generic_to_shared(myq);
+            // 8-byte aligned: word index (sy+3)*TPW + 2q + 2 + xo/2 is even (TPW, xo/2 even)
+            const unsigned lane_s = (unsigned)__cvta_generic_to_shared(s_img) + (unsigned)(3 * TPW + 2 * lane + 2 + (xo >> 1)) * 4u;
             for (int item = wid; item < 2 * nsr; item += NWARP) {
                 const int sy = item >> 1, half = item & 1;
                 if (half * 128 >= need) continue;            // warp-uniform: no needed pixel in this half
                 const int q = half * 32 + lane;              // quad column
                 unsigned m0 = 0, m1 = 0;
                 if (4 * q < need) {
-                    // 8-byte aligned: word index (sy+3)*TPW + 2q + 2 + xo/2 is even (TPW, xo/2 even)
-                    const uint2* wp = reinterpret_cast<const uint2*>(reinterpret_cast<const uint32_t*>(s_img) + (sy + 3) * TPW + 2 * q + 2 + (xo >> 1));
-                    const uint2 c = wp[0], n = wp[-3 * (TPW / 2)], s = wp[3 * (TPW / 2)], e2 = wp[1], w2 = wp[-1];
+                    const unsigned ad = lane_s + (unsigned)(sy * TPW + half * 64) * 4u;
+                    const uint2 c = lds_v2(ad), n = lds_v2(ad - 3 * TPW * 4), s = lds_v2(ad + 3 * TPW * 4), e2 = lds_v2(ad + 8), w2 = lds_v2(ad - 8);
                     const unsigned e0 = __byte_perm(c.y, e2.x, 0x5432), e1 = __byte_perm(e2.x, e2.y, 0x5432);
                     const unsigned w0 = __byte_perm(w2.x, w2.y, 0x5432), w1 = __byte_perm(w2.y, c.x, 0x5432);
                     const unsigned D0 = vmax2(vmin2(n.x, s.x), vmin2(e0, w0)), B0 = vmin2(vmax2(n.x, s.x), vmax2(e0, w0));
@@ -470,18 +483,18 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
                     m0 = (c.x + K - D0) | (B0 + K - c.x);
                     m1 = (c.y + K - D1) | (B1 + K - c.y);
                 }
+                // pass flags of the quad's four pixels: bit 9 / bit 25 of m0, m1
+                const unsigned f0 = (m0 >> 9) & 1u, f1 = (m0 >> 25) & 1u, f2 = (m1 >> 9) & 1u, f3 = (m1 >> 25) & 1u;
+                const unsigned cnt = f0 + f1 + f2 + f3;      // 0 .. 4
+                const unsigned c0 = __ballot_sync(0xffffffffu, cnt & 1u), c1 = __ballot_sync(0xffffffffu, cnt & 2u), c2 = __ballot_sync(0xffffffffu, cnt & 4u);
+                unsigned pos = (unsigned)qn + __popc(c0 & lt) + 2u * __popc(c1 & lt) + 4u * __popc(c2 & lt);
+                qn += __popc(c0) + 2 * __popc(c1) + 4 * __popc(c2);
                 const unsigned ent = (unsigned)(sy << 8) | (unsigned)(4 * q);
-                const bool p0 = m0 & 0x200u, p1 = m0 & 0x02000000u, p2 = m1 & 0x200u, p3 = m1 & 0x02000000u;
-                const unsigned b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
-                const unsigned b2 = __ballot_sync(0xffffffffu, p2), b3 = __ballot_sync(0xffffffffu, p3);
-                if (p0) myq[qn + __popc(b0 & lt)] = (uint16_t)ent;
-                qn += __popc(b0);
-                if (p1) myq[qn + __popc(b1 & lt)] = (uint16_t)(ent + 1);
-                qn += __popc(b1);
-                if (p2) myq[qn + __popc(b2 & lt)] = (uint16_t)(ent + 2);
-                qn += __popc(b2);
-                if (p3) myq[qn + __popc(b3 & lt)] = (uint16_t)(ent + 3);
-                qn += __popc(b3);
+                unsigned sa = q_s + 2u * pos;
+                if (f0) { sts_u16(sa, ent); sa += 2u; }
+                if (f1) { sts_u16(sa, ent + 1u); sa += 2u; }
+                if (f2) { sts_u16(sa, ent + 2u); sa += 2u; }
+                if (f3) sts_u16(sa, ent + 3u);
             }
         }
         __syncwarp();
