@@ -483,9 +483,10 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
                     m0 = (c.x + K - D0) | (B0 + K - c.x);
                     m1 = (c.y + K - D1) | (B1 + K - c.y);
                 }
-                // pass flags of the quad's four pixels: bit 9 / bit 25 of m0, m1
-                const unsigned f0 = (m0 >> 9) & 1u, f1 = (m0 >> 25) & 1u, f2 = (m1 >> 9) & 1u, f3 = (m1 >> 25) & 1u;
-                const unsigned cnt = f0 + f1 + f2 + f3;      // 0 .. 4
+                // pass flags of the quad's four pixels: bits 9 / 25 of m0 and (moved up one) bits 10 / 26 of m1, in one word
+                const unsigned pf = (m0 & 0x02000200u) | ((m1 << 1) & 0x04000400u);
+                const unsigned cnt = (unsigned)__popc(pf);   // 0 .. 4
+                const unsigned f0 = pf & 0x200u, f1 = pf & 0x02000000u, f2 = pf & 0x400u, f3 = pf & 0x04000000u;
                 const unsigned c0 = __ballot_sync(0xffffffffu, cnt & 1u), c1 = __ballot_sync(0xffffffffu, cnt & 2u), c2 = __ballot_sync(0xffffffffu, cnt & 4u);
                 unsigned pos = (unsigned)qn + __popc(c0 & lt) + 2u * __popc(c1 & lt) + 4u * __popc(c2 & lt);
                 qn += __popc(c0) + 2 * __popc(c1) + 4 * __popc(c2);
