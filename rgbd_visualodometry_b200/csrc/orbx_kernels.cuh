@@ -42,6 +42,8 @@ __device__ __forceinline__ uint2 lds_v2(unsigned addr)
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned lds_u16(unsigned addr) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ void sts_u8(unsigned addr, unsigned v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_u16(unsigned addr, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(addr), "h"((unsigned short)v) : "memory"); }
 __device__ __forceinline__ uint4 lds_v4(unsigned addr)
 {
@@ -501,43 +503,49 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
         __syncwarp();
         // ---- phase B (same warp): full segment test + score; corners inside the output region -> private NMS queue
         int cn = 0;
-        for (int i0 = 0; i0 < qn; i0 += 32) {
-            const int i = i0 + lane;
-            bool corner = false;
-            int e = 0;
-            if (i < qn) {
-                e = myq[i];
-                const int sy = e >> 8, sx = e & 255;
-                const uint16_t* c = &s_img[(sy + 3) * TP + sx + 4 + xo];
-                const int v = c[0];
-                unsigned q[16];
-#define ORBX_PK(k, dx, dy) q[k] = (unsigned)c[(dy) * TP + (dx)] * 0xFFFF0001u + 0x00FF0000u
-                ORBX_PK(0, 0, 3);   ORBX_PK(1, 1, 3);   ORBX_PK(2, 2, 2);    ORBX_PK(3, 3, 1);
-                ORBX_PK(4, 3, 0);   ORBX_PK(5, 3, -1);  ORBX_PK(6, 2, -2);   ORBX_PK(7, 1, -3);
-                ORBX_PK(8, 0, -3);  ORBX_PK(9, -1, -3); ORBX_PK(10, -2, -2); ORBX_PK(11, -3, -1);
-                ORBX_PK(12, -3, 0); ORBX_PK(13, -3, 1); ORBX_PK(14, -2, 2);  ORBX_PK(15, -1, 3);
+        {
+            const unsigned q_s = (unsigned)__cvta_generic_to_shared(myq);
+            const unsigned img_s = (unsigned)__cvta_generic_to_shared(s_img) + (unsigned)(3 * TP + 4 + xo) * 2u;   // pixel (sy, sx) at + (sy * TP + sx) * 2
+            const unsigned sc_s = (unsigned)__cvta_generic_to_shared(s_score);
+            // sx window of corners that belong to this chunk's output region: x = ox0 - 4 + sx in [max(ox0, EDGE), ox1)
+            const int sx_lo = max(ox0, ORBX_EDGE) - (ox0 - 4), sx_hi = ox1 - (ox0 - 4), sy_hi = y1 - y0;
+            for (int i0 = 0; i0 < qn; i0 += 32) {
+                const int i = i0 + lane;
+                bool corner = false;
+                unsigned e = 0;
+                if (i < qn) {
+                    e = lds_u16(q_s + 2u * (unsigned)i);
+                    const unsigned sy = e >> 8, sx = e & 255u;
+                    const unsigned c = img_s + (sy * TP + sx) * 2u;
+                    const int v = (int)lds_u16(c);
+                    unsigned q[16];
+#define ORBX_PK(k, dx, dy) q[k] = lds_u16(c + ((dy) * TP + (dx)) * 2) * 0xFFFF0001u + 0x00FF0000u
+                    ORBX_PK(0, 0, 3);   ORBX_PK(1, 1, 3);   ORBX_PK(2, 2, 2);    ORBX_PK(3, 3, 1);
+                    ORBX_PK(4, 3, 0);   ORBX_PK(5, 3, -1);  ORBX_PK(6, 2, -2);   ORBX_PK(7, 1, -3);
+                    ORBX_PK(8, 0, -3);  ORBX_PK(9, -1, -3); ORBX_PK(10, -2, -2); ORBX_PK(11, -3, -1);
+                    ORBX_PK(12, -3, 0); ORBX_PK(13, -3, 1); ORBX_PK(14, -2, 2);  ORBX_PK(15, -1, 3);
 #undef ORBX_PK
-                unsigned m3[16], m9[16];
+                    unsigned m3[16], m9[16];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) m3[k] = vmax3(q[k], q[(k + 1) & 15], q[(k + 2) & 15]);
+                    for (int k = 0; k < 16; ++k) m3[k] = vmax3(q[k], q[(k + 1) & 15], q[(k + 2) & 15]);
 #pragma unroll
-                for (int k = 0; k < 16; ++k) m9[k] = vmax3(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
-                unsigned mm = vmin3(vmin3(vmin3(m9[0], m9[1], m9[2]), vmin3(m9[3], m9[4], m9[5]), vmin3(m9[6], m9[7], m9[8])),
-                                    vmin3(vmin3(m9[9], m9[10], m9[11]), vmin3(m9[12], m9[13], m9[14]), m9[15]),
-                                    0xFFFFFFFFu);
-                const int A = v - (int)(mm & 0xffffu);
-                const int nB = 255 - (int)(mm >> 16) - v;
-                const int sc = max(A, nB);
-                if (sc > T) {
-                    s_score[sy * SP + sx] = (uint8_t)(sc - 1);
-                    const int x = ox0 - 4 + sx;
-                    corner = x >= max(ox0, ORBX_EDGE) && x < ox1 && sy >= 1 && sy <= y1 - y0;
+                    for (int k = 0; k < 16; ++k) m9[k] = vmax3(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+                    unsigned mm = vmin3(vmin3(vmin3(m9[0], m9[1], m9[2]), vmin3(m9[3], m9[4], m9[5]), vmin3(m9[6], m9[7], m9[8])),
+                                        vmin3(vmin3(m9[9], m9[10], m9[11]), vmin3(m9[12], m9[13], m9[14]), m9[15]),
+                                        0xFFFFFFFFu);
+                    const int A = v - (int)(mm & 0xffffu);
+                    const int nB = 255 - (int)(mm >> 16) - v;
+                    const int sc = max(A, nB);
+                    if (sc > T) {
+                        sts_u8(sc_s + sy * SP + sx, (unsigned)(sc - 1));
+                        corner = (int)sx >= sx_lo && (int)sx < sx_hi && sy - 1u < (unsigned)sy_hi;   // 1 <= sy <= y1 - y0
+                    }
                 }
+                const unsigned bc = __ballot_sync(0xffffffffu, corner);
+                __syncwarp();                                // every lane has read its entry of this batch before slots <= i0 + 31 are rewritten
+                if (corner) sts_u16(q_s + 2u * (unsigned)(cn + __popc(bc & lt)), e);
+                cn += __popc(bc);
             }
-            const unsigned bc = __ballot_sync(0xffffffffu, corner);
-            __syncwarp();                                    // every lane has read its entry of this batch before slots <= i0 + 31 are rewritten
-            if (corner) mycq[cn + __popc(bc & lt)] = (uint16_t)e;
-            cn += __popc(bc);
         }
         __syncthreads();                                     // every score of the tile is in place
         // ---- phase C (per warp): 3x3 NMS of its queued corners
