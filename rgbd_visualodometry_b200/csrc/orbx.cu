@@ -35,7 +35,6 @@ constexpr int MAX_LANES = 4;               // concurrent frame-range pipelines o
 constexpr int HOST_MAX_LANES = 8;          // host-buffer calls: more, shorter ranges shrink the un-overlapped head (first upload) and tail
 constexpr int LANE_MIN_FRAMES = 64;        // a lane must still fill the GPU on its own
 constexpr int HOST_LANE_MIN_FRAMES = 16;   // host-buffer batches: lanes mainly overlap PCIe copies with kernels
-constexpr int FUSED_PYR_MIN_BATCH = 128;   // from this batch size on, one CTA per frame (k_gray_pyr) fills the GPU
 constexpr int N_STAGES = 7;
 const char* const k_stage_names[N_STAGES] = {"gray", "pyramid", "fast_nms", "select_harris", "blur", "describe", "match"};
 
@@ -253,7 +252,7 @@ void stage_mark(orbx_ctx* c, int i)
 // The extraction pipeline on device-resident frames; everything asynchronous on c->stream.
 // The kernel sequence for frames [f0, f0 + nb) on stream `st`.  Every buffer is frame-major, so a frame range is
 // just a base-pointer offset.
-int run_extract_range(orbx_ctx* c, cudaStream_t st, bool marks, bool fused, int f0, int nb,
+int run_extract_range(orbx_ctx* c, cudaStream_t st, bool marks, int f0, int nb,
                       const uint8_t* d_imgs, size_t step, size_t frame_stride, int channels, float* d_kps, uint8_t* d_desc, int cap,
                       int* d_counts)
 {
@@ -273,16 +272,7 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, bool marks, bool fused, int 
     const unsigned B = (unsigned)nb;
 
     if (marks) stage_mark(c, 0);
-    const int aligned4 = ((reinterpret_cast<uintptr_t>(d_imgs) | step | frame_stride) & 3) == 0;
-    bool narrow = true;                                      // every level within the 3-word window of the narrow pyramid kernels
-    for (int l = 1; l < g.nlevels; ++l) narrow = narrow && g.L[l].xspan <= 7;
-    if (fused && narrow) {
-        // the batch alone fills the GPU: one CTA per frame runs gray + the whole level chain in a single launch
-        if (channels == 3) k_gray_pyr<3><<<B, GP_NT, 0, st>>>(d_imgs, frame_stride, step, aligned4, g, pyr, tabs);
-        else               k_gray_pyr<1><<<B, GP_NT, 0, st>>>(d_imgs, frame_stride, step, aligned4, g, pyr, tabs);
-        ++c->launches;
-        if (marks) stage_mark(c, 1);
-    } else {
+    {
         {
             const int aligned16 = ((reinterpret_cast<uintptr_t>(d_imgs) | step | frame_stride) & 15) == 0;
             const dim3 blk(32, 8);
@@ -339,10 +329,9 @@ int run_extract(orbx_ctx* c, const uint8_t* d_imgs, int batch, int w, int h, siz
     static const int env_lanes = getenv("ORBX_LANES") ? atoi(getenv("ORBX_LANES")) : 3;
     int lanes = std::max(1, std::min(env_lanes, MAX_LANES));
     if (batch < lanes * LANE_MIN_FRAMES) lanes = 1;
-    const bool fused = batch / lanes >= FUSED_PYR_MIN_BATCH;    // per-stage profiling (one lane) times the same kernels the lanes run
     if (c->profiling) lanes = 1;
     if (lanes == 1) {
-        rc = run_extract_range(c, c->stream, c->profiling, fused, 0, batch, d_imgs, step,
+        rc = run_extract_range(c, c->stream, c->profiling, 0, batch, d_imgs, step,
                                frame_stride, channels, d_kps, d_desc, cap, d_counts);
         if (rc) return rc;
     } else {
@@ -351,7 +340,7 @@ int run_extract(orbx_ctx* c, const uint8_t* d_imgs, int batch, int w, int h, siz
             const int f0 = (int)((long)batch * k / lanes), f1 = (int)((long)batch * (k + 1) / lanes);
             cudaStream_t st = k == 0 ? c->stream : c->lane[k];
             if (k > 0) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
-            rc = run_extract_range(c, st, false, fused, f0, f1 - f0, d_imgs, step, frame_stride, channels, d_kps, d_desc, cap, d_counts);
+            rc = run_extract_range(c, st, false, f0, f1 - f0, d_imgs, step, frame_stride, channels, d_kps, d_desc, cap, d_counts);
             if (rc) return rc;
             if (k > 0) { CU(cudaEventRecord(c->ev_join[k], st)); CU(cudaStreamWaitEvent(c->stream, c->ev_join[k], 0)); }
         }
@@ -623,7 +612,7 @@ int orbx_detect_and_compute_batch(orbx_ctx* c, const uint8_t* const* imgs, int b
         cudaStream_t st = k == 0 ? c->stream : c->lane[k];
         if (k > 0) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
         if ((rc = upload_frames(c, st, imgs, f0, f1, step, row, h, dstep, fstride))) return rc;
-        if ((rc = run_extract_range(c, st, c->profiling, f1 - f0 >= FUSED_PYR_MIN_BATCH, f0, f1 - f0, (const uint8_t*)c->in.p, dstep,
+        if ((rc = run_extract_range(c, st, c->profiling, f0, f1 - f0, (const uint8_t*)c->in.p, dstep,
                                     fstride, channels, (float*)c->kps.p, (uint8_t*)c->desc.p, cap, (int*)c->counts.p)))
             return rc;
         const size_t n = (size_t)(f1 - f0);
@@ -700,7 +689,7 @@ int orbx_extract_match_batch(orbx_ctx* c, const uint8_t* const* imgs, int batch,
         cudaStream_t st = k == 0 ? c->stream : c->lane[k];
         if (k > 0) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
         if ((rc = upload_frames(c, st, imgs, f0, f1, step, row, h, dstep, fstride))) return rc;
-        if ((rc = run_extract_range(c, st, c->profiling, f1 - f0 >= FUSED_PYR_MIN_BATCH, f0, f1 - f0, (const uint8_t*)c->in.p, dstep,
+        if ((rc = run_extract_range(c, st, c->profiling, f0, f1 - f0, (const uint8_t*)c->in.p, dstep,
                                     fstride, channels, (float*)c->kps.p, (uint8_t*)c->desc.p, cap, (int*)c->counts.p)))
             return rc;
         CU(cudaMemcpyAsync(h_counts + f0, (int*)c->counts.p + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
@@ -1212,7 +1201,7 @@ int orbx_submit_frame(orbx_ctx* c, const uint8_t* img, int w, int h, size_t step
     // everything below is stream-ordered behind the previous frame: the shared per-frame workspace is reused safely
     CU(cudaMemcpyAsync(c->in.p, a.h_in, fstride, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemsetAsync(c->status.p, 0, sizeof(int), c->stream));
-    if ((rc = run_extract_range(c, c->stream, false, false, 0, 1, (const uint8_t*)c->in.p, dstep, fstride, channels, (float*)a.d_kps.p,
+    if ((rc = run_extract_range(c, c->stream, false, 0, 1, (const uint8_t*)c->in.p, dstep, fstride, channels, (float*)a.d_kps.p,
                                 (uint8_t*)a.d_desc.p, cap, (int*)a.d_counts.p)))
         return rc;
     CU(cudaMemcpyAsync(a.h_out, a.d_counts.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));

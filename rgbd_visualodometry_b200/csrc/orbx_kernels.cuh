@@ -3,9 +3,8 @@
 // and is bit-exact against OpenCV: integer stages in integer arithmetic, float stages with explicit
 // round-to-nearest intrinsics (never contracted) and __fmaf_rn only where OpenCV's own build uses FMA (A.8).
 //
-//   k_gray_pyr      A.1+2 fused gray + 8-level pyramid, one CTA per frame (large batches); k_gray / k_pyr_down per level otherwise
-//   k_gray          A.1   BGR -> gray (level 0)                         HBM-bound, 4 px / thread
-//   k_pyr_down      A.2   INTER_LINEAR_EXACT level l from level l-1     thread = output column, horizontal pass reused
+//   k_gray          A.1   BGR -> gray (level 0)                         HBM-bound, 16 px / thread
+//   k_pyr_down      A.2   INTER_LINEAR_EXACT level l from level l-1     thread = 8 output columns x 16 rows, source rows streamed by cp.async
 //   k_fast_bands    A.3   FAST-9/16 score + 3x3 NMS -> per-row lists    smem tiles with halos, u16x2 SIMD min/max,
 //                                                                       ballot compaction, raster order kept
 //   k_select        A.4-6 retainBest(2n) -> Harris -> retainBest(n)     libstdc++ introselect order reproduced
@@ -105,81 +104,13 @@ __global__ void __launch_bounds__(256) k_gray(const uint8_t* __restrict__ in, un
 
 // ------------------------------------------------------------------------------------------------ A.2 pyramid
 // dst(x,y) = (h0*(256-cy) + h1*cy + 32768) >> 16,  h = p[i0]*(256-cx) + p[i1]*cx  (8.8 taps from host tables).
-// One thread owns 4 adjacent output columns (taps, byte offsets and funnel-shift amounts stay in registers) and
-// walks PYR_RH output rows.  A source row costs three aligned 32-bit loads (the 4 outputs read <= 9 consecutive
-// source bytes); each output's horizontal pass is one funnel shift + one IDP.2A (u16 taps x u8 pixels), and it is
-// reused by the next output row when that row needs the same source row (the common case at ratio 1.2).
-// Load/store instructions per pixel drop ~6x against byte gathers -- the LSU issue rate was the bound.
+// A quad of 4 adjacent output columns keeps its taps, byte offsets and funnel-shift amounts in registers; a source row
+// costs it three (wide: four) aligned 32-bit words (the 4 outputs read <= 9 consecutive source bytes at the reference's
+// ratio 1.2); each output's horizontal pass is one funnel shift + one IDP.2A (u16 taps x u8 pixels), taken once per
+// source row and reused by the next output row that needs the same row.
 constexpr int PYR_RH = 16;          // output rows per thread
-constexpr int PYR_BY = 4;           // row strips (warps) per CTA; a warp covers 128 output columns
 struct PyrRow { uint32_t h[4]; };
-// NOTE: plain (coherent) loads on purpose -- the fused per-frame kernel reads rows that other threads of the same
-// CTA wrote earlier in the same launch, which the non-coherent read-only path does not guarantee to see.
-__device__ __forceinline__ PyrRow pyr_hpass(const uint8_t* row, bool w2ok, const uint32_t* coef, const uint32_t* sh, const bool* hi)
-{
-    const uint32_t* p = reinterpret_cast<const uint32_t*>(row);
-    const uint32_t w0 = p[0], w1 = p[1], w2 = w2ok ? p[2] : 0u;
-    PyrRow r;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t v = __funnelshift_r(hi[k] ? w1 : w0, hi[k] ? w2 : w1, sh[k]);     // bytes: p[i0], p[i0 + 1], ...
-        r.h[k] = __dp2a_lo(coef[k], v, 0u);                                               // p[i0]*c0 + p[i0+1]*c1, exact 8.8
-    }
-    return r;
-}
-
-// output columns x .. x+3, rows [ys, ye) of level l of frame f
-__device__ __forceinline__ void pyr_down_item(const Geom& g, int l, int f, int x, int ys, int ye, uint8_t* pyr, const uint32_t* __restrict__ tabs)
-{
-    const LevelGeom& D = g.L[l];
-    const LevelGeom& S = g.L[l - 1];
-    uint8_t* dst = pyr + (size_t)f * g.pyr_frame + D.img_off + (size_t)ys * D.pitch + x;
-    if (x >= D.w) {                                          // row padding: keep it zero
-        for (int y = ys; y < ye; ++y, dst += D.pitch) *reinterpret_cast<uint32_t*>(dst) = 0u;
-        return;
-    }
-    uint32_t coef[4], sh[4];
-    bool hi[4];
-    const uint32_t t0 = __ldg(tabs + D.xtab + x);
-    const int a = (int)(t0 & 0xffffu) & ~3;                  // aligned source byte all four outputs are addressed from
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        uint32_t t = (x + k < D.w) ? __ldg(tabs + D.xtab + x + k) : (uint32_t)a;       // padding columns: taps 0 -> output 0
-        const int off = (int)(t & 0xffffu) - a;              // 0 .. 7
-        const uint32_t c1 = t >> 16;
-        coef[k] = (x + k < D.w) ? ((256u - c1) | (c1 << 16)) : 0u;
-        hi[k] = off >= 4;
-        sh[k] = (uint32_t)(off & 3) * 8u;
-    }
-    const bool w2ok = a + 8 < S.pitch;
-    const uint8_t* src = pyr + (size_t)f * g.pyr_frame + S.img_off + a;
-    const uint32_t* ytab = tabs + D.ytab;
-    int have = -1;                                           // source row whose horizontal pass is in hb
-    PyrRow ha, hb;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { ha.h[k] = 0; hb.h[k] = 0; }
-#pragma unroll 2
-    for (int y = ys; y < ye; ++y, dst += D.pitch) {
-        const uint32_t ty = __ldg(ytab + y);
-        const int y0 = ty & 0xffff, y1 = min(y0 + 1, S.h - 1);
-        const uint32_t cy1 = ty >> 16, cy0 = 256u - cy1;
-        if (y0 == have) ha = hb;
-        else ha = pyr_hpass(src + (size_t)y0 * S.pitch, w2ok, coef, sh, hi);
-        if (y1 != y0) hb = pyr_hpass(src + (size_t)y1 * S.pitch, w2ok, coef, sh, hi);
-        else hb = ha;
-        have = y1;
-        uint32_t out = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t v = (ha.h[k] * cy0 + hb.h[k] * cy1 + 32768u) >> 16;
-            out |= min(v, 255u) << (8 * k);
-        }
-        *reinterpret_cast<uint32_t*>(dst) = out;
-    }
-}
-
-// One level per launch (the path every lane of a batch takes unless the batch alone fills the GPU).  Same arithmetic
-// as pyr_down_item, restructured around the SOURCE rows: the thread streams the source rows it needs, in order,
+// One level per launch.  The kernel is organised around the SOURCE rows: the thread streams the source rows it needs, in order,
 // through a private shared-memory ring filled by cp.async (PYR_DEPTH rows in flight), takes the horizontal pass of
 // each once, and emits an output row as soon as its lower source row has passed.  Load latency sits under the
 // arithmetic of the rows already there instead of in front of every output row.
@@ -316,58 +247,6 @@ __global__ void __launch_bounds__(PYR_NT) k_pyr_down(const __grid_constant__ Geo
     for (int s = s0; s <= s1; s += 2) {
         step(s, hA, hB);
         if (s + 1 <= s1) step(s + 1, hB, hA);
-    }
-}
-
-// Fused gray + whole pyramid, ONE CTA PER FRAME: the level chain l-1 -> l is a dependency only inside a frame, so a
-// frame-private CTA walks it with block barriers -- one launch instead of eight, no per-level launch tails, and the
-// frame's levels stay hot in L1/L2 while they are consumed.  Used when the batch alone fills the GPU.
-constexpr int GP_NT = 512;
-constexpr int GP_RS = 8;               // output rows per work item
-template <int CH>
-__global__ void __launch_bounds__(GP_NT, 2) k_gray_pyr(const uint8_t* __restrict__ in, unsigned long long frame_stride,
-                                                       unsigned long long step, int aligned4, const __grid_constant__ Geom g,
-                                                       uint8_t* pyr, const uint32_t* __restrict__ tabs)
-{
-    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    {
-        const LevelGeom& L = g.L[0];
-        const int nq = L.pitch >> 2;
-        for (int y = wid; y < L.h; y += GP_NT / 32) {
-            const uint8_t* srow = in + (size_t)f * frame_stride + (size_t)y * step;
-            uint32_t* drow = reinterpret_cast<uint32_t*>(pyr + (size_t)f * g.pyr_frame + L.img_off + (size_t)y * L.pitch);
-            for (int q = lane; q < nq; q += 32) {
-                const int x = q * 4;
-                uint32_t out = 0;
-                if (aligned4 && x + 3 < L.w) {
-                    if (CH == 3) {
-                        const uint32_t* s4 = reinterpret_cast<const uint32_t*>(srow + (size_t)x * 3);
-                        out = gray4(__ldg(s4), __ldg(s4 + 1), __ldg(s4 + 2));
-                    } else {
-                        out = __ldg(reinterpret_cast<const uint32_t*>(srow + x));
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        if (x + k < L.w) {
-                            const uint8_t* s = srow + (size_t)(x + k) * CH;
-                            const uint32_t p = CH == 3 ? (3735u * __ldg(s) + 19235u * __ldg(s + 1) + 9798u * __ldg(s + 2) + 16384u) >> 15 : (uint32_t)__ldg(s);
-                            out |= p << (8 * k);
-                        }
-                }
-                drow[q] = out;
-            }
-        }
-    }
-    for (int l = 1; l < g.nlevels; ++l) {
-        __syncthreads();                                     // level l-1 of this frame is complete (block-visible)
-        const LevelGeom& D = g.L[l];
-        if (D.w <= 0 || D.h <= 0) continue;
-        const int nq = D.pitch >> 2, nstrips = (D.h + GP_RS - 1) / GP_RS;
-        for (int item = tid; item < nq * nstrips; item += GP_NT) {
-            const int strip = item / nq, q = item - strip * nq;
-            pyr_down_item(g, l, f, q * 4, strip * GP_RS, min(strip * GP_RS + GP_RS, D.h), pyr, tabs);
-        }
     }
 }
 

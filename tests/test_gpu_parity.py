@@ -263,9 +263,8 @@ def test_orb_noise_global_workspace(orbmod, oracle):
     _assert_kp_equal(k, d, ko, do, "noise vga")
 
 
-def test_orb_large_batch_fused_pyramid(orbmod, oracle):
-    """Batches >= 128 frames take the fused one-CTA-per-frame gray+pyramid kernel: every frame checked, plus the
-    level images of two frames."""
+def test_orb_large_batch_lanes(orbmod, oracle):
+    """A large batch is cut into frame ranges that run on their own streams: every frame checked against the oracle."""
     from rgbd_visualodometry_b200.synth import synth_frame
     b = 130
     frames = [synth_frame(150, 200, 5000 + i) for i in range(b)]
@@ -278,7 +277,7 @@ def test_orb_large_batch_fused_pyramid(orbmod, oracle):
             assert np.array_equal(ctx.debug_level(i, l, ws[l], hs[l]), dump["levels"][l]), f"frame {i} level {l}"
     for i, fr in enumerate(frames):
         ko, do = oracle.detect_and_compute(fr, 200)
-        _assert_kp_equal(kps[i, :cnt[i]], desc[i, :cnt[i]], ko, do, f"fused batch frame {i}")
+        _assert_kp_equal(kps[i, :cnt[i]], desc[i, :cnt[i]], ko, do, f"large batch frame {i}")
     ctx.close()
 
 

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Small end-to-end run for compute-sanitizer (memcheck): every kernel on tiny inputs, including the fused pyramid path."""
+"""Small end-to-end run for compute-sanitizer (memcheck): every kernel on tiny inputs, including the multi-lane batch path."""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -8,7 +8,7 @@ from rgbd_visualodometry_b200 import orb
 from rgbd_visualodometry_b200.synth import synth_frame, synth_descriptors, synth_map_queries
 ctx = orb.Context(150, 1.2, 8, 200, 150, 130)
 frames = [synth_frame(150, 200, 7000 + i) for i in range(130)]
-k, d, n = ctx.detect_and_compute_batch(frames)                      # fused pyramid + lanes
+k, d, n = ctx.detect_and_compute_batch(frames)                      # lanes
 k1, d1 = ctx.detect_and_compute(synth_frame(149, 197, 3))           # per-level kernels, odd size
 t = synth_descriptors(333, 1); q = synth_map_queries(t, 517, 2)
 m = ctx.match(q, t); m2 = ctx.knn_match2(q, t)
