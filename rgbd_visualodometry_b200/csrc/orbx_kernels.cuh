@@ -41,6 +41,7 @@ __device__ __forceinline__ uint2 lds_v2(unsigned addr)
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned lds_u32(unsigned addr) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
 __device__ __forceinline__ unsigned lds_u16(unsigned addr) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory"); return v; }
 __device__ __forceinline__ void sts_u8(unsigned addr, unsigned v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_u16(unsigned addr, unsigned v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(addr), "h"((unsigned short)v) : "memory"); }
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(PYR_NT) k_pyr_down(const __grid_constant__ Geo
 //             score = max(A, -B) - 1 (corner iff > t).  Corners inside the output region go to a private NMS queue.
 //   phase C   3x3 NMS (strict >) of the queued corners on the shared score tile -> per-row bit masks
 //   phase D   ordered extraction of the bit masks (popc prefix) -> global per-row lists
-template <int R, int NT>
+template <int R, int NT, int DBG = 0>
 __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr,
                                                    uint32_t* __restrict__ rowcnt, uint32_t* __restrict__ rowent)
 {
@@ -338,15 +339,17 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
             if (tid < R * MW) s_mask[tid] = 0;
         }
         __syncthreads();
-        // ---- phase A (per warp): compass rejection on (row, 128-pixel half) items -> private queue
-        // Shared memory is addressed through one precomputed 32-bit base per chunk (LDS with immediate offsets), and the
-        // survivors of an item are compacted with ONE warp prefix: each lane counts its 0..4 passing pixels, the counts'
-        // three bit planes go through three ballots (prefix = popc of the lower lanes' bits, weighted 1 / 2 / 4), and the
-        // lane writes its entries back to back.  (Queue order is free: phase B scores every entry, the NMS works on bits.)
-        int qn = 0;
+        if (DBG == 1) continue;
+        // ---- phase A (per warp): compass rejection on (row, 128-pixel half) items -> private QUAD queue
+        // Shared memory is addressed through one precomputed 32-bit base per chunk (LDS with immediate offsets).  Only about
+        // one pixel in 13 passes, so the per-item bookkeeping is kept to ONE ballot: a lane whose quad has any passing
+        // pixel appends one 16-bit quad entry (sy << 10 | quad column << 4 | 4 pass flags).  The quad queue sits in the
+        // last quarter of the warp's queue region.
+        int qn4 = 0;
+        constexpr int QQ0 = QCAP - ITEMS * 32;               // first slot of the quad queue
         {
             constexpr unsigned K = ((511u - T) << 16) | (511u - T);
-            const unsigned q_s = (unsigned)__cvta_generic_to_shared(myq);
+            const unsigned qq_s = (unsigned)__cvta_generic_to_shared(myq + QQ0);
             // 8-byte aligned: word index (sy+3)*TPW + 2q + 2 + xo/2 is even (TPW, xo/2 even)
             const unsigned lane_s = (unsigned)__cvta_generic_to_shared(s_img) + (unsigned)(3 * TPW + 2 * lane + 2 + (xo >> 1)) * 4u;
             for (int item = wid; item < 2 * nsr; item += NWARP) {
@@ -364,19 +367,59 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
                     m0 = (c.x + K - D0) | (B0 + K - c.x);
                     m1 = (c.y + K - D1) | (B1 + K - c.y);
                 }
-                // pass flags of the quad's four pixels: bits 9 / 25 of m0 and (moved up one) bits 10 / 26 of m1, in one word
+                // pass flags of the quad's four pixels: bits 9 / 25 of m0 and (moved up one) bits 10 / 26 of m1, folded to
+                // a nibble: bit 0 = pixel 0, bit 1 = pixel 2, bit 2 = pixel 1, bit 3 = pixel 3
                 const unsigned pf = (m0 & 0x02000200u) | ((m1 << 1) & 0x04000400u);
-                const unsigned cnt = (unsigned)__popc(pf);   // 0 .. 4
-                const unsigned f0 = pf & 0x200u, f1 = pf & 0x02000000u, f2 = pf & 0x400u, f3 = pf & 0x04000000u;
+                const unsigned nib = ((pf | (pf >> 14)) >> 9) & 15u;
+                const unsigned any = __ballot_sync(0xffffffffu, nib != 0u);
+                if (nib) sts_u16(qq_s + 2u * (unsigned)(qn4 + __popc(any & lt)), (unsigned)(sy << 10) | (unsigned)(q << 4) | nib);
+                qn4 += __popc(any);
+            }
+        }
+        __syncwarp();
+        if (DBG == 2) { if (qn4 == 12345) s_rowcnt[0] = 1; continue; }
+        // ---- phase A2 (same warp): quad entries -> pixel entries (sy << 8 | sx), 32 quad entries at a time.
+        // First the SECOND rejection test, on the quads that survived only: the two diagonal opposite pairs of the circle
+        // ((+-2, +-2): points 2/10 and 6/14) must also hold a darker or a brighter pixel each -- same u16x2 arithmetic as
+        // phase A, from three loads per row +-2.  It roughly halves the pixels that reach the 16-point test, whose 17
+        // scattered 16-bit loads (bank conflicts) are the expensive part.  (The flags of the two tests are ANDed per pixel
+        // without their polarity: still a necessary condition.)
+        // Then each lane counts its 0..4 flagged pixels; the counts' three bit planes go through three ballots (prefix =
+        // popc of the lower lanes' bits, weighted 1 / 2 / 4) and the lane writes its entries back to back.  (Queue order is
+        // free: phase B scores every entry, the NMS works on bits.)  In place: after k quad entries at most
+        // 4k <= 3 * ITEMS * 32 + k pixel slots are written, which never reaches the unread part of the quad queue.
+        int qn = 0;
+        {
+            constexpr unsigned K = ((511u - T) << 16) | (511u - T);
+            const unsigned q_s = (unsigned)__cvta_generic_to_shared(myq);
+            const unsigned img_q = (unsigned)__cvta_generic_to_shared(s_img) + (unsigned)(3 * TPW + 2 + (xo >> 1)) * 4u;   // quad (sy, q) at + (sy * TPW + 2q) * 4
+            for (int i0 = 0; i0 < qn4; i0 += 32) {
+                const int i = i0 + lane;
+                unsigned e = 0;
+                if (i < qn4) {
+                    e = lds_u16(q_s + 2u * (unsigned)(QQ0 + i));
+                    const unsigned ad = img_q + ((e >> 10) * TPW + ((e >> 3) & 0x7Eu)) * 4u;
+                    const unsigned up = ad - 2 * TPW * 4, dn = ad + 2 * TPW * 4;
+                    const uint2 c = lds_v2(ad), u = lds_v2(up), d = lds_v2(dn);
+                    const unsigned um = lds_u32(up - 4), upp = lds_u32(up + 8), dm = lds_u32(dn - 4), dpp = lds_u32(dn + 8);
+                    // pixels 0,1: NW = um, NE = u.y, SW = dm, SE = d.y;   pixels 2,3: NW = u.x, NE = upp, SW = d.x, SE = dpp
+                    const unsigned D0 = vmax2(vmin2(um, d.y), vmin2(u.y, dm)), B0 = vmin2(vmax2(um, d.y), vmax2(u.y, dm));
+                    const unsigned D1 = vmax2(vmin2(u.x, dpp), vmin2(upp, d.x)), B1 = vmin2(vmax2(u.x, dpp), vmax2(upp, d.x));
+                    const unsigned m0 = (c.x + K - D0) | (B0 + K - c.x);
+                    const unsigned m1 = (c.y + K - D1) | (B1 + K - c.y);
+                    const unsigned pf = (m0 & 0x02000200u) | ((m1 << 1) & 0x04000400u);
+                    e &= 0xFFF0u | (((pf | (pf >> 14)) >> 9) & 15u);
+                }
+                const unsigned cnt = (unsigned)__popc(e & 15u);      // 0 .. 4
                 const unsigned c0 = __ballot_sync(0xffffffffu, cnt & 1u), c1 = __ballot_sync(0xffffffffu, cnt & 2u), c2 = __ballot_sync(0xffffffffu, cnt & 4u);
-                unsigned pos = (unsigned)qn + __popc(c0 & lt) + 2u * __popc(c1 & lt) + 4u * __popc(c2 & lt);
+                const unsigned pos = (unsigned)qn + __popc(c0 & lt) + 2u * __popc(c1 & lt) + 4u * __popc(c2 & lt);
                 qn += __popc(c0) + 2 * __popc(c1) + 4 * __popc(c2);
-                const unsigned ent = (unsigned)(sy << 8) | (unsigned)(4 * q);
+                const unsigned ent = (e >> 2) & 0x3FFCu;             // sy << 8 | 4 * quad column
                 unsigned sa = q_s + 2u * pos;
-                if (f0) { sts_u16(sa, ent); sa += 2u; }
-                if (f1) { sts_u16(sa, ent + 1u); sa += 2u; }
-                if (f2) { sts_u16(sa, ent + 2u); sa += 2u; }
-                if (f3) sts_u16(sa, ent + 3u);
+                if (e & 1u) { sts_u16(sa, ent); sa += 2u; }
+                if (e & 4u) { sts_u16(sa, ent + 1u); sa += 2u; }
+                if (e & 2u) { sts_u16(sa, ent + 2u); sa += 2u; }
+                if (e & 8u) sts_u16(sa, ent + 3u);
             }
         }
         __syncwarp();
@@ -426,6 +469,7 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
                 cn += __popc(bc);
             }
         }
+        if (DBG == 3) { if (cn == 12345) s_rowcnt[0] = 1; continue; }
         __syncthreads();                                     // every score of the tile is in place
         // ---- phase C (per warp): 3x3 NMS of its queued corners
         for (int i = lane; i < cn; i += 32) {
@@ -1121,7 +1165,6 @@ __device__ __forceinline__ int dp4a_us(unsigned a_u8x4, unsigned b_s8x4, int c) 
     return d;
 }
 __device__ __forceinline__ unsigned lds_u8(unsigned addr) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
-__device__ __forceinline__ unsigned lds_u32(unsigned addr) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
 
 struct DescKp { int x, y, lvl; float response; };
 
