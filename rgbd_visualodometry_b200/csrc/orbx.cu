@@ -32,7 +32,7 @@ const int8_t k_pattern_host[256 * 4] = {
 
 constexpr int FAST_R = 16, FAST_NT = 256;
 constexpr int MAX_LANES = 4;               // concurrent frame-range pipelines of one device-resident extraction call
-constexpr int HOST_MAX_LANES = 8;          // host-buffer calls: more, shorter ranges shrink the un-overlapped head (first upload) and tail
+constexpr int HOST_MAX_LANES = 12, HOST_DEFAULT_LANES = 8;         // host-buffer calls: more, shorter ranges shrink the un-overlapped head (first upload) and tail
 constexpr int LANE_MIN_FRAMES = 64;        // a lane must still fill the GPU on its own
 constexpr int HOST_LANE_MIN_FRAMES = 16;   // host-buffer batches: lanes mainly overlap PCIe copies with kernels
 constexpr int N_STAGES = 7;
@@ -250,6 +250,17 @@ void stage_mark(orbx_ctx* c, int i)
 }
 
 // The extraction pipeline on device-resident frames; everything asynchronous on c->stream.
+// Frame range of host-buffer lane k.  The ranges taper towards both ends (weights 1, 2, 4, 4, ..., 4, 2, 1): the first
+// upload has nothing to hide under and the last range's kernels + download have nothing left to hide, so both are short.
+static void host_lane_range(int batch, int lanes, int k, int* f0, int* f1)
+{
+    auto wgt = [&](int i) { return 1 << std::min(2, std::min(i, lanes - 1 - i)); };
+    long tot = 0, before = 0;
+    for (int i = 0; i < lanes; ++i) { tot += wgt(i); if (i < k) before += wgt(i); }
+    *f0 = (int)((long)batch * before / tot);
+    *f1 = (int)((long)batch * (before + wgt(k)) / tot);
+}
+
 // The kernel sequence for frames [f0, f0 + nb) on stream `st`.  Every buffer is frame-major, so a frame range is
 // just a base-pointer offset.
 int run_extract_range(orbx_ctx* c, cudaStream_t st, bool marks, int f0, int nb,
@@ -425,7 +436,7 @@ int run_match(orbx_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int n
     int* keys = nullptr;
     const size_t nout = (size_t)nq * nsets;
     int rc;
-    if ((rc = ensure(c, c->mstatus, sizeof(int) * 8))) return rc;
+    if ((rc = ensure(c, c->mstatus, sizeof(int) * 16))) return rc;
     int* d_status = (int*)c->mstatus.p + slot;
     CU(cudaMemsetAsync(d_status, 0, sizeof(int), st));
     if (!lane_call) stage_mark(c, 7);
@@ -605,7 +616,7 @@ int orbx_detect_and_compute_batch(orbx_ctx* c, const uint8_t* const* imgs, int b
     for (int i = 0; i < batch; ++i) if (!imgs[i]) return fail(c, ORBX_E_ARG, "null frame pointer");
     if ((rc = set_geometry(c, w, h))) return rc;
     CU(cudaMemsetAsync(c->status.p, 0, sizeof(int) * (size_t)batch, c->stream));
-    static const int host_lanes_max = std::max(1, std::min(HOST_MAX_LANES, getenv("ORBX_HOST_LANES") ? atoi(getenv("ORBX_HOST_LANES")) : HOST_MAX_LANES));
+    static const int host_lanes_max = std::max(1, std::min(HOST_MAX_LANES, getenv("ORBX_HOST_LANES") ? atoi(getenv("ORBX_HOST_LANES")) : HOST_DEFAULT_LANES));
     int* h_counts = c->h_small;
     int* h_status = c->h_small + batch;
     // Frame ranges ("lanes") on their own streams: upload -> kernels -> download per lane, so the H2D copy of lane k+1
@@ -613,7 +624,8 @@ int orbx_detect_and_compute_batch(orbx_ctx* c, const uint8_t* const* imgs, int b
     const int lanes = c->profiling ? 1 : std::max(1, std::min(host_lanes_max, batch / HOST_LANE_MIN_FRAMES));
     if (lanes > 1) CU(cudaEventRecord(c->ev_fork, c->stream));
     for (int k = 0; k < lanes; ++k) {
-        const int f0 = (int)((long)batch * k / lanes), f1 = (int)((long)batch * (k + 1) / lanes);
+        int f0, f1;
+        host_lane_range(batch, lanes, k, &f0, &f1);
         cudaStream_t st = k == 0 ? c->stream : c->lane[k];
         if (k > 0) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
         if ((rc = upload_frames(c, st, imgs, f0, f1, step, row, h, dstep, fstride))) return rc;
@@ -670,7 +682,7 @@ int orbx_extract_match_batch(orbx_ctx* c, const uint8_t* const* imgs, int batch,
     if ((rc = ensure(c, c->in, fstride * batch)) || (rc = ensure(c, c->kps, sizeof(orbx_keypoint) * (size_t)cap * batch)) ||
         (rc = ensure(c, c->desc, (size_t)32 * cap * batch)) || (rc = ensure(c, c->counts, sizeof(int) * (size_t)batch)) ||
         (rc = ensure(c, c->mq, std::max<size_t>(qrows, 1) * 32)) || (rc = ensure(c, c->mbest, std::max<size_t>(mrows, 1) * 16)) ||
-        (rc = ensure(c, c->mstatus, sizeof(int) * 8)))
+        (rc = ensure(c, c->mstatus, sizeof(int) * 16)))
         return rc;
     for (int i = 0; i < batch; ++i) if (!imgs[i]) return fail(c, ORBX_E_ARG, "null frame pointer");
     if ((rc = set_geometry(c, w, h))) return rc;
@@ -682,14 +694,15 @@ int orbx_extract_match_batch(orbx_ctx* c, const uint8_t* const* imgs, int batch,
             off += (size_t)nq[j];
         }
     }
-    static const int host_lanes_max = std::max(1, std::min(HOST_MAX_LANES, getenv("ORBX_HOST_LANES") ? atoi(getenv("ORBX_HOST_LANES")) : HOST_MAX_LANES));
+    static const int host_lanes_max = std::max(1, std::min(HOST_MAX_LANES, getenv("ORBX_HOST_LANES") ? atoi(getenv("ORBX_HOST_LANES")) : HOST_DEFAULT_LANES));
     int* h_counts = c->h_small;
     int* h_status = c->h_small + batch;
     int* h_mstatus = c->h_small + 2 * batch;
     const int lanes = c->profiling ? 1 : std::max(1, std::min(host_lanes_max, batch / HOST_LANE_MIN_FRAMES));
     CU(cudaEventRecord(c->ev_fork, c->stream));
     for (int k = 0; k < lanes; ++k) {
-        const int f0 = (int)((long)batch * k / lanes), f1 = (int)((long)batch * (k + 1) / lanes);
+        int f0, f1;
+        host_lane_range(batch, lanes, k, &f0, &f1);
         const size_t n = (size_t)(f1 - f0);
         cudaStream_t st = k == 0 ? c->stream : c->lane[k];
         if (k > 0) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
