@@ -19,6 +19,7 @@
 #include "orbx_geom.h"
 #include "orbx_kernels.cuh"
 #include "orbx_match.cuh"
+#include "orbx_match2.cuh"
 #include "orbx_map.cuh"
 #include <unordered_map>
 
@@ -397,6 +398,14 @@ int check_args_extract(orbx_ctx* c, int batch, int w, int h, int channels, int c
     return ORBX_OK;
 }
 
+// A matcher status word was found set (an mbarrier wait timed out on the device): clear all of them, so that the next
+// call starts clean without a per-call memset on the matcher's critical path, and report.
+int match_timed_out(orbx_ctx* c)
+{
+    cudaMemset(c->mstatus.p, 0, sizeof(int) * 16);
+    return fail(c, ORBX_E_INTERNAL, "matcher pipeline timed out on an mbarrier (device status set)");
+}
+
 // The matcher on device-resident operands, asynchronous on `st` (default: the context's stream).  `slot` selects the
 // status word (one per lane, so concurrent lanes never reset each other's); lanes never take the split-train path,
 // whose key scratch is shared.
@@ -407,7 +416,13 @@ int run_match(orbx_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int n
     if (!st) st = c->stream;
     if (nt >= MT_MAX_TRAIN) return fail(c, ORBX_E_UNSUPPORTED, "train set larger than 2^20 - 1 rows");
     const bool knn2 = d_second != nullptr;
-    const int tiles_m = (nq + MT_QROWS - 1) / MT_QROWS;
+    // CTA-pair kernel (tcgen05 cta_group::2, query tiles in twos) whenever the (query tile, set) pairs alone fill the GPU;
+    // small problems keep the single-CTA kernel, whose CTAs are independent units for the train-row split.
+    // ORBX_MATCH_2CTA = 0 / 1 forces one of them (experiments).
+    static const int pair_env = getenv("ORBX_MATCH_2CTA") ? atoi(getenv("ORBX_MATCH_2CTA")) : -1;
+    const int tiles_1 = (nq + MT_QROWS - 1) / MT_QROWS, tiles_2 = (tiles_1 + 1) & ~1;
+    const bool pair = pair_env >= 0 ? pair_env != 0 : (tiles_1 >= 2 && (long)tiles_2 * nsets >= 148);
+    const int tiles_m = pair ? tiles_2 : tiles_1;
     const int ntile_n = (nt + MT_BN - 1) / MT_BN;
     constexpr int kSMs = 148;                                // one CTA per SM (163 KB of shared memory each)
     // Few (query tile, set) pairs: split the train rows across CTAs and merge with atomicMax on the packed key.
@@ -437,8 +452,7 @@ int run_match(orbx_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int n
     const size_t nout = (size_t)nq * nsets;
     int rc;
     if ((rc = ensure(c, c->mstatus, sizeof(int) * 16))) return rc;
-    int* d_status = (int*)c->mstatus.p + slot;
-    CU(cudaMemsetAsync(d_status, 0, sizeof(int), st));
+    int* d_status = (int*)c->mstatus.p + slot;               // zero since orbx_create; re-zeroed by match_timed_out() after a failure
     if (!lane_call) stage_mark(c, 7);
     if (nsplit > 1) {
         if ((rc = ensure(c, c->mkeys, nout * sizeof(int)))) return rc;
@@ -449,7 +463,9 @@ int run_match(orbx_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int n
     const dim3 grd((unsigned)tiles_m, (unsigned)nsplit, (unsigned)zgroups);
     if (getenv("ORBX_MATCH_TRACE") && !c->mtrace.p) { if ((rc = ensure(c, c->mtrace, 16 * 16 * 8))) return rc; cudaMemset(c->mtrace.p, 0, 16 * 16 * 8); }
     static const int dbg = getenv("ORBX_MATCH_DBG") ? atoi(getenv("ORBX_MATCH_DBG")) : 0;   // perf experiments only: skips a role's work (wrong results)
-    if (knn2) k_hamming_umma<true><<<grd, MT_THREADS, MT_SMEM_BYTES, st>>>(d_q, nq, d_t, nt, stride_rows, d_counts, nsets, rows_per_split, d_best, d_second, keys, d_status, dbg, (long long*)c->mtrace.p);
+    if (pair && knn2) k_hamming_umma2<true><<<grd, MT_THREADS, MT_SMEM_BYTES, st>>>(d_q, nq, d_t, nt, stride_rows, d_counts, nsets, rows_per_split, d_best, d_second, keys, d_status, dbg, (long long*)c->mtrace.p);
+    else if (pair) k_hamming_umma2<false><<<grd, MT_THREADS, MT_SMEM_BYTES, st>>>(d_q, nq, d_t, nt, stride_rows, d_counts, nsets, rows_per_split, d_best, d_second, keys, d_status, dbg, (long long*)c->mtrace.p);
+    else if (knn2) k_hamming_umma<true><<<grd, MT_THREADS, MT_SMEM_BYTES, st>>>(d_q, nq, d_t, nt, stride_rows, d_counts, nsets, rows_per_split, d_best, d_second, keys, d_status, dbg, (long long*)c->mtrace.p);
     else      k_hamming_umma<false><<<grd, MT_THREADS, MT_SMEM_BYTES, st>>>(d_q, nq, d_t, nt, stride_rows, d_counts, nsets, rows_per_split, d_best, d_second, keys, d_status, dbg, (long long*)c->mtrace.p);
     ++c->launches;
     if (nsplit > 1) {
@@ -485,7 +501,7 @@ int match_host(orbx_ctx* c, const uint8_t* query, int nq, const uint8_t* train, 
     }
     CU(cudaMemcpyAsync(c->h_small, c->mstatus.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if (c->h_small[0]) return fail(c, ORBX_E_INTERNAL, "matcher pipeline timed out on an mbarrier (device status set)");
+    if (c->h_small[0]) return match_timed_out(c);
     if (n_out) *n_out = nq;
     return ORBX_OK;
 }
@@ -526,8 +542,9 @@ int orbx_create(orbx_ctx** out, int device, int nfeatures, float scale_factor, i
     if (ensure(c, c->pyr, g.pyr_frame * B + (size_t)(96 + 8) * g.L[0].pitch) ||   // + slack: the blur streams up to ~100 rows past a level's end (masked outputs)
         ensure(c, c->blur, g.pyr_frame * B) || ensure(c, c->rowcnt, g.cnt_frame * 4 * B) || ensure(c, c->rowent, g.ent_frame * 4 * B) ||
         ensure(c, c->work, g.ws_frame * sizeof(Elem) * B) || ensure(c, c->selpos, g.ws_frame * 8 * B) || ensure(c, c->fincnt, sizeof(int) * ORBX_LEVELS_MAX * B) ||
-        ensure(c, c->status, sizeof(int) * B) || ensure(c, c->pattern, sizeof(float) * 1024))
+        ensure(c, c->status, sizeof(int) * B) || ensure(c, c->pattern, sizeof(float) * 1024) || ensure(c, c->mstatus, sizeof(int) * 16))
         return bail(ORBX_E_NOMEM);
+    if (cudaMemset(c->mstatus.p, 0, sizeof(int) * 16) != cudaSuccess) return bail(ORBX_E_CUDA);
     {
         float pat[1024];                                     // the rBRIEF pattern as float4 (x0, y0, x1, y1) per test,
         for (int t = 0; t < 8; ++t)                          // transposed to [t][lane]: test lane * 8 + t  (k_describe)
@@ -537,7 +554,9 @@ int orbx_create(orbx_ctx** out, int device, int nfeatures, float scale_factor, i
     }
     if (cudaMemset(c->status.p, 0, sizeof(int) * B) != cudaSuccess) return bail(ORBX_E_CUDA);
     if (cudaMallocHost((void**)&c->h_small, sizeof(int) * (2 * B + 16)) != cudaSuccess) return bail(ORBX_E_NOMEM);
-    if (cudaFuncSetAttribute(k_hamming_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES) != cudaSuccess ||
+    if (cudaFuncSetAttribute(k_hamming_umma2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_hamming_umma2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_hamming_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(k_hamming_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES) != cudaSuccess)
         return bail(ORBX_E_CUDA);
     *out = c;
@@ -735,7 +754,7 @@ int orbx_extract_match_batch(orbx_ctx* c, const uint8_t* const* imgs, int batch,
     c->view_desc = (const uint8_t*)c->desc.p; c->view_counts = (const int*)c->counts.p; c->view_frames = batch;
     if (c->profiling) for (int i = 0; i < 6; ++i) c->stage_valid[i] = true;
     CU(cudaStreamSynchronize(c->stream));
-    for (int k = 0; k < lanes; ++k) if (nmaps > 0 && h_mstatus[k]) return fail(c, ORBX_E_INTERNAL, "matcher pipeline timed out on an mbarrier (device status set)");
+    for (int k = 0; k < lanes; ++k) if (nmaps > 0 && h_mstatus[k]) return match_timed_out(c);
     bool over = false;
     for (int i = 0; i < batch; ++i) {
         if (h_status[i]) return fail(c, ORBX_E_INTERNAL, "device-side status set for a frame");
@@ -811,7 +830,7 @@ int orbx_match_hamming_sets(orbx_ctx* c, const uint8_t* query, int nq, const uin
     if (second) CU(cudaMemcpyAsync(second, c->msecond.p, obytes, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(c->h_small, c->mstatus.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if (c->h_small[0]) return fail(c, ORBX_E_INTERNAL, "matcher pipeline timed out on an mbarrier (device status set)");
+    if (c->h_small[0]) return match_timed_out(c);
     return ORBX_OK;
 }
 
@@ -1141,7 +1160,7 @@ int orbx_track_match(orbx_ctx* c, const int64_t* ids, int m, const double* pose_
     CU(cudaMemcpyAsync(h + 1, c->t_minmax.p, 2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(h + 3, c->mstatus.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    if (h[3]) return fail(c, ORBX_E_INTERNAL, "matcher pipeline timed out on an mbarrier (device status set)");
+    if (h[3]) return match_timed_out(c);
     const int nm = h[0];
     if (nm > 0) CU(cudaMemcpy(matches, c->t_filtered.p, (size_t)nm * 16, cudaMemcpyDeviceToHost));
     *n_matches = nm;
