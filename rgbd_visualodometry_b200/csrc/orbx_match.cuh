@@ -134,6 +134,25 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
                    "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                  : "r"(taddr) : "memory");
 }
+// .pack::16b: two adjacent 32-bit columns -> the low halves of both in one register (the accumulators fit in 16 bits);
+// .xN counts destination registers, so N registers cover 2N columns
+__device__ __forceinline__ void tc_ld32_pack16(uint32_t taddr, uint32_t* r) {     // 64 columns -> 32 registers
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld16_pack16(uint32_t taddr, uint32_t* r) {     // 32 columns -> 16 registers
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version 1 at bit 46, layout 2 at bit 61);
@@ -421,8 +440,32 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
                 constexpr int NCH = MT_BN / 32;
                 uint32_t r[NCH][32];
                 if (!(dbg & 1)) {
+                    const uint32_t tacc = tmem_base + lane_base + (uint32_t)((b * 2 + a) * MT_BN);
+                    int k1 = INT_MIN, k2 = INT_MIN;
+                    if (!KNN2 && full) {
+                        // accumulator = 127 * dot + code lies in [-32512, 32607]: it fits in 16 bits, so the tile comes out of
+                        // tensor memory packed two columns per register (half the registers, half the max operations), and every
+                        // value of a row is distinct (distinct codes), so the packed maximum loses nothing
+                        uint32_t rp[MT_BN / 2];
+                        tc_ld32_pack16(tacc, rp);
+                        tc_ld16_pack16(tacc + 64, rp + 32);
+                        tc_wait_ld();
+                        if (tr_on) trace[(t - 40) * 16 + 6] = clock64();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8 * b);           // TMEM buffer back to the issuer BEFORE the reduction
+                        unsigned p[8];                           // eight independent max chains (ILP), then a short tree
 #pragma unroll
-                    for (int ch = 0; ch < NCH; ++ch) tc_ld32(tmem_base + lane_base + (uint32_t)((b * 2 + a) * MT_BN + ch * 32), r[ch]);
+                        for (int u = 0; u < 8; ++u) {
+                            p[u] = __vimax3_s16x2(rp[u], rp[8 + u], rp[16 + u]);
+                            p[u] = __vimax3_s16x2(p[u], rp[24 + u], rp[32 + u]);
+                            p[u] = __vmaxs2(p[u], rp[40 + u]);
+                        }
+                        const unsigned pk = __vimax3_s16x2(__vimax3_s16x2(p[0], p[1], p[2]), __vimax3_s16x2(p[3], p[4], p[5]), __vmaxs2(p[6], p[7]));
+                        k1 = max((int)(pk << 16) >> 16, (int)pk >> 16);
+                    } else {
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch) tc_ld32(tacc + (uint32_t)(ch * 32), r[ch]);
                     tc_wait_ld();
                     if (tr_on) trace[(t - 40) * 16 + 6] = clock64();
                     // The accumulators now live in registers: hand the TMEM buffer back to the issuer BEFORE the max
@@ -430,21 +473,7 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
-                    // accumulator = 127 * dot + (MT_BN-1 - jl): the raw integer maximum is (largest dot, lowest index)
-                    int k1 = INT_MIN, k2 = INT_MIN;
-                    if (!KNN2 && full) {
-                        int p[8];                                // eight independent max chains (ILP), then a short tree
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) p[u] = __vimax3_s32((int)r[0][u * 4], (int)r[0][u * 4 + 1], max((int)r[0][u * 4 + 2], (int)r[0][u * 4 + 3]));
-#pragma unroll
-                        for (int ch = 1; ch < NCH; ++ch)
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                p[u] = __vimax3_s32(p[u], (int)r[ch][u * 4], (int)r[ch][u * 4 + 1]);
-                                p[u] = __vimax3_s32(p[u], (int)r[ch][u * 4 + 2], (int)r[ch][u * 4 + 3]);
-                            }
-                        k1 = __vimax3_s32(__vimax3_s32(p[0], p[1], p[2]), __vimax3_s32(p[3], p[4], p[5]), max(p[6], p[7]));
-                    } else if (!KNN2) {
+                    if (!KNN2) {
                         // a set's partial last tile: whole valid 32-column chunks as above, the boundary chunk masked with
                         // warp-uniform selects, chunks beyond skipped (the generic per-column loop below made every set
                         // boundary a ~1500-cycle bubble in the pipeline)
@@ -482,6 +511,7 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
                                     if (KNN2) k2 = max(k2, min(k1, k));
                                     k1 = max(k1, k);
                                 }
+                    }
                     }
                     // decode the tile winner(s) into the global key  dot << 20 | (0xFFFFF - j)
 #pragma unroll

@@ -269,8 +269,32 @@ k_hamming_umma2(const uint8_t* __restrict__ query, int nq, const uint8_t* __rest
                 constexpr int NCH = MT_BN / 32;
                 uint32_t r[NCH][32];
                 if (!(dbg & 1)) {
+                    const uint32_t tacc = tmem_base + lane_base + (uint32_t)((b * 2 + a) * MT_BN);
+                    int k1 = INT_MIN, k2 = INT_MIN;
+                    if (!KNN2 && full) {
+                        // accumulator = 127 * dot + code lies in [-32512, 32607]: it fits in 16 bits, so the tile comes out of
+                        // tensor memory packed two columns per register (half the registers, half the max operations), and every
+                        // value of a row is distinct (distinct codes), so the packed maximum loses nothing
+                        uint32_t rp[MT_BN / 2];
+                        tc_ld32_pack16(tacc, rp);
+                        tc_ld16_pack16(tacc + 64, rp + 32);
+                        tc_wait_ld();
+                        if (tr_on) trace[(t - 40) * 16 + 6] = clock64();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * b);           // TMEM buffer back to the issuer BEFORE the reduction
+                        unsigned p[8];                           // eight independent max chains (ILP), then a short tree
 #pragma unroll
-                    for (int ch = 0; ch < NCH; ++ch) tc_ld32(tmem_base + lane_base + (uint32_t)((b * 2 + a) * MT_BN + ch * 32), r[ch]);
+                        for (int u = 0; u < 8; ++u) {
+                            p[u] = __vimax3_s16x2(rp[u], rp[8 + u], rp[16 + u]);
+                            p[u] = __vimax3_s16x2(p[u], rp[24 + u], rp[32 + u]);
+                            p[u] = __vmaxs2(p[u], rp[40 + u]);
+                        }
+                        const unsigned pk = __vimax3_s16x2(__vimax3_s16x2(p[0], p[1], p[2]), __vimax3_s16x2(p[3], p[4], p[5]), __vmaxs2(p[6], p[7]));
+                        k1 = max((int)(pk << 16) >> 16, (int)pk >> 16);
+                    } else {
+#pragma unroll
+                    for (int ch = 0; ch < NCH; ++ch) tc_ld32(tacc + (uint32_t)(ch * 32), r[ch]);
                     tc_wait_ld();
                     if (tr_on) trace[(t - 40) * 16 + 6] = clock64();
                     // The accumulators now live in registers: hand the TMEM buffer back to the issuer BEFORE the max
@@ -278,21 +302,7 @@ k_hamming_umma2(const uint8_t* __restrict__ query, int nq, const uint8_t* __rest
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * b);
-                    // accumulator = 127 * dot + (MT_BN-1 - jl): the raw integer maximum is (largest dot, lowest index)
-                    int k1 = INT_MIN, k2 = INT_MIN;
-                    if (!KNN2 && full) {
-                        int p[8];                                // eight independent max chains (ILP), then a short tree
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) p[u] = __vimax3_s32((int)r[0][u * 4], (int)r[0][u * 4 + 1], max((int)r[0][u * 4 + 2], (int)r[0][u * 4 + 3]));
-#pragma unroll
-                        for (int ch = 1; ch < NCH; ++ch)
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                p[u] = __vimax3_s32(p[u], (int)r[ch][u * 4], (int)r[ch][u * 4 + 1]);
-                                p[u] = __vimax3_s32(p[u], (int)r[ch][u * 4 + 2], (int)r[ch][u * 4 + 3]);
-                            }
-                        k1 = __vimax3_s32(__vimax3_s32(p[0], p[1], p[2]), __vimax3_s32(p[3], p[4], p[5]), max(p[6], p[7]));
-                    } else if (!KNN2) {
+                    if (!KNN2) {
                         // a set's partial last tile: whole valid 32-column chunks as above, the boundary chunk masked with
                         // warp-uniform selects, chunks beyond skipped (the generic per-column loop below made every set
                         // boundary a ~1500-cycle bubble in the pipeline)
@@ -330,6 +340,7 @@ k_hamming_umma2(const uint8_t* __restrict__ query, int nq, const uint8_t* __rest
                                     if (KNN2) k2 = max(k2, min(k1, k));
                                     k1 = max(k1, k);
                                 }
+                    }
                     }
                     // decode the tile winner(s) into the global key  dot << 20 | (0xFFFFF - j)
 #pragma unroll
