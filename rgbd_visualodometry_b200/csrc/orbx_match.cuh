@@ -209,14 +209,27 @@ __device__ __forceinline__ void expand_half_row(uint8_t* tile, int rows, int r, 
 // ONCE and then walks sets z, z + gridDim.z, ... with all three pipelines running continuously across set
 // boundaries (the map is shared by every frame, so the A operand never has to be rebuilt).
 struct MatchSetRange { int n0, n1, ntiles; };
-__device__ __forceinline__ MatchSetRange match_set_range(const int* __restrict__ counts, int set, int nt, int split, int rows_per_split)
+// rows present in a set (ragged sets: the raw count, clamped later) -- split from the range arithmetic so that a caller can
+// issue the load a whole set ahead and only consume it at the next set boundary
+__device__ __forceinline__ int match_set_count(const int* __restrict__ counts, int set, int nt)
 {
-    const int nvalid = counts ? max(0, min(__ldg(counts + set), nt)) : nt;               // ragged sets: rows actually present
+    if (!counts) return nt;
+    int v;                                                   // volatile: issued HERE, not sunk to the point of use
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(counts + set));
+    return v;
+}
+__device__ __forceinline__ MatchSetRange match_set_range_n(int count, int nt, int split, int rows_per_split)
+{
+    const int nvalid = max(0, min(count, nt));
     MatchSetRange r;
     r.n0 = split * rows_per_split;
     r.n1 = min(nvalid, r.n0 + rows_per_split);
     r.ntiles = r.n1 > r.n0 ? (r.n1 - r.n0 + MT_BN - 1) / MT_BN : 0;
     return r;
+}
+__device__ __forceinline__ MatchSetRange match_set_range(const int* __restrict__ counts, int set, int nt, int split, int rows_per_split)
+{
+    return match_set_range_n(match_set_count(counts, set, nt), nt, split, rows_per_split);
 }
 
 template <bool KNN2>
@@ -305,8 +318,11 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
         auto fetch = [&](int slot) {                         // raw row of the tile `ahead` names -> ring slot (own row only)
             uint8_t* dst = raw + slot * (MT_BN * 32);
             if (ahead.set < nsets) {
-                const int j = ahead.rg.n0 + ahead.i * MT_BN + r;
-                if (j < ahead.rg.n1) {
+                // rows past the set's end (partial last tile) repeat the set's LAST row: a copy scores like the original but
+                // carries a smaller index code, so it can never win -- and the epilogue needs no per-column masking
+                const int j0t = ahead.rg.n0 + ahead.i * MT_BN;
+                const int j = min(j0t + r, ahead.rg.n1 - 1);
+                if (r < ((min(MT_BN, ahead.rg.n1 - j0t) + 31) & ~31)) {
                     const uint8_t* src = train + ((size_t)ahead.set * train_stride_rows + j) * 32;
                     const uint32_t d = smem_u32(dst);
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
@@ -362,10 +378,10 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
         bool ready_next = false;                             // barriers of tile t already observed complete (probed mid-tile)
         // (the row count of the NEXT set is loaded a whole set ahead: its global-load latency would otherwise stall the
         //  pipeline at every set boundary)
-        MatchSetRange rg_next = match_set_range(train_counts, min((int)blockIdx.z, nsets - 1), nt, split, rows_per_split);
+        int cnt_next = match_set_count(train_counts, min((int)blockIdx.z, nsets - 1), nt);
         for (int set = blockIdx.z; set < nsets && ok; set += gridDim.z) {
-            const MatchSetRange rg = rg_next;
-            if (set + (int)gridDim.z < nsets) rg_next = match_set_range(train_counts, set + (int)gridDim.z, nt, split, rows_per_split);
+            const MatchSetRange rg = match_set_range_n(cnt_next, nt, split, rows_per_split);
+            if (set + (int)gridDim.z < nsets) cnt_next = match_set_count(train_counts, set + (int)gridDim.z, nt);   // consumed at the next set boundary
             for (int i = 0; i < rg.ntiles; ++i, ++t) {
                 if ((t & 1) != issuer) continue;              // the other issuer's tile
                 const int s = t % MT_STAGES;
@@ -384,10 +400,10 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
                 const uint32_t sb = sbu + MT_SMEM_B + s * MT_B_BYTES;
                 const uint64_t db0 = umma_desc_sw128(sb);
                 // A set's last tile usually holds fewer than MT_BN rows: issue it with the smallest UMMA N (multiple of 16)
-                // that covers them -- tensor time is proportional to N.  Columns beyond keep stale values the epilogue
+                // that covers them -- tensor time is proportional to N.  (Multiples of 32: the epilogue reads 32-column chunks.)  Columns beyond keep stale values the epilogue
                 // never reads (it bounds partial tiles by the row count).
                 const int rows_here = min(MT_BN, rg.n1 - (rg.n0 + i * MT_BN));
-                const uint32_t idesc = (MT_IDESC & ~(0x3Fu << 17)) | ((uint32_t)(((rows_here + 15) & ~15) >> 3) << 17);
+                const uint32_t idesc = (MT_IDESC & ~(0x3Fu << 17)) | ((uint32_t)(((rows_here + 31) & ~31) >> 3) << 17);
                 // barriers of this issuer's NEXT tile, t + 2 (same pipelines, consecutive tile numbers even across set boundaries)
                 const int s1 = (t + 2) % MT_STAGES, b1 = b;
                 const uint32_t ph1 = (uint32_t)((t + 2) / MT_STAGES) & 1u, bph1 = (uint32_t)((t + 2) >> 1) & 1u;
@@ -422,10 +438,10 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
         const int qrow = q0 + a * 128 + (warp & 3) * 32 + lane;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         int t = 0;
-        MatchSetRange rg_next = match_set_range(train_counts, min((int)blockIdx.z, nsets - 1), nt, split, rows_per_split);
+        int cnt_next = match_set_count(train_counts, min((int)blockIdx.z, nsets - 1), nt);
         for (int set = blockIdx.z; set < nsets && ok; set += gridDim.z) {
-            const MatchSetRange rg = rg_next;                // (next set's row count loaded a set ahead, as in the issuer)
-            if (set + (int)gridDim.z < nsets) rg_next = match_set_range(train_counts, set + (int)gridDim.z, nt, split, rows_per_split);
+            const MatchSetRange rg = match_set_range_n(cnt_next, nt, split, rows_per_split);   // (next set's row count loaded a set ahead, as in the issuer)
+            if (set + (int)gridDim.z < nsets) cnt_next = match_set_count(train_counts, set + (int)gridDim.z, nt);
             int m1 = INT_MIN, m2 = INT_MIN;
             for (int i = 0; i < rg.ntiles; ++i, ++t) {
                 const int b = t & 1;
@@ -463,6 +479,33 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
                         }
                         const unsigned pk = __vimax3_s16x2(__vimax3_s16x2(p[0], p[1], p[2]), __vimax3_s16x2(p[3], p[4], p[5]), __vmaxs2(p[6], p[7]));
                         k1 = max((int)(pk << 16) >> 16, (int)pk >> 16);
+                    } else if (!KNN2) {
+                        // a set's partial last tile was issued with N = 32, 64 (or 96) columns, its rows past the set's end are
+                        // copies of the last row (never the maximum): same packed path, 32-column chunks as far as N goes
+                        const int nch = (rg.n1 - j0 + 31) >> 5;
+                        uint32_t rp[MT_BN / 2];
+#pragma unroll
+                        for (int ch = 0; ch < NCH; ++ch) {
+                            if (ch < nch) tc_ld16_pack16(tacc + (uint32_t)(ch * 32), rp + ch * 16);
+                            else {
+#pragma unroll
+                                for (int u = 0; u < 16; ++u) rp[ch * 16 + u] = 0x80008000u;
+                            }
+                        }
+                        tc_wait_ld();
+                        if (tr_on) trace[(t - 40) * 16 + 6] = clock64();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+                        unsigned p[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            p[u] = __vimax3_s16x2(rp[u], rp[8 + u], rp[16 + u]);
+                            p[u] = __vimax3_s16x2(p[u], rp[24 + u], rp[32 + u]);
+                            p[u] = __vmaxs2(p[u], rp[40 + u]);
+                        }
+                        const unsigned pk = __vimax3_s16x2(__vimax3_s16x2(p[0], p[1], p[2]), __vimax3_s16x2(p[3], p[4], p[5]), __vmaxs2(p[6], p[7]));
+                        k1 = max((int)(pk << 16) >> 16, (int)pk >> 16);
                     } else {
 #pragma unroll
                     for (int ch = 0; ch < NCH; ++ch) tc_ld32(tacc + (uint32_t)(ch * 32), r[ch]);
@@ -473,35 +516,6 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
-                    if (!KNN2) {
-                        // a set's partial last tile: whole valid 32-column chunks as above, the boundary chunk masked with
-                        // warp-uniform selects, chunks beyond skipped (the generic per-column loop below made every set
-                        // boundary a ~1500-cycle bubble in the pipeline)
-                        const int nv = rg.n1 - j0;
-                        int p[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) p[u] = INT_MIN;
-#pragma unroll
-                        for (int ch = 0; ch < NCH; ++ch) {
-                            const int nvc = nv - ch * 32;
-                            if (nvc >= 32) {
-#pragma unroll
-                                for (int u = 0; u < 8; ++u) {
-                                    p[u] = __vimax3_s32(p[u], (int)r[ch][u * 4], (int)r[ch][u * 4 + 1]);
-                                    p[u] = __vimax3_s32(p[u], (int)r[ch][u * 4 + 2], (int)r[ch][u * 4 + 3]);
-                                }
-                            } else if (nvc > 0) {
-#pragma unroll
-                                for (int u = 0; u < 8; ++u) {
-                                    const int v0 = u * 4 < nvc ? (int)r[ch][u * 4] : INT_MIN, v1 = u * 4 + 1 < nvc ? (int)r[ch][u * 4 + 1] : INT_MIN;
-                                    const int v2 = u * 4 + 2 < nvc ? (int)r[ch][u * 4 + 2] : INT_MIN, v3 = u * 4 + 3 < nvc ? (int)r[ch][u * 4 + 3] : INT_MIN;
-                                    p[u] = __vimax3_s32(p[u], v0, v1);
-                                    p[u] = __vimax3_s32(p[u], v2, v3);
-                                }
-                            }
-                        }
-                        k1 = __vimax3_s32(__vimax3_s32(p[0], p[1], p[2]), __vimax3_s32(p[3], p[4], p[5]), max(p[6], p[7]));
-                    } else {
 #pragma unroll
                         for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
@@ -511,7 +525,6 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
                                     if (KNN2) k2 = max(k2, min(k1, k));
                                     k1 = max(k1, k);
                                 }
-                    }
                     }
                     // decode the tile winner(s) into the global key  dot << 20 | (0xFFFFF - j)
 #pragma unroll

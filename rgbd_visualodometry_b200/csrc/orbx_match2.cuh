@@ -136,9 +136,11 @@ k_hamming_umma2(const uint8_t* __restrict__ query, int nq, const uint8_t* __rest
             uint8_t* dst = raw + slot * (MT_BN * 16);
             if (ahead.set < nsets) {
                 const int j0t = ahead.rg.n0 + ahead.i * MT_BN;
-                const int nh = ((min(MT_BN, ahead.rg.n1 - j0t) + 15) & ~15) >> 1;    // rows per CTA of this tile (UMMA N / 2)
-                const int j = j0t + (int)rank * nh + r;
-                if (r < nh && j < ahead.rg.n1) {
+                const int nh = ((min(MT_BN, ahead.rg.n1 - j0t) + 31) & ~31) >> 1;    // rows per CTA of this tile (UMMA N / 2)
+                // rows past the set's end repeat the set's LAST row: a copy scores like the original but carries a smaller
+                // index code, so it can never win -- and the epilogue needs no per-column masking
+                const int j = min(j0t + (int)rank * nh + r, ahead.rg.n1 - 1);
+                if (r < nh) {
                     const uint8_t* src = train + ((size_t)ahead.set * train_stride_rows + j) * 32 + hk * 16;
                     const uint32_t d = smem_u32(dst);
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
@@ -191,10 +193,10 @@ k_hamming_umma2(const uint8_t* __restrict__ query, int nq, const uint8_t* __rest
         bool ready_next = false;                             // barriers of tile t already observed complete (probed mid-tile)
         // (the row count of the NEXT set is loaded a whole set ahead: its global-load latency would otherwise stall the
         //  pipeline at every set boundary)
-        MatchSetRange rg_next = match_set_range(train_counts, min((int)blockIdx.z, nsets - 1), nt, split, rows_per_split);
+        int cnt_next = match_set_count(train_counts, min((int)blockIdx.z, nsets - 1), nt);
         for (int set = blockIdx.z; set < nsets && ok; set += gridDim.z) {
-            const MatchSetRange rg = rg_next;
-            if (set + (int)gridDim.z < nsets) rg_next = match_set_range(train_counts, set + (int)gridDim.z, nt, split, rows_per_split);
+            const MatchSetRange rg = match_set_range_n(cnt_next, nt, split, rows_per_split);
+            if (set + (int)gridDim.z < nsets) cnt_next = match_set_count(train_counts, set + (int)gridDim.z, nt);   // consumed at the next set boundary
             for (int i = 0; i < rg.ntiles; ++i, ++t) {
                 if ((t & 1) != issuer) continue;              // the other issuer's tile
                 const int s = t % MT_STAGES;
@@ -216,7 +218,7 @@ k_hamming_umma2(const uint8_t* __restrict__ query, int nq, const uint8_t* __rest
                 // that covers them -- tensor time is proportional to N.  Columns beyond keep stale values the epilogue
                 // never reads (it bounds partial tiles by the row count).
                 const int rows_here = min(MT_BN, rg.n1 - (rg.n0 + i * MT_BN));
-                const uint32_t idesc = (MT2_IDESC & ~(0x3Fu << 17)) | ((uint32_t)(((rows_here + 15) & ~15) >> 3) << 17);
+                const uint32_t idesc = (MT2_IDESC & ~(0x3Fu << 17)) | ((uint32_t)(((rows_here + 31) & ~31) >> 3) << 17);
                 // barriers of this issuer's NEXT tile, t + 2 (same pipelines, consecutive tile numbers even across set boundaries)
                 const int s1 = (t + 2) % MT_STAGES, b1 = b;
                 const uint32_t ph1 = (uint32_t)((t + 2) / MT_STAGES) & 1u, bph1 = (uint32_t)((t + 2) >> 1) & 1u;
@@ -251,10 +253,10 @@ k_hamming_umma2(const uint8_t* __restrict__ query, int nq, const uint8_t* __rest
         const int qrow = q0 + a * 128 + (warp & 3) * 32 + lane;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         int t = 0;
-        MatchSetRange rg_next = match_set_range(train_counts, min((int)blockIdx.z, nsets - 1), nt, split, rows_per_split);
+        int cnt_next = match_set_count(train_counts, min((int)blockIdx.z, nsets - 1), nt);
         for (int set = blockIdx.z; set < nsets && ok; set += gridDim.z) {
-            const MatchSetRange rg = rg_next;                // (next set's row count loaded a set ahead, as in the issuer)
-            if (set + (int)gridDim.z < nsets) rg_next = match_set_range(train_counts, set + (int)gridDim.z, nt, split, rows_per_split);
+            const MatchSetRange rg = match_set_range_n(cnt_next, nt, split, rows_per_split);   // (next set's row count loaded a set ahead, as in the issuer)
+            if (set + (int)gridDim.z < nsets) cnt_next = match_set_count(train_counts, set + (int)gridDim.z, nt);
             int m1 = INT_MIN, m2 = INT_MIN;
             for (int i = 0; i < rg.ntiles; ++i, ++t) {
                 const int b = t & 1;
@@ -292,6 +294,33 @@ k_hamming_umma2(const uint8_t* __restrict__ query, int nq, const uint8_t* __rest
                         }
                         const unsigned pk = __vimax3_s16x2(__vimax3_s16x2(p[0], p[1], p[2]), __vimax3_s16x2(p[3], p[4], p[5]), __vmaxs2(p[6], p[7]));
                         k1 = max((int)(pk << 16) >> 16, (int)pk >> 16);
+                    } else if (!KNN2) {
+                        // a set's partial last tile was issued with N = 32, 64 (or 96) columns, its rows past the set's end are
+                        // copies of the last row (never the maximum): same packed path, 32-column chunks as far as N goes
+                        const int nch = (rg.n1 - j0 + 31) >> 5;
+                        uint32_t rp[MT_BN / 2];
+#pragma unroll
+                        for (int ch = 0; ch < NCH; ++ch) {
+                            if (ch < nch) tc_ld16_pack16(tacc + (uint32_t)(ch * 32), rp + ch * 16);
+                            else {
+#pragma unroll
+                                for (int u = 0; u < 16; ++u) rp[ch * 16 + u] = 0x80008000u;
+                            }
+                        }
+                        tc_wait_ld();
+                        if (tr_on) trace[(t - 40) * 16 + 6] = clock64();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * b);
+                        unsigned p[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            p[u] = __vimax3_s16x2(rp[u], rp[8 + u], rp[16 + u]);
+                            p[u] = __vimax3_s16x2(p[u], rp[24 + u], rp[32 + u]);
+                            p[u] = __vmaxs2(p[u], rp[40 + u]);
+                        }
+                        const unsigned pk = __vimax3_s16x2(__vimax3_s16x2(p[0], p[1], p[2]), __vimax3_s16x2(p[3], p[4], p[5]), __vmaxs2(p[6], p[7]));
+                        k1 = max((int)(pk << 16) >> 16, (int)pk >> 16);
                     } else {
 #pragma unroll
                     for (int ch = 0; ch < NCH; ++ch) tc_ld32(tacc + (uint32_t)(ch * 32), r[ch]);
@@ -302,35 +331,6 @@ k_hamming_umma2(const uint8_t* __restrict__ query, int nq, const uint8_t* __rest
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(lead_tempty + 8 * b);
-                    if (!KNN2) {
-                        // a set's partial last tile: whole valid 32-column chunks as above, the boundary chunk masked with
-                        // warp-uniform selects, chunks beyond skipped (the generic per-column loop below made every set
-                        // boundary a ~1500-cycle bubble in the pipeline)
-                        const int nv = rg.n1 - j0;
-                        int p[8];
-#pragma unroll
-                        for (int u = 0; u < 8; ++u) p[u] = INT_MIN;
-#pragma unroll
-                        for (int ch = 0; ch < NCH; ++ch) {
-                            const int nvc = nv - ch * 32;
-                            if (nvc >= 32) {
-#pragma unroll
-                                for (int u = 0; u < 8; ++u) {
-                                    p[u] = __vimax3_s32(p[u], (int)r[ch][u * 4], (int)r[ch][u * 4 + 1]);
-                                    p[u] = __vimax3_s32(p[u], (int)r[ch][u * 4 + 2], (int)r[ch][u * 4 + 3]);
-                                }
-                            } else if (nvc > 0) {
-#pragma unroll
-                                for (int u = 0; u < 8; ++u) {
-                                    const int v0 = u * 4 < nvc ? (int)r[ch][u * 4] : INT_MIN, v1 = u * 4 + 1 < nvc ? (int)r[ch][u * 4 + 1] : INT_MIN;
-                                    const int v2 = u * 4 + 2 < nvc ? (int)r[ch][u * 4 + 2] : INT_MIN, v3 = u * 4 + 3 < nvc ? (int)r[ch][u * 4 + 3] : INT_MIN;
-                                    p[u] = __vimax3_s32(p[u], v0, v1);
-                                    p[u] = __vimax3_s32(p[u], v2, v3);
-                                }
-                            }
-                        }
-                        k1 = __vimax3_s32(__vimax3_s32(p[0], p[1], p[2]), __vimax3_s32(p[3], p[4], p[5]), max(p[6], p[7]));
-                    } else {
 #pragma unroll
                         for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
@@ -341,7 +341,6 @@ k_hamming_umma2(const uint8_t* __restrict__ query, int nq, const uint8_t* __rest
                                     k1 = max(k1, k);
                                 }
                     }
-                    }
                     // decode the tile winner(s) into the global key  dot << 20 | (0xFFFFF - j)
 #pragma unroll
                     for (int w = 0; w < (KNN2 ? 2 : 1); ++w) {
@@ -350,7 +349,7 @@ k_hamming_umma2(const uint8_t* __restrict__ query, int nq, const uint8_t* __rest
                             const unsigned kk = (unsigned)(k + MT_ASCALE * 256);
                             const unsigned q = kk / (unsigned)MT_ASCALE;          // dot + 256
                             const int code = (MT_BN - 1) - (int)(kk - q * (unsigned)MT_ASCALE);   // 48 * (CTA holding the row) + local row
-                            const int nh = ((min(MT_BN, rg.n1 - j0) + 15) & ~15) >> 1;
+                            const int nh = ((min(MT_BN, rg.n1 - j0) + 31) & ~31) >> 1;
                             const int jl = code >= MT2_HALF ? nh + code - MT2_HALF : code;
                             const int gk = ((int)q - 256) * (1 << MT_KEY_SHIFT) + ((MT_MAX_TRAIN - 1) - (j0 + jl));
                             if (KNN2) m2 = max(m2, min(m1, gk));
@@ -366,6 +365,8 @@ k_hamming_umma2(const uint8_t* __restrict__ query, int nq, const uint8_t* __rest
                 if (tr_on) trace[(t - 40) * 16 + 11] = clock64() + (m1 & 1);
                 if (tr_on) trace[(t - 40) * 16 + 7] = clock64();
             }
+            const bool tr_set = trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && t > 40 && t <= 56 && warp == MT_EPI_WARP0 + 1 && lane == 0;
+            if (tr_set) trace[(t - 1 - 40) * 16 + 12] = clock64();
             if (ok && qrow < nq) {
                 const size_t o = (size_t)set * nq + qrow;
                 if (keys) {
@@ -386,6 +387,7 @@ k_hamming_umma2(const uint8_t* __restrict__ query, int nq, const uint8_t* __rest
                     }
                 }
             }
+            if (tr_set) trace[(t - 1 - 40) * 16 + 13] = clock64();
         }
     }
     if (!ok) atomicOr(status, 2);

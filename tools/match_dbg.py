@@ -31,7 +31,7 @@ if os.environ.get("ORBX_MATCH_TRACE"):
     ctx.lib.orbx_debug_match_trace(ctx.h, tr.ctypes.data)
     tr = tr.reshape(16, 16)
     base = tr[0, 0]
-    names = ["iss:start", "iss:tempty", "iss:full", "iss:committed", "epi:start", "epi:tfull", "epi:ld_done", "epi:arrived", "exp:start", "exp:empty", "exp:arrived", "epi:computed", "epi:fenced"]
+    names = ["iss:start", "iss:tempty", "iss:full", "iss:committed", "epi:start", "epi:tfull", "epi:ld_done", "epi:arrived", "exp:start", "exp:empty", "exp:arrived", "epi:computed", "epi:set_end", "epi:stored"]
     print("tile " + " ".join(f"{n:>13s}" for n in names))
     for i in range(16):
-        print(f"{40+i:4d} " + " ".join(f"{(tr[i, k] - base) if tr[i, k] else -1:13d}" for k in range(13)))
+        print(f"{40+i:4d} " + " ".join(f"{(tr[i, k] - base) if tr[i, k] else -1:13d}" for k in range(14)))
