@@ -284,7 +284,7 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
     ext_total = sum(ext_stages.values())
     roofline = None
     traffic = None                                       # DRAM bytes of the dominant kernel per launch, from the committed ncu --set full capture
-    traffic_file = "profiles/r1_v14_ncu_dram_traffic.json"
+    traffic_file = "profiles/r1_v15_ncu_dram_traffic.json"
     try:
         tj = json.load(open(os.path.join(ROOT, traffic_file)))["kernels"]
         kname = {"gray": "k_gray", "pyramid": "k_pyr_down", "fast_nms": "k_fast_bands", "select_harris": "k_select", "blur": "k_blur",
@@ -305,9 +305,9 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
     roof_match = None
     if "match" in stage_ms:
         tops = match_ops / (stage_ms["match"] / 1e3) / 1e12
-        roof_match = {"bound": "tensor", "kernel": "k_hamming_umma (tcgen05 kind::i8)", "achieved": tops, "peak": 4500.0, "unit": "TOP/s",
+        roof_match = {"bound": "tensor", "kernel": "k_hamming_umma2 (tcgen05 cta_group::2 kind::i8)", "achieved": tops, "peak": 4500.0, "unit": "TOP/s",
                       "frac": tops / 4500.0, "peak_source": "nominal dense int8 (no measured int8 peak available)", "kernel_ms": stage_ms["match"],
-                      "ncu_tensor_pipe_cycles_active_pct": 61.2, "ncu_source": "profiles/r1_v14_ncu_full_summary.csv (sm__pipe_tensor_cycles_active, same launch shape)"}
+                      "ncu_tensor_pipe_cycles_active_pct": 76.4, "ncu_source": "profiles/r1_v15_ncu_full_summary.csv (sm__pipe_tensor_cycles_active, same launch shape)"}
 
     # ---- CPU baseline: the reference's own operators (cv2) on this box's host cores, bounded sample
     cpu = None

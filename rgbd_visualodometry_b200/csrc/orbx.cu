@@ -305,11 +305,6 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, bool marks, int f0, int nb,
     }
     if (marks) stage_mark(c, 2);
     if (g.total_bands > 0) {
-        static const int fdbg = getenv("ORBX_FAST_DBG") ? atoi(getenv("ORBX_FAST_DBG")) : 0;
-        if (fdbg == 1) k_fast_bands<FAST_R, FAST_NT, 1><<<dim3((unsigned)g.total_bands, B), FAST_NT, 0, st>>>(g, pyr, rowcnt, rowent);
-        else if (fdbg == 2) k_fast_bands<FAST_R, FAST_NT, 2><<<dim3((unsigned)g.total_bands, B), FAST_NT, 0, st>>>(g, pyr, rowcnt, rowent);
-        else if (fdbg == 3) k_fast_bands<FAST_R, FAST_NT, 3><<<dim3((unsigned)g.total_bands, B), FAST_NT, 0, st>>>(g, pyr, rowcnt, rowent);
-        else
         k_fast_bands<FAST_R, FAST_NT><<<dim3((unsigned)g.total_bands, B), FAST_NT, 0, st>>>(g, pyr, rowcnt, rowent);
         ++c->launches;
     }

@@ -259,15 +259,20 @@ __global__ void __launch_bounds__(PYR_NT) k_pyr_down(const __grid_constant__ Geo
 // Per chunk (score tile = (R+2) rows x 256 columns, x = ox0-4 .. ox0+251), four block barriers:
 //   load      (R+8) x 288 pixels widened to u16 into smem with 128-bit global loads (16-byte aligned tile origin)
 //   phase A   per WARP, on its own (row, 128-pixel half) items: 4-compass-point rejection test of every pixel quad in
-//             u16x2 SIMD (native VIMNMX.U16x2) from five 64-bit shared loads; survivors are appended to the warp's
-//             private queue straight from the ballots (no atomics, no block scan, no barrier)
-//   phase B   the same warp runs the full 16-point test on its queue.  Each circle pixel is packed
+//             u16x2 SIMD (native VIMNMX.U16x2) from five 64-bit shared loads; a quad with any passing pixel becomes one
+//             entry of the warp's private quad queue (one ballot per item, no atomics, no block scan, no barrier)
+//   phase A2  the same warp, on its queued quads: second rejection test on the two diagonal pairs of the circle, then the
+//             surviving pixels are expanded to pixel entries (bit-sliced warp prefix), in place
+//   phase B   the same warp runs the full 16-point test on its pixel queue.  Each circle pixel is packed
 //             (p | (255-p) << 16) so ONE sliding max over the 16 nine-long arcs (VIMNMX3.U16x2) yields both
 //             min-of-max(p) and max-of-min(p):  A = v - min_arcs max p,  -B = max_arcs min p - v,
 //             score = max(A, -B) - 1 (corner iff > t).  Corners inside the output region go to a private NMS queue.
 //   phase C   3x3 NMS (strict >) of the queued corners on the shared score tile -> per-row bit masks
 //   phase D   ordered extraction of the bit masks (popc prefix) -> global per-row lists
-template <int R, int NT, int DBG = 0>
+// Measured and dropped (tools/stage_times.py): register-prefetched next tile with three barriers per chunk,
+// persistent CTAs over (band, frame) items with static or ticket scheduling, a CTA-wide survivor queue that balances
+// phase B across warps, a u8 image tile (half the shared-memory wavefronts, more PRMT), 6-7 CTAs per SM by register cap.
+template <int R, int NT>
 __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr,
                                                    uint32_t* __restrict__ rowcnt, uint32_t* __restrict__ rowent)
 {
@@ -339,7 +344,6 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
             if (tid < R * MW) s_mask[tid] = 0;
         }
         __syncthreads();
-        if (DBG == 1) continue;
         // ---- phase A (per warp): compass rejection on (row, 128-pixel half) items -> private QUAD queue
         // Shared memory is addressed through one precomputed 32-bit base per chunk (LDS with immediate offsets).  Only about
         // one pixel in 13 passes, so the per-item bookkeeping is kept to ONE ballot: a lane whose quad has any passing
@@ -377,7 +381,6 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
             }
         }
         __syncwarp();
-        if (DBG == 2) { if (qn4 == 12345) s_rowcnt[0] = 1; continue; }
         // ---- phase A2 (same warp): quad entries -> pixel entries (sy << 8 | sx), 32 quad entries at a time.
         // First the SECOND rejection test, on the quads that survived only: the two diagonal opposite pairs of the circle
         // ((+-2, +-2): points 2/10 and 6/14) must also hold a darker or a brighter pixel each -- same u16x2 arithmetic as
@@ -469,7 +472,6 @@ __global__ void __launch_bounds__(NT) k_fast_bands(const __grid_constant__ Geom 
                 cn += __popc(bc);
             }
         }
-        if (DBG == 3) { if (cn == 12345) s_rowcnt[0] = 1; continue; }
         __syncthreads();                                     // every score of the tile is in place
         // ---- phase C (per warp): 3x3 NMS of its queued corners
         for (int i = lane; i < cn; i += 32) {
