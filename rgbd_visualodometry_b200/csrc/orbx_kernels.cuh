@@ -226,16 +226,18 @@ __global__ void __launch_bounds__(PYR_NT) k_pyr_down(const __grid_constant__ Geo
             const bool clamped = (int)(ty & 0xffffu) == s;   // y1 == y0: both taps read the last source row
             const uint32_t cy1 = ty >> 16, cy0 = 256u - cy1;
             uint32_t out[PYR_NQ];
+            // vertical pass: h <= 255 * 256, so top * cy0 + cur * cy1 + 2^15 < 2^24 and its byte 2 IS the rounded pixel
+            // (never above 255): two IMADs per pixel on the FMA pipe and three PRMTs per quad to gather the bytes
+            auto blend = [&](const PyrRow* top) {
 #pragma unroll
-            for (int q = 0; q < PYR_NQ; ++q) {
-                out[q] = 0;
+                for (int q = 0; q < PYR_NQ; ++q) {
+                    uint32_t v[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint32_t top = clamped ? hc[q].h[k] : hp[q].h[k];
-                    const uint32_t v = (top * cy0 + hc[q].h[k] * cy1 + 32768u) >> 16;
-                    out[q] |= min(v, 255u) << (8 * k);
+                    for (int k = 0; k < 4; ++k) v[k] = top[q].h[k] * cy0 + (hc[q].h[k] * cy1 + 32768u);
+                    out[q] = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
                 }
-            }
+            };
+            if (clamped) blend(hc); else blend(hp);
             *reinterpret_cast<uint2*>(dst) = make_uint2(out[0], out[1]);
             dst += D.pitch;
             ++y;
