@@ -189,6 +189,38 @@ def test_match_device_batched(orbmod, oracle):
     ctx.close()
 
 
+def test_match_pair_kernel_ragged_sets(orbmod, oracle):
+    """Enough (query tile, set) pairs to select the CTA-pair kernel (tcgen05 cta_group::2): ragged train sets whose sizes sit on
+    every tile / chunk boundary (0, 1, 15..17, 31..33, 47..49, 63..65, 95..97, 191..193, full), an odd number of query tiles
+    (the last pair's peer CTA has no rows) and duplicated rows across the boundary of the padded last tile (ties -> lowest index)."""
+    import torch
+    from rgbd_visualodometry_b200.synth import synth_descriptors, synth_map_queries
+    cap, nq = 300, 5 * 256 - 77                      # 5 query tiles -> padded to 6 for the pairs
+    sizes = [0, 1, 15, 16, 17, 31, 32, 33, 47, 48, 49, 63, 64, 65, 95, 96, 97, 191, 192, 193, 255, 299, 300]
+    sizes = sizes + [int(x) for x in np.random.default_rng(5).integers(0, cap + 1, 40 - len(sizes))]
+    nsets = len(sizes)
+    assert 6 * nsets >= 148
+    trains = np.stack([synth_descriptors(cap, 900 + i) for i in range(nsets)])
+    for i, n in enumerate(sizes):                    # the set's last row also appears earlier: the padded copies must not win
+        if n >= 3:
+            trains[i, n - 1] = trains[i, n // 2]
+    q = synth_map_queries(trains[1 + int(np.argmax(sizes[1:]))], nq, 71)
+    ctx = orbmod.Context(1, 1.2, 1, 64, 64, 1)
+    dq = torch.from_numpy(q).cuda(); dt = torch.from_numpy(trains).cuda()
+    dn = torch.tensor(sizes, dtype=torch.int32, device="cuda")
+    best = torch.zeros((nsets, nq, 4), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.match_device_ragged(dq.data_ptr(), nq, dt.data_ptr(), cap, dn.data_ptr(), nsets, best.data_ptr())
+    ctx.synchronize()
+    got = best.cpu().numpy().view(orbmod.DMATCH_DTYPE).reshape(nsets, nq)
+    for s, n in enumerate(sizes):
+        if n == 0:
+            assert (got[s]["trainIdx"] == -1).all(), f"empty set {s}"
+        else:
+            assert got[s].tobytes() == oracle.match_hamming(q, trains[s, :n]).tobytes(), f"set {s} ({n} rows)"
+    ctx.close()
+
+
 def test_orb_device_resident_full_size(orbmod, oracle):
     """BASELINE config 2 shape: a device-resident batch of 640x480 frames, 1000 features; every frame checked."""
     import torch
