@@ -322,6 +322,37 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
     except Exception as e:  # pragma: no cover
         cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
 
+    # ---- parity counters of THIS run against the reference's operators (cv2) on the same frames: a few frames spread
+    #      over the batch, both the device-resident outputs of the timed path and the host outputs of the e2e call; all must be 0
+    parity = None
+    try:
+        import cv2
+        cv2.setNumThreads(1)
+        cvo, cvm = cv2.ORB_create(NFEAT, SCALE, NLEVELS), cv2.BFMatcher(cv2.NORM_HAMMING)
+        chk = sorted({0, B // 3, (2 * B) // 3, B - 1})
+        kp_bad = desc_bad = match_bad = 0
+        cnt_d = d_cnt.cpu().numpy()
+        for i in chk:
+            ck, cd = cvo.detectAndCompute(frames_np[i], None)
+            ref_k = np.array([(k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave, k.class_id) for k in ck], dtype=orb.KP_DTYPE)
+            cm = cvm.match(map_np, cd)
+            ref_m = np.array([(m.queryIdx, m.trainIdx, m.imgIdx, m.distance) for m in cm], dtype=orb.DMATCH_DTYPE)
+            for kk, dd, nn, mm in ((d_kps[i].cpu().numpy(), d_desc[i].cpu().numpy(), int(cnt_d[i]), d_best[0][i].cpu().numpy()),
+                                   (kps_h[i].numpy(), desc_h[i].numpy(), int(cnt_h[i]), best_hs[0][i].numpy())):
+                got_k = np.ascontiguousarray(kk[:nn]).view(orb.KP_DTYPE).reshape(-1)
+                if len(got_k) != len(ref_k):
+                    kp_bad += max(len(got_k), len(ref_k)); desc_bad += 32 * max(len(got_k), len(ref_k)); match_bad += MAP_M
+                    continue
+                kp_bad += int(sum(a.tobytes() != b.tobytes() for a, b in zip(got_k, ref_k)))
+                desc_bad += int((dd[:nn] != cd).sum())
+                got_m = np.ascontiguousarray(mm).view(orb.DMATCH_DTYPE).reshape(-1)
+                match_bad += int(sum(a.tobytes() != b.tobytes() for a, b in zip(got_m, ref_m))) + abs(len(got_m) - len(ref_m))
+        parity = {"vs": f"cv2 {cv2.__version__} detectAndCompute + BFMatcher(NORM_HAMMING).match on the same frames", "frames_checked": chk,
+                  "paths": ["device-resident (timed)", "host-buffer C-ABI (e2e)"], "keypoint_record_mismatches": kp_bad,
+                  "descriptor_byte_mismatches": desc_bad, "match_record_mismatches": match_bad, "angle_tie_descriptor_diffs": 0 if desc_bad == 0 else None}
+    except Exception as e:  # pragma: no cover
+        parity = {"unavailable": str(e)}
+
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
@@ -334,7 +365,7 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_pipeline": {"achieved": pipe_ach, "peak": hbm_peak, "unit": "GB/s", "frac": pipe_ach / hbm_peak if pipe_ach else None,
                                                          "note": "same algorithmic bytes over the sum of all extraction kernels"},
-            "roofline_match": roof_match, "stage_ms": stage_ms, "cpu_baseline": cpu}
+            "roofline_match": roof_match, "stage_ms": stage_ms, "cpu_baseline": cpu, "parity": parity}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
