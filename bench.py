@@ -158,6 +158,9 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; rank 0's stdout must stay one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
