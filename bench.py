@@ -124,7 +124,7 @@ def run_reference(args, rank: int, world: int):
     try:
         import cv2  # noqa: F401
     except Exception as e:  # pragma: no cover
-        print(json.dumps({"impl": "reference", "unavailable": f"cv2 not importable: {e}"}))
+        emit({"impl": "reference", "unavailable": f"cv2 not importable: {e}"})
         return
     threads = os.cpu_count() or 1
     sample = 64
@@ -148,7 +148,7 @@ def run_reference(args, rank: int, world: int):
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "reference",
                              "sample": f"{sample} frames per step, frame-parallel over {threads} host threads, cv2.setNumThreads(1)"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_orbx(args, rank: int, world: int, local_rank: int):
@@ -158,9 +158,6 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
-        # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; rank 0's stdout must stay one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist_
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -369,9 +366,29 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
             "roofline": roofline, "roofline_pipeline": {"achieved": pipe_ach, "peak": hbm_peak, "unit": "GB/s", "frac": pipe_ach / hbm_peak if pipe_ach else None,
                                                          "note": "same algorithmic bytes over the sum of all extraction kernels"},
             "roofline_match": roof_match, "stage_ms": stage_ms, "cpu_baseline": cpu, "parity": parity}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+# Rank 0's stdout carries exactly ONE JSON line: everything else a library may print there (NCCL's version banner goes to
+# stdout whatever NCCL_DEBUG says) is sent to stderr by pointing fd 1 at fd 2 for the whole run; emit() writes the line to the
+# real stdout.
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    data = (json.dumps(obj) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def main():
@@ -385,6 +402,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
