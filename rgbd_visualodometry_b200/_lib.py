@@ -14,7 +14,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 SO = os.path.join(PKG, "liborbx.so")
-SOURCES = ["orbx.cu", "orbx_kernels.cuh", "orbx_match.cuh", "orbx_match2.cuh", "orbx_map.cuh", "orbx_geom.h", "brief_pattern.inc"]
+SOURCES = ["orbx.cu", "orbx_kernels.cuh", "orbx_match.cuh", "orbx_map.cuh", "orbx_geom.h", "brief_pattern.inc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared"]
 

@@ -19,7 +19,6 @@
 #include "orbx_geom.h"
 #include "orbx_kernels.cuh"
 #include "orbx_match.cuh"
-#include "orbx_match2.cuh"
 #include "orbx_map.cuh"
 #include <unordered_map>
 

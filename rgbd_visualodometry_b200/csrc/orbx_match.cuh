@@ -232,9 +232,74 @@ __device__ __forceinline__ MatchSetRange match_set_range(const int* __restrict__
     return match_set_range_n(match_set_count(counts, set, nt), nt, split, rows_per_split);
 }
 
-template <bool KNN2>
-__global__ void __launch_bounds__(MT_THREADS, 1)
-k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restrict__ train, int nt, int train_stride_rows,
+// ---- CTA pair (tcgen05 cta_group::2): the same body with PAIR = true ---------------------------------------------
+// Two CTAs on the SMs of one TPC share every B tile.  Each CTA still owns 256 query rows (two
+// 128-row A tiles parked in its own tensor memory) and its own accumulators and epilogue; of a 96-row train tile each
+// CTA expands only HALF (48 rows, two threads per row) into its own shared memory, and one UMMA of M = 256 issued by the
+// leader feeds both SMs' tensor cores (the hardware exchanges the B halves).  Per SM that halves the bit expansion and the
+// shared-memory operand reads of every MMA -- the two things that kept the single-CTA kernel at ~57 instead of 48 cycles
+// per MMA.  Barriers: "stage full" and "accumulators free" live in the leader (the peer arrives on them through the
+// cluster address space); "stage free" and "accumulators full" are signalled in BOTH CTAs by multicast tcgen05.commit.
+// Row code of the bias k-step: local row i of CTA r carries 95 - (48 r + i); for a partial last tile issued with a smaller
+// UMMA N the peer holds rows N/2 .. N-1, still in decreasing code order, and the epilogue maps the code back with N.
+constexpr int MT2_HALF = MT_BN / 2;                          // train rows of a B tile held by each CTA of the pair
+constexpr int MT2_GROUP_WARPS = MT_BN / 32;                  // expander warps per group (two threads per local row)
+// instruction descriptor: as MT_IDESC but M = 256 (cta_group::2)
+constexpr uint32_t MT2_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(MT_BN >> 3) << 17) | ((256u >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t cta) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");   // (default .release.cta, as CUTLASS' ClusterBarrier::arrive(cta_id): the cluster-scope form stalls the warp for ~1000 cycles)
+}
+__device__ __forceinline__ void tc_commit2(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma2_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_mma2_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+
+// PAIR-generic pieces of the body
+template <bool PAIR> __device__ __forceinline__ void group_sync() { if (PAIR) cluster_sync_all(); else __syncthreads(); }
+template <bool PAIR> __device__ __forceinline__ void tmem_alloc_all(uint32_t slot_saddr) {
+    if (PAIR) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_saddr), "r"(MT_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_saddr), "r"(MT_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+}
+template <bool PAIR> __device__ __forceinline__ void tmem_dealloc_all(uint32_t base) {
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(MT_TMEM_COLS) : "memory");
+    else      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(MT_TMEM_COLS) : "memory");
+}
+template <bool PAIR> __device__ __forceinline__ void bar_arrive_lead(uint32_t addr) { if (PAIR) mbar_arrive_cluster(addr); else mbar_arrive(addr); }
+template <bool PAIR> __device__ __forceinline__ void umma_i8_ts(uint32_t d, uint32_t a, uint64_t db, uint32_t idesc, uint32_t acc) {
+    if (PAIR) tc_mma2_i8_ts(d, a, db, idesc, acc); else tc_mma_i8_ts(d, a, db, idesc, acc);
+}
+template <bool PAIR> __device__ __forceinline__ void umma_i8(uint32_t d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    if (PAIR) tc_mma2_i8(d, da, db, idesc, acc); else tc_mma_i8(d, da, db, idesc, acc);
+}
+template <bool PAIR> __device__ __forceinline__ void umma_commit(uint32_t bar) { if (PAIR) tc_commit2(bar); else tc_commit(bar); }
+
+template <bool KNN2, bool PAIR>
+__device__ __forceinline__ void
+hamming_umma_body(const uint8_t* __restrict__ query, int nq, const uint8_t* __restrict__ train, int nt, int train_stride_rows,
                const int* __restrict__ train_counts, int nsets, int rows_per_split, int4* __restrict__ best,
                int4* __restrict__ second, int* __restrict__ keys, int* __restrict__ status, int dbg, long long* __restrict__ trace)
 {
@@ -248,16 +313,20 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int split = blockIdx.y;
     const int q0 = blockIdx.x * MT_QROWS;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // pair: 0 = leader (issues the MMAs of the pair), 1 = peer
+    constexpr int ROWS_CTA = PAIR ? MT2_HALF : MT_BN;        // rows of a B tile this CTA expands and holds
+    constexpr uint32_t IDESC = PAIR ? MT2_IDESC : MT_IDESC;
 
     // ---- setup: barriers, TMEM, A tiles (expanded in registers and parked in tensor memory)
     if (tid == 0) {
-        for (int s = 0; s < MT_STAGES; ++s) { mbar_init(bar_full + 8 * s, MT_BN / 32); mbar_init(bar_empty + 8 * s, 1); }   // one arrive per warp:
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, 8); }             // same-address arrives serialise
+        // one arrive per warp (same-address arrives serialise).  Pair: full / tempty are only used in the leader, the peer
+        // arrives on them remotely, so they count both CTAs' warps
+        for (int s = 0; s < MT_STAGES; ++s) { mbar_init(bar_full + 8 * s, (PAIR ? 2 : 1) * MT2_GROUP_WARPS); mbar_init(bar_empty + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_tfull + 8 * b, 1); mbar_init(bar_tempty + 8 * b, PAIR ? 16 : 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MT_ISSUER_WARP) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_slot)), "r"(MT_TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        tmem_alloc_all<PAIR>(smem_u32((const void*)tmem_slot));
     }
     for (int i = tid; i < (128 * 128 + MT_BN * 128) / 16; i += MT_THREADS) reinterpret_cast<uint4*>(smem + MT_SMEM_CA)[i] = make_uint4(0, 0, 0, 0);
     tc_fence_before();
@@ -265,9 +334,9 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
     tc_fence_after();
     // bias k-step operands: logical byte k = 0 of row r sits at (r / 8) * 1024 + (r % 8) * 128 + ((0 ^ (r % 8)) << 4)
     if (tid < 128) smem[MT_SMEM_CA + (tid >> 3) * 1024 + (tid & 7) * 128 + ((tid & 7) << 4)] = 1;
-    else if (tid < 128 + MT_BN) {
-        const int jl = tid - 128;
-        smem[MT_SMEM_CB + (jl >> 3) * 1024 + (jl & 7) * 128 + ((jl & 7) << 4)] = (uint8_t)(MT_BN - 1 - jl);
+    else if (tid < 128 + ROWS_CTA) {                         // this CTA's rows of the bias B tile: local row i <-> code 95 - (ROWS_CTA * rank + i)
+        const int i = tid - 128;
+        smem[MT_SMEM_CB + (i >> 3) * 1024 + (i & 7) * 128 + ((i & 7) << 4)] = (uint8_t)(MT_BN - 1 - ((int)rank * ROWS_CTA + i));
     }
     const uint32_t tmem_base = *tmem_slot;
     bool ok = true;
@@ -291,13 +360,20 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
     }
     fence_proxy_async_smem();                                // constant bias tiles (generic-proxy stores) -> visible to the tensor core
     tc_fence_before();
-    __syncthreads();
+    group_sync<PAIR>();                                      // (pair: both CTAs) barriers initialised, TMEM allocated, A tiles parked
     tc_fence_after();
+    // where "stage full" / "accumulators free" are signalled: the leader's barriers through the cluster address space, or simply the CTA's own
+    const uint32_t lead_full = PAIR ? mapa_u32(bar_full, 0) : bar_full, lead_tempty = PAIR ? mapa_u32(bar_tempty, 0) : bar_tempty;
 
     if (warp < MT_EXP_WARPS) {
         // ================= expanders: one B-tile row per thread; raw rows arrive through a cp.async ring
         //                   MT_PREFETCH tiles ahead, so global-load latency never sits on the pipeline's critical path
-        const int grp = tid / MT_BN, r = tid - grp * MT_BN;   // expander group and B-tile row of this thread
+        // 96 threads per group, two groups on alternate tiles.  Single CTA: one B-tile row (32 raw bytes) per thread.  Pair: a
+        // tile of N rows is split between the CTAs -- rows [0, N/2) live in the leader's shared memory, [N/2, N) in the
+        // peer's -- and two threads share a local row (one 16-byte K half each).
+        const int grp = tid / MT_BN, tl = tid - grp * MT_BN;
+        const int r = PAIR ? tl % MT2_HALF : tl, hk = PAIR ? tl / MT2_HALF : 0;      // local row, K half
+        constexpr int PIECE = PAIR ? 16 : 32;                // raw bytes per thread and tile
         struct TileIter {
             int set, i; MatchSetRange rg;
         };
@@ -314,22 +390,23 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
         seek(cur);
         for (int k = 0; k < grp; ++k) step(cur);             // group g owns tiles g, g + GROUPS, g + 2 GROUPS, ...
         TileIter ahead = cur;
-        uint8_t* raw = smem + MT_SMEM_RAW + (grp * MT_PREFETCH * MT_BN + r) * 32;
-        auto fetch = [&](int slot) {                         // raw row of the tile `ahead` names -> ring slot (own row only)
-            uint8_t* dst = raw + slot * (MT_BN * 32);
+        uint8_t* raw = smem + MT_SMEM_RAW + (grp * MT_PREFETCH * MT_BN + tl) * PIECE;
+        auto fetch = [&](int slot) {                         // raw (half) row of the tile `ahead` names -> ring slot (own piece only)
+            uint8_t* dst = raw + slot * (MT_BN * PIECE);
             if (ahead.set < nsets) {
-                // rows past the set's end (partial last tile) repeat the set's LAST row: a copy scores like the original but
-                // carries a smaller index code, so it can never win -- and the epilogue needs no per-column masking
                 const int j0t = ahead.rg.n0 + ahead.i * MT_BN;
-                const int j = min(j0t + r, ahead.rg.n1 - 1);
-                if (r < ((min(MT_BN, ahead.rg.n1 - j0t) + 31) & ~31)) {
-                    const uint8_t* src = train + ((size_t)ahead.set * train_stride_rows + j) * 32;
+                const int nh = ((min(MT_BN, ahead.rg.n1 - j0t) + 31) & ~31) >> (PAIR ? 1 : 0);    // rows per CTA of this tile (UMMA N, halved for a pair)
+                // rows past the set's end repeat the set's LAST row: a copy scores like the original but carries a smaller
+                // index code, so it can never win -- and the epilogue needs no per-column masking
+                const int j = min(j0t + (int)rank * nh + r, ahead.rg.n1 - 1);
+                if (r < nh) {
+                    const uint8_t* src = train + ((size_t)ahead.set * train_stride_rows + j) * 32 + hk * 16;
                     const uint32_t d = smem_u32(dst);
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16), "l"(src + 16) : "memory");
+                    if (!PAIR) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16), "l"(src + 16) : "memory");
                 } else {
                     reinterpret_cast<uint4*>(dst)[0] = make_uint4(0, 0, 0, 0);
-                    reinterpret_cast<uint4*>(dst)[1] = make_uint4(0, 0, 0, 0);
+                    if (!PAIR) reinterpret_cast<uint4*>(dst)[1] = make_uint4(0, 0, 0, 0);
                 }
 #pragma unroll 1
                 for (int k = 0; k < MT_EXP_GROUPS; ++k) step(ahead);
@@ -342,8 +419,9 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
         while (cur.set < nsets) {
             asm volatile("cp.async.wait_group %0;" ::"n"(MT_PREFETCH - 1) : "memory");
             const int slot = n % MT_PREFETCH;
-            const uint4 clo = reinterpret_cast<const uint4*>(raw + slot * (MT_BN * 32))[0];
-            const uint4 chi = reinterpret_cast<const uint4*>(raw + slot * (MT_BN * 32))[1];
+            const uint4 cv = reinterpret_cast<const uint4*>(raw + slot * (MT_BN * PIECE))[0];
+            uint4 cv2 = cv;
+            if (!PAIR) cv2 = reinterpret_cast<const uint4*>(raw + slot * (MT_BN * PIECE))[1];
             fetch(slot);                                     // refill the slot just consumed
             const int s = t % MT_STAGES;
             const uint32_t ph = (uint32_t)(t / MT_STAGES) & 1u;
@@ -351,10 +429,13 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
             if (tr_on) trace[(t - 40) * 16 + 8] = clock64();
             if (!mbar_wait(bar_empty + 8 * s, ph ^ 1u)) { ok = false; break; }
             if (tr_on) trace[(t - 40) * 16 + 9] = clock64();
-            if (!(dbg & 4)) expand_row(smem + MT_SMEM_B + s * MT_B_BYTES, MT_BN, r, clo, chi);
-            fence_proxy_async_smem();                        // every writer fences, then one lane arrives for the warp
+            if (!(dbg & 4)) {
+                if (PAIR) expand_half_row(smem + MT_SMEM_B + s * MT_B_BYTES, MT2_HALF, r, hk, cv);
+                else      expand_row(smem + MT_SMEM_B + s * MT_B_BYTES, MT_BN, r, cv, cv2);
+            }
+            fence_proxy_async_smem();                        // every writer fences, then one lane arrives for the warp (on the leader's barrier)
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_full + 8 * s);
+            if (lane == 0) bar_arrive_lead<PAIR>(lead_full + 8 * s);
             if (tr_on) trace[(t - 40) * 16 + 10] = clock64();
 #pragma unroll 1
             for (int k = 0; k < MT_EXP_GROUPS; ++k) step(cur);
@@ -362,7 +443,7 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
             ++n;
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
-    } else if (warp == MT_ISSUER_WARP || warp == MT_ISSUER2_WARP) {
+    } else if ((warp == MT_ISSUER_WARP || warp == MT_ISSUER2_WARP) && rank == 0) {   // (pair: the leader issues for both CTAs)
         // ================= MMA issuers =================
         // The whole warp runs the loop so that every operand is computed in warp-uniform code (uniform registers, no
         // per-instruction ELECT / R2UR waterfall); one elected lane issues the tcgen05 instructions.
@@ -400,10 +481,10 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
                 const uint32_t sb = sbu + MT_SMEM_B + s * MT_B_BYTES;
                 const uint64_t db0 = umma_desc_sw128(sb);
                 // A set's last tile usually holds fewer than MT_BN rows: issue it with the smallest UMMA N (multiple of 16)
-                // that covers them -- tensor time is proportional to N.  (Multiples of 32: the epilogue reads 32-column chunks.)  Columns beyond keep stale values the epilogue
+                // that covers them -- tensor time is proportional to N.  Columns beyond keep stale values the epilogue
                 // never reads (it bounds partial tiles by the row count).
                 const int rows_here = min(MT_BN, rg.n1 - (rg.n0 + i * MT_BN));
-                const uint32_t idesc = (MT_IDESC & ~(0x3Fu << 17)) | ((uint32_t)(((rows_here + 31) & ~31) >> 3) << 17);
+                const uint32_t idesc = (IDESC & ~(0x3Fu << 17)) | ((uint32_t)(((rows_here + 31) & ~31) >> 3) << 17);
                 // barriers of this issuer's NEXT tile, t + 2 (same pipelines, consecutive tile numbers even across set boundaries)
                 const int s1 = (t + 2) % MT_STAGES, b1 = b;
                 const uint32_t ph1 = (uint32_t)((t + 2) / MT_STAGES) & 1u, bph1 = (uint32_t)((t + 2) >> 1) & 1u;
@@ -414,10 +495,10 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
                         const uint32_t ta = tb + MT_TMEM_A + (uint32_t)a * 64u;
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks) {      // K = 256 = 8 x UMMA_K(32 int8): 8 TMEM columns of A, 4 k-steps per 128-B swizzle atom of B
-                            const uint64_t db = db0 + (uint64_t)(((ks >> 2) * (MT_BN * 128) + (ks & 3) * 32) >> 4);   // start-address field, 16-byte units
-                            tc_mma_i8_ts(d, ta + (uint32_t)ks * 8u, db, idesc, ks > 0 ? 1u : 0u);
+                            const uint64_t db = db0 + (uint64_t)(((ks >> 2) * (ROWS_CTA * 128) + (ks & 3) * 32) >> 4);   // start-address field, 16-byte units
+                            umma_i8_ts<PAIR>(d, ta + (uint32_t)ks * 8u, db, idesc, ks > 0 ? 1u : 0u);
                         }
-                        tc_mma_i8(d, dca, dcb, idesc, 1u);  // bias k-step: + (MT_BN-1 - jl) in every row
+                        umma_i8<PAIR>(d, dca, dcb, idesc, 1u); // bias k-step: + row code in every row
                     }
                     // While the queued MMAs execute, probe the next tile's barriers so its issue can start without a wait.
                     // The probe sits AFTER the last MMA of the tile: issuing blocks on the MMA queue for most of the tile's
@@ -425,8 +506,8 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
                     if (a == 1) ready_next = mbar_test(bar_tempty + 8 * b1, bph1 ^ 1u) && mbar_test(bar_full + 8 * s1, ph1);
                 }
                 if (elect_one()) {
-                    tc_commit(bar_empty + 8 * s);            // smem stage reusable once these MMAs retire
-                    tc_commit(bar_tfull + 8 * b);            // accumulators of this tile complete
+                    umma_commit<PAIR>(bar_empty + 8 * s);           // smem stage reusable once these MMAs retire (both CTAs' barriers)
+                    umma_commit<PAIR>(bar_tfull + 8 * b);           // accumulators of this tile complete (both CTAs' barriers)
                 }
                 __syncwarp();
                 if (tr_on) trace[(t - 40) * 16 + 3] = clock64();
@@ -469,7 +550,7 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
                         if (tr_on) trace[(t - 40) * 16 + 6] = clock64();
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_tempty + 8 * b);           // TMEM buffer back to the issuer BEFORE the reduction
+                        if (lane == 0) bar_arrive_lead<PAIR>(lead_tempty + 8 * b);           // TMEM buffer back to the issuer BEFORE the reduction
                         unsigned p[8];                           // eight independent max chains (ILP), then a short tree
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
@@ -496,7 +577,7 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
                         if (tr_on) trace[(t - 40) * 16 + 6] = clock64();
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+                        if (lane == 0) bar_arrive_lead<PAIR>(lead_tempty + 8 * b);
                         unsigned p[8];
 #pragma unroll
                         for (int u = 0; u < 8; ++u) {
@@ -515,7 +596,7 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
                     // reduction, so the epilogue's arithmetic overlaps the MMAs of tile t + 2 instead of gating them.
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+                    if (lane == 0) bar_arrive_lead<PAIR>(lead_tempty + 8 * b);
 #pragma unroll
                         for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
@@ -533,7 +614,9 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
                         if (k != INT_MIN) {
                             const unsigned kk = (unsigned)(k + MT_ASCALE * 256);
                             const unsigned q = kk / (unsigned)MT_ASCALE;          // dot + 256
-                            const int jl = (MT_BN - 1) - (int)(kk - q * (unsigned)MT_ASCALE);
+                            const int code = (MT_BN - 1) - (int)(kk - q * (unsigned)MT_ASCALE);   // 48 * (CTA holding the row) + local row
+                            const int nh = ((min(MT_BN, rg.n1 - j0) + 31) & ~31) >> 1;
+                            const int jl = PAIR && code >= MT2_HALF ? nh + code - MT2_HALF : code;
                             const int gk = ((int)q - 256) * (1 << MT_KEY_SHIFT) + ((MT_MAX_TRAIN - 1) - (j0 + jl));
                             if (KNN2) m2 = max(m2, min(m1, gk));
                             m1 = max(m1, gk);
@@ -543,11 +626,13 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
                 else {                                       // (perf-experiment mode without TMEM loads: still release the buffer)
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+                    if (lane == 0) bar_arrive_lead<PAIR>(lead_tempty + 8 * b);
                 }
                 if (tr_on) trace[(t - 40) * 16 + 11] = clock64() + (m1 & 1);
                 if (tr_on) trace[(t - 40) * 16 + 7] = clock64();
             }
+            const bool tr_set = trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && t > 40 && t <= 56 && warp == MT_EPI_WARP0 + 1 && lane == 0;
+            if (tr_set) trace[(t - 1 - 40) * 16 + 12] = clock64();
             if (ok && qrow < nq) {
                 const size_t o = (size_t)set * nq + qrow;
                 if (keys) {
@@ -568,16 +653,31 @@ k_hamming_umma(const uint8_t* __restrict__ query, int nq, const uint8_t* __restr
                     }
                 }
             }
+            if (tr_set) trace[(t - 1 - 40) * 16 + 13] = clock64();
         }
     }
     if (!ok) atomicOr(status, 2);
     tc_fence_before();
-    __syncthreads();
+    group_sync<PAIR>();                                      // (pair: neither CTA may free tensor memory or exit while the other still works)
     if (warp == MT_ISSUER_WARP) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(MT_TMEM_COLS) : "memory");
+        tmem_dealloc_all<PAIR>(tmem_base);
     }
 }
+
+
+#define ORBX_MATCH_PARAMS const uint8_t* __restrict__ query, int nq, const uint8_t* __restrict__ train, int nt, int train_stride_rows, \
+               const int* __restrict__ train_counts, int nsets, int rows_per_split, int4* __restrict__ best, \
+               int4* __restrict__ second, int* __restrict__ keys, int* __restrict__ status, int dbg, long long* __restrict__ trace
+#define ORBX_MATCH_ARGS query, nq, train, nt, train_stride_rows, train_counts, nsets, rows_per_split, best, second, keys, status, dbg, trace
+// single CTA per query tile (small problems: independent CTAs, train rows can be split across them)
+template <bool KNN2>
+__global__ void __launch_bounds__(MT_THREADS, 1) k_hamming_umma(ORBX_MATCH_PARAMS) { hamming_umma_body<KNN2, false>(ORBX_MATCH_ARGS); }
+// CTA pair on the two SMs of a TPC (tcgen05 cta_group::2): blockIdx.x = 2 * pair + rank
+template <bool KNN2>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MT_THREADS, 1) k_hamming_umma2(ORBX_MATCH_PARAMS) { hamming_umma_body<KNN2, true>(ORBX_MATCH_ARGS); }
+#undef ORBX_MATCH_PARAMS
+#undef ORBX_MATCH_ARGS
 
 __global__ void k_match_keys_init(int* __restrict__ keys, size_t n)
 {
