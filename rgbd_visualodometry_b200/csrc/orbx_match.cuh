@@ -11,17 +11,20 @@
 // One CTA owns 256 query rows (two 128-row A tiles).  The map is shared by every frame, so the A operand is expanded
 // ONCE per CTA and parked in TENSOR MEMORY (tcgen05.st; the MMA then takes A from TMEM, "TS" form), which removes
 // half of the shared-memory operand traffic of every MMA.  The CTA then walks train sets and, inside a set, tiles of
-// 96 train rows (B tiles).  Warp roles:
-//   warps 8-13  expanders : (two threads per row) 32-byte descriptor rows -> +-1 int8 rows written straight into the 128B-swizzled K-major
-//                           UMMA layout; the bit expansion is pure ALU (multiply-spread), never touches HBM or a LUT
-//   warp  14    issuer    : one thread issues 2 x 8 tcgen05.mma.kind::i8 (M128 N96 K32, A from TMEM) per B tile into a
+// 96 train rows (B tiles).  Warp roles (ids chosen so that the latency-critical roles sit on the higher warp ids):
+//   warps 0-5   expanders : two groups of 96 threads on alternate tiles; 32-byte descriptor rows -> +-1 int8 rows written
+//                           straight into the 128B-swizzled K-major UMMA layout; the bit expansion is pure ALU
+//                           (multiply-spread), never touches HBM or a LUT; raw rows arrive through a cp.async ring
+//   warps 15, 6 issuers   : alternate tiles; per tile 2 x (8 + 1) tcgen05.mma.kind::i8 (N96 K32, A from TMEM) into a
 //                           double-buffered pair of TMEM accumulators, commits to mbarriers
-//   warps 0-7   epilogue  : tcgen05.ld 32 lanes x 96 columns, pack key = dot << 20 | (0xFFFFF - j) so a single
-//                           integer max carries both the best distance and the lowest-index tie-break
+//   warps 7-14  epilogue  : tcgen05.ld of the tile's 96 columns PACKED to 16 bits, TMEM buffer released right away, row
+//                           maximum by VIMNMX3.S16x2; per set one packed key  dot << 20 | (0xFFFFF - j)
 // Index tie-break folded into the GEMM: query bits expand to +-127, and one extra k-step multiplies a constant A
-// tile (a single 1 per row) with a constant B tile whose row jl holds (MT_BN-1 - jl).  The accumulator then reads
-// 127 * dot + (MT_BN-1 - jl): its plain integer maximum over a tile IS "largest dot, lowest train index", so the
-// epilogue is one VIMNMX3 per two columns instead of a multiply-and-pack per column.
+// tile (a single 1 per row) with a constant B tile whose row jl holds the code (MT_BN-1 - jl).  The accumulator then reads
+// 127 * dot + code: its plain integer maximum over a tile IS "largest dot, lowest train index", so the epilogue is one
+// packed max per four columns instead of a multiply-and-pack per column, and the winner's index is decoded from the code.
+// The same body runs as a single CTA per query tile (k_hamming_umma, cta_group::1, M = 128) and as a CTA PAIR that shares
+// every B tile (k_hamming_umma2, cta_group::2, M = 256; see "CTA pair" below).
 // TMEM map (512 columns): accumulators [buffer 0..1][A tile 0..1] x 96 columns at 0..383, A tiles 2 x 64 columns at 384.
 // Pipelines: smem stages (expanders <-> issuer) and TMEM accumulators (issuer <-> epilogue), all mbarrier based,
 // running continuously across set boundaries (persistent CTAs).  Train-row ranges can be split across CTAs (small
