@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(PYR_NT) k_pyr_down(const __grid_constant__ Geo
 //             score = max(A, -B) - 1 (corner iff > t).  Corners inside the output region go to a private NMS queue.
 //   phase C   3x3 NMS (strict >) of the queued corners on the shared score tile -> per-row bit masks
 //   phase D   ordered extraction of the bit masks (popc prefix) -> global per-row lists
-// Measured and dropped (tools/stage_times.py, DESIGN.md section 4): register-prefetched next tile with three barriers per chunk,
+// Measured and dropped (tools/stage_times.py, DESIGN.md section 8): register-prefetched next tile with three barriers per chunk,
 // persistent CTAs over (band, frame) items with static or ticket scheduling, a CTA-wide survivor queue that balances
 // phase B across warps, a u8 image tile (half the shared-memory wavefronts, more PRMT), 6-7 CTAs per SM by register cap.
 template <int R, int NT>
