@@ -19,6 +19,7 @@
 #include "orbx_geom.h"
 #include "orbx_kernels.cuh"
 #include "orbx_match.cuh"
+#include "orbx_fast.cuh"
 #include "orbx_map.cuh"
 #include <unordered_map>
 
@@ -31,6 +32,8 @@ const int8_t k_pattern_host[256 * 4] = {
 };
 
 constexpr int FAST_R = 16, FAST_NT = 256;
+constexpr int FAST_NWARP = 4;             // warps per CTA of k_fast_warp (independent units; 7 CTAs per SM by shared memory)
+static_assert(FAST_R == FW_R, "band height");
 constexpr int MAX_LANES = 4;               // concurrent frame-range pipelines of one device-resident extraction call
 constexpr int HOST_MAX_LANES = 12, HOST_DEFAULT_LANES = 8;         // host-buffer calls: more, shorter ranges shrink the un-overlapped head (first upload) and tail
 constexpr int LANE_MIN_FRAMES = 64;        // a lane must still fill the GPU on its own
@@ -55,6 +58,7 @@ struct orbx_ctx {
     uint64_t launches = 0;
 
     Geom geom{};             // geometry of the current frame size
+    FastMaps fmaps{};        // TMA tensor maps (x, y, frame) of the pyramid levels for the current geometry
     Geom geom_max{};         // geometry of (max_w, max_h): sizes the buffers
     int geom_w = 0, geom_h = 0;
     size_t tabs_len = 0;
@@ -229,6 +233,35 @@ void build_geom(const orbx_ctx* c, int w, int h, Geom* g, std::vector<uint32_t>*
     }
 }
 
+// One 3-D u8 tensor map (x = pitch, y = rows, z = frame) per pyramid level over the context's pyramid buffer: k_fast_warp's
+// image tiles are TMA boxes of FW_TP x FW_TR x 1 (out-of-range parts are zero-filled by the hardware).
+int build_fast_maps(orbx_ctx* c)
+{
+    typedef CUresult (*enc_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                              CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static enc_t enc = nullptr;
+    if (!enc) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn)
+            return fail(c, ORBX_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        enc = (enc_t)fn;
+    }
+    const Geom& g = c->geom;
+    memset(&c->fmaps, 0, sizeof c->fmaps);
+    for (int l = 0; l < g.nlevels; ++l) {
+        const LevelGeom& L = g.L[l];
+        if (L.nbands <= 0 || L.in_w <= 0) continue;
+        const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)L.h, (cuuint64_t)c->max_batch};
+        const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)g.pyr_frame};
+        const cuuint32_t box[3] = {FW_TP, FW_TR, 1}, es[3] = {1, 1, 1};
+        const CUresult r = enc(&c->fmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (uint8_t*)c->pyr.p + L.img_off, dims, strides, box, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(c, ORBX_E_CUDA, "cuTensorMapEncodeTiled failed for a pyramid level");
+    }
+    return ORBX_OK;
+}
+
 int set_geometry(orbx_ctx* c, int w, int h)
 {
     if (c->geom_w == w && c->geom_h == h) return ORBX_OK;
@@ -240,6 +273,7 @@ int set_geometry(orbx_ctx* c, int w, int h)
     if (rc) return rc;
     CU(cudaMemcpyAsync(c->tabs.p, tabs.data(), tabs.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));       // `tabs` is a local
+    if ((rc = build_fast_maps(c))) return rc;
     c->geom_w = w; c->geom_h = h;
     return ORBX_OK;
 }
@@ -304,7 +338,10 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, bool marks, int f0, int nb,
     }
     if (marks) stage_mark(c, 2);
     if (g.total_bands > 0) {
-        k_fast_bands<FAST_R, FAST_NT><<<dim3((unsigned)g.total_bands, B), FAST_NT, 0, st>>>(g, pyr, rowcnt, rowent);
+        static const int old_fast = getenv("ORBX_FAST_OLD") ? atoi(getenv("ORBX_FAST_OLD")) : 0;   // A/B timing only
+        if (old_fast) k_fast_bands<FAST_R, FAST_NT><<<dim3((unsigned)g.total_bands, B), FAST_NT, 0, st>>>(g, pyr, rowcnt, rowent);
+        else k_fast_warp<FAST_NWARP><<<dim3((unsigned)((g.total_bands + FAST_NWARP - 1) / FAST_NWARP), B), FAST_NWARP * 32, FAST_NWARP * FW_WARP_BYTES + 128, st>>>(
+                 g, c->fmaps, f0, rowcnt, rowent, status);
         ++c->launches;
     }
     // (Selection and blur were also tried as interleaved CTAs of one launch and as concurrent kernels on a side stream:
@@ -551,7 +588,8 @@ int orbx_create(orbx_ctx** out, int device, int nfeatures, float scale_factor, i
     if (cudaFuncSetAttribute(k_hamming_umma2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(k_hamming_umma2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(k_hamming_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(k_hamming_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES) != cudaSuccess)
+        cudaFuncSetAttribute(k_hamming_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_fast_warp<FAST_NWARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_NWARP * FW_WARP_BYTES + 128) != cudaSuccess)
         return bail(ORBX_E_CUDA);
     *out = c;
     return ORBX_OK;
