@@ -99,7 +99,11 @@ int orbx_detect_and_compute_device(orbx_ctx* ctx, const uint8_t* d_imgs, int bat
  * the image into pinned staging and queues upload, kernels and download, returning at once, so the host can run PnP / BA
  * of frame i (or decode frame i+2) while the GPU extracts frame i+1; collect blocks until the OLDEST submitted frame is
  * done and hands out its keypoints and descriptors (same results as orbx_detect_and_compute).  At most two frames in
- * flight (ORBX_E_BUSY beyond).  The collected frame also becomes "frame 0 of the last extraction" for orbx_track_match. */
+ * flight (ORBX_E_BUSY beyond).  The collected frame also becomes "frame 0 of the last extraction" for orbx_track_match /
+ * orbx_map_upsert_from_frame -- until a later orbx_submit_frame reuses the slot that holds it (the second submit after the
+ * collect): from then on those calls return ORBX_E_ARG instead of silently reading the newer frame, so call them between the
+ * collect and that submit (the order INTEGRATION.md shows).  A frame whose device-side status flag is set is never handed
+ * out: collect drops it and returns ORBX_E_INTERNAL, exactly as the synchronous call does. */
 int orbx_submit_frame(orbx_ctx* ctx, const uint8_t* img, int w, int h, size_t step, int channels);
 int orbx_collect_frame(orbx_ctx* ctx, orbx_keypoint* kps, uint8_t* desc, int cap, int* n_out);
 

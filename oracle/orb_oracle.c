@@ -16,7 +16,7 @@
  *
  * Parity pin: this restatement is checked bit-for-bit (every KeyPoint field, keypoint order, all
  * descriptor bytes, all DMatch fields) against the in-image OpenCV build (cv2 4.13.0) by
- * tests/test_oracle_vs_cv2.py and against the committed fixtures under tests/golden/
+ * tests/test_oracle.py and against the committed fixtures under tests/golden/
  * (generated from cv2 by tools/make_golden.py).
  *
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math -shared -fPIC  (see oracle/Makefile).

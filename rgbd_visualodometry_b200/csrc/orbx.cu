@@ -340,8 +340,16 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, bool marks, int f0, int nb,
     if (g.total_bands > 0) {
         static const int old_fast = getenv("ORBX_FAST_OLD") ? atoi(getenv("ORBX_FAST_OLD")) : 0;   // A/B timing only
         if (old_fast) k_fast_bands<FAST_R, FAST_NT><<<dim3((unsigned)g.total_bands, B), FAST_NT, 0, st>>>(g, pyr, rowcnt, rowent);
-        else k_fast_warp<FAST_NWARP><<<dim3((unsigned)((g.total_bands + FAST_NWARP - 1) / FAST_NWARP), B), FAST_NWARP * 32, FAST_NWARP * FW_WARP_BYTES + 128, st>>>(
-                 g, c->fmaps, f0, rowcnt, rowent, status);
+        else {
+            static const int nw = getenv("ORBX_FAST_NWARP") ? atoi(getenv("ORBX_FAST_NWARP")) : FAST_NWARP;   // experiments
+            auto launch = [&](auto tag) {
+                constexpr int NW = decltype(tag)::value;
+                static bool attr = false;
+                if (!attr) { cudaFuncSetAttribute(k_fast_warp<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, NW * FW_WARP_BYTES + 128); attr = true; }
+                k_fast_warp<NW><<<dim3((unsigned)((g.total_bands + NW - 1) / NW), B), NW * 32, NW * FW_WARP_BYTES + 128, st>>>(g, c->fmaps, f0, rowcnt, rowent, status);
+            };
+            if (nw == 2) launch(ic<2>{}); else if (nw == 7) launch(ic<7>{}); else if (nw == 1) launch(ic<1>{}); else launch(ic<FAST_NWARP>{});
+        }
         ++c->launches;
     }
     // (Selection and blur were also tried as interleaved CTAs of one launch and as concurrent kernels on a side stream:
@@ -630,7 +638,10 @@ int orbx_synchronize(orbx_ctx* c)
     CU(cudaSetDevice(c->device));
     const int b = c->last_batch;
     if (b > 0) CU(cudaMemcpyAsync(c->h_small, c->status.p, sizeof(int) * (size_t)b, cudaMemcpyDeviceToHost, c->stream));
+    int* h_m = c->h_small + 2 * (size_t)c->max_batch;        // the asynchronous matcher entry points defer their status words to this call
+    CU(cudaMemcpyAsync(h_m, c->mstatus.p, sizeof(int) * 16, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 16; ++i) if (h_m[i]) return match_timed_out(c);
     for (int i = 0; i < b; ++i)
         if (c->h_small[i]) return fail(c, ORBX_E_INTERNAL, "device-side status set for a frame");
     return ORBX_OK;
@@ -869,11 +880,15 @@ int orbx_match_hamming_sets(orbx_ctx* c, const uint8_t* query, int nq, const uin
 int orbx_filter_matches(orbx_match* m, int n, float ratio)
 {
     if (!m || n <= 0) return 0;
-    float mn = m[0].distance;
-    for (int i = 1; i < n; ++i) mn = std::min(mn, m[i].distance);
+    // records with trainIdx < 0 are the "empty train set" placeholders of the batched matchers (distance 0): they are neither
+    // matches nor candidates for the minimum -- same rule as the device filter k_filter_matches
+    bool any = false;
+    float mn = 0.0f;
+    for (int i = 0; i < n; ++i) if (m[i].trainIdx >= 0 && (!any || m[i].distance < mn)) { mn = m[i].distance; any = true; }
+    if (!any) return 0;
     const float mx = std::max(mn * ratio, 30.0f);
     int k = 0;
-    for (int i = 0; i < n; ++i) if (m[i].distance <= mx) m[k++] = m[i];
+    for (int i = 0; i < n; ++i) if (m[i].trainIdx >= 0 && m[i].distance <= mx) m[k++] = m[i];
     return k;
 }
 
@@ -1265,6 +1280,9 @@ int orbx_submit_frame(orbx_ctx* c, const uint8_t* img, int w, int h, size_t step
         (rc = ensure(c, a.d_counts, 32)))
         return rc;
     a.cap = cap;
+    if (c->view_desc == (const uint8_t*)a.d_desc.p) {         // the last collected frame lives in this slot: its descriptors are about to be
+        c->view_desc = nullptr; c->view_counts = nullptr; c->view_frames = 0;   // overwritten, so "frame 0 of the last extraction" no longer exists
+    }
     if ((rc = set_geometry(c, w, h))) return rc;
     for (int y = 0; y < h; ++y) memcpy(a.h_in + (size_t)y * dstep, img + (size_t)y * step, row);     // the caller's buffer is free on return
     // everything below is stream-ordered behind the previous frame: the shared per-frame workspace is reused safely
@@ -1301,6 +1319,11 @@ int orbx_collect_frame(orbx_ctx* c, orbx_keypoint* kps, uint8_t* desc, int cap, 
         a.busy = false; c->a_head ^= 1; --c->a_inflight;
         return fail(c, ORBX_E_CAPACITY, "internal capacity exceeded; use orbx_detect_and_compute for this frame");
     }
+    if (status) {                                             // device-side flag (selection fallback bound / TMA timeout): never hand out a possibly wrong frame
+        a.busy = false; c->a_head ^= 1; --c->a_inflight;
+        *n_out = 0;
+        return fail(c, ORBX_E_INTERNAL, "device-side status set for the collected frame");
+    }
     if (n > cap) return fail(c, ORBX_E_CAPACITY, "output capacity too small; n_out holds the needed count (frame still in flight)");
     memcpy(kps, a.h_out + 32, sizeof(orbx_keypoint) * (size_t)n);
     memcpy(desc, a.h_out + 32 + (size_t)a.cap * 28, (size_t)32 * n);
@@ -1309,7 +1332,6 @@ int orbx_collect_frame(orbx_ctx* c, orbx_keypoint* kps, uint8_t* desc, int cap, 
     a.busy = false;
     c->a_head ^= 1;
     --c->a_inflight;
-    (void)status;
     return ORBX_OK;
 }
 

@@ -51,6 +51,8 @@ constexpr int FW_OFF_MASK = FW_OFF_CQ + FW_CQ * 2;
 constexpr int FW_OFF_ROWCNT = FW_OFF_MASK + FW_R * 4 * 4;
 constexpr int FW_OFF_BAR = FW_OFF_ROWCNT + FW_R * 4;
 constexpr int FW_WARP_BYTES = (FW_OFF_BAR + 8 + 127) / 128 * 128;
+constexpr int FW_CLR = (FW_SR * FW_SP / 16 + 31) / 32;   // 128-bit stores per lane that clear the score tile
+static_assert(FW_CLR * 32 * 16 <= FW_OFF_CQ - FW_OFF_SCORE, "the score-tile clear may only spill into the (empty) quad / pixel queues");
 static_assert(FW_OFF_SCORE % 16 == 0 && FW_OFF_MASK % 4 == 0 && FW_OFF_BAR % 8 == 0, "layout");
 
 struct FastMaps { CUtensorMap m[ORBX_LEVELS_MAX]; };   // one (x, y, frame) u8 tensor map per pyramid level
@@ -66,7 +68,7 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned bar_s, unsigned bytes)
 }
 
 template <int NWARP>
-__global__ void __launch_bounds__(NWARP * 32) k_fast_warp(const __grid_constant__ Geom g, const __grid_constant__ FastMaps maps, int f0,
+__global__ void __launch_bounds__(NWARP * 32, 28 / NWARP) k_fast_warp(const __grid_constant__ Geom g, const __grid_constant__ FastMaps maps, int f0,
                                                           uint32_t* __restrict__ rowcnt, uint32_t* __restrict__ rowent, int* __restrict__ status)
 {
     extern __shared__ __align__(128) uint8_t fw_smem[];
@@ -121,12 +123,10 @@ __global__ void __launch_bounds__(NWARP * 32) k_fast_warp(const __grid_constant_
         const int need = ncols + 4;                          // score columns that matter: sx = 0 .. ncols + 3
         const unsigned xo = (unsigned)((ox0 - 7) & 15);
         const unsigned quad0_s = img_s + xo + 4u;            // tile byte of score column 0 in tile row 0
-        // ---- clear the score tile (18 x 128 B = 144 x 16 B)
+        // ---- clear the score tile: 160 x 16 B (the 16 x 16 B past its end fall into the quad / pixel queues, empty right now)
 #pragma unroll
-        for (int i = 0; i < (FW_SR * FW_SP / 16 + 31) / 32; ++i) {
-            const int j = i * 32 + lane;
-            if (j < FW_SR * FW_SP / 16) asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" :: "r"(score_s + 16u * j), "r"(0u) : "memory");
-        }
+        for (int i = 0; i < FW_CLR; ++i)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" :: "r"(score_s + 16u * (unsigned)(i * 32 + lane)), "r"(0u) : "memory");
         __syncwarp();
         if (!mbar_wait(bar_s, phase)) { if (lane == 0) atomicOr(&status[f], 2); return; }
         phase ^= 1u;
@@ -181,12 +181,12 @@ __global__ void __launch_bounds__(NWARP * 32) k_fast_warp(const __grid_constant_
             }
         };
 
-        // ---- phase A2 on quad entries [first, first + cnt): diagonal pairs, polarity aware; pixel entries pol << 15 | sy << 8 | sx
-        auto phaseA2 = [&](int first, int cnt) {
+        // ---- phase A2 on the cnt quad entries at shared address first_s: diagonal pairs, polarity aware; pixel entries pol << 15 | sy << 8 | sx
+        auto phaseA2 = [&](unsigned first_s, int cnt) {
             constexpr unsigned K = ((511u - T) << 16) | (511u - T);
             unsigned m8 = 0, ent = 0;
             if (lane < cnt) {
-                const unsigned e = lds_u16(qq_s + 2u * (unsigned)(first + lane));
+                const unsigned e = lds_u16(first_s + 2u * (unsigned)lane);
                 const unsigned sy = e >> 9, q4 = (e >> 2) & 0x7Cu;               // 4 * quad column
                 const unsigned a = quad0_s + (sy + 3u) * FW_TP + q4;
                 const unsigned up = a - 2 * FW_TP, dn = a + 2 * FW_TP;
@@ -230,27 +230,32 @@ __global__ void __launch_bounds__(NWARP * 32) k_fast_warp(const __grid_constant_
         // ---- phase A: one score row (128 pixels) per step
         {
             constexpr unsigned M7 = 0x7f7f7f7fu, KT = (127u - T) * 0x01010101u;
-            const bool live = 4 * lane < need;
+            unsigned livemask = 4 * lane < need ? 0x80808080u : 0u;            // lanes past the chunk's last needed column never flag
+            unsigned qq_full = qq_s + 64u;
+            livemask = __shfl_sync(0xffffffffu, livemask, lane);               // (identity shuffles: opaque to ptxas, which otherwise
+            qq_full = __shfl_sync(0xffffffffu, qq_full, lane);                 //  rematerialises both values in every row of the loop)
             unsigned a = quad0_s + 3u * FW_TP + 4u * lane;
+            unsigned ent = (unsigned)lane << 4;                                // quad entry: sy << 9 | quad column << 4 | pixel flags
+            unsigned qt = qq_s;                                                // byte address of the quad queue's tail
 #pragma unroll 2
-            for (int sy = 0; sy < nsr; ++sy, a += FW_TP) {
+            for (int sy = 0; sy < nsr; ++sy, a += FW_TP, ent += 512u) {
                 const unsigned c = lds_u32(a), pv = lds_u32(a - 4), nx = lds_u32(a + 4), n = lds_u32(a - 3 * FW_TP), s = lds_u32(a + 3 * FW_TP);
                 const unsigned e = __byte_perm(c, nx, 0x6543), w = __byte_perm(pv, c, 0x4321);
                 const unsigned dn = __vabsdiffu4(n, c), ds = __vabsdiffu4(s, c), de = __vabsdiffu4(e, c), dw = __vabsdiffu4(w, c);
                 // bit 7 of ((d & 0x7f) + (127 - t)) | d  <=>  d > t, per byte, no carries between bytes
                 const unsigned ns = ((dn & M7) + KT) | dn | ((ds & M7) + KT) | ds;
                 const unsigned ew = ((de & M7) + KT) | de | ((dw & M7) + KT) | dw;
-                const unsigned r = ns & ew & 0x80808080u;
-                const unsigned nib = live ? (r * 0x00204081u) >> 28 : 0u;       // bit i = pixel i of the quad
+                const unsigned nib = ((ns & ew & livemask) * 0x00204081u) >> 28;   // bit i = pixel i of the quad
                 const unsigned any = __ballot_sync(0xffffffffu, nib != 0u);
-                if (nib) sts_u16(qq_s + 2u * (unsigned)(nq + __popc(any & lt)), ((unsigned)sy << 9) | ((unsigned)lane << 4) | nib);
-                nq += __popc(any);
-                if (nq >= 32) { __syncwarp(); phaseA2(nq - 32, 32); nq -= 32; }
+                if (nib) sts_u16(qt + 2u * (unsigned)__popc(any & lt), ent | nib);
+                qt += 2u * (unsigned)__popc(any);
+                if (qt >= qq_full) { __syncwarp(); qt -= 64u; phaseA2(qt, 32); }
             }
+            nq = (int)(qt - qq_s) >> 1;
         }
         // ---- drain
         __syncwarp();
-        if (nq > 0) phaseA2(0, nq);
+        if (nq > 0) phaseA2(qq_s, nq);
         if (np > 0) { phaseB(0, np); }
         __syncwarp();                                        // every lane is done with the image tile
         overflow_any |= overflow;

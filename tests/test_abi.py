@@ -70,6 +70,23 @@ def test_filter_matches_host_glue(oracle):
     assert len(orb.filter_matches(np.zeros(0, orb.DMATCH_DTYPE))) == 0
 
 
+def test_filter_matches_skips_empty_frame_placeholders(oracle):
+    """The batched matchers emit trainIdx = -1, distance = 0 for a frame without keypoints; such a record is neither a match
+    nor a candidate for the minimum (a shim would otherwise index keypointsCurr_[-1], src/frontend.cpp:208-209)."""
+    from rgbd_visualodometry_b200 import orb
+    from rgbd_visualodometry_b200.synth import synth_descriptors, synth_map_queries
+    t = synth_descriptors(300, 5)
+    m = oracle.match_hamming(synth_map_queries(t, 200, 6), t).astype(orb.DMATCH_DTYPE)
+    want = oracle.filter_matches(m, 2.0)
+    holes = m.copy()
+    holes = np.insert(holes, [0, 50, 200], np.array([(7, -1, 0, 0.0)], orb.DMATCH_DTYPE))
+    got = orb.filter_matches(holes, 2.0)
+    assert (got["trainIdx"] >= 0).all()
+    assert got[["trainIdx", "distance"]].tobytes() == want.astype(orb.DMATCH_DTYPE)[["trainIdx", "distance"]].tobytes()
+    only = np.array([(0, -1, 0, 0.0), (1, -1, 0, 0.0)], orb.DMATCH_DTYPE)
+    assert len(orb.filter_matches(only, 2.0)) == 0
+
+
 def test_product_never_imports_oracle():
     """The oracle is test infrastructure: nothing under the package may reference it (or cv2)."""
     pkg = os.path.join(ROOT, "rgbd_visualodometry_b200")
