@@ -20,6 +20,7 @@
 #include "orbx_kernels.cuh"
 #include "orbx_match.cuh"
 #include "orbx_fast.cuh"
+#include "orbx_pyr.cuh"
 #include "orbx_map.cuh"
 #include <unordered_map>
 
@@ -59,6 +60,7 @@ struct orbx_ctx {
 
     Geom geom{};             // geometry of the current frame size
     FastMaps fmaps{};        // TMA tensor maps (x, y, frame) of the pyramid levels for the current geometry
+    PyrMaps pmaps{};         // ... of every level as the SOURCE of the next one (k_pyr_tma boxes)
     Geom geom_max{};         // geometry of (max_w, max_h): sizes the buffers
     int geom_w = 0, geom_h = 0;
     size_t tabs_len = 0;
@@ -228,6 +230,29 @@ void build_geom(const orbx_ctx* c, int w, int h, Geom* g, std::vector<uint32_t>*
                     span = std::max(span, (int)((*tabs)[L.xtab + xl] & 0xffffu) - a);
                 }
                 g->L[l].xspan = span;
+                // k_pyr_tma: a lane's 4 outputs must read at most 7 consecutive source bytes, and the source box of a
+                // (128-column tile, 16-row strip) must fit a TMA box (<= 256 per dimension, 16-byte aligned first column)
+                LevelGeom& D = g->L[l];
+                const uint32_t* xt = tabs->data() + D.xtab;
+                const uint32_t* yt = tabs->data() + D.ytab;
+                int quad_span = 0, bw = 0, bh = 0;
+                for (int x = 0; x < D.w; x += 4)
+                    quad_span = std::max(quad_span, (int)(xt[std::min(x + 3, D.w - 1)] & 0xffffu) - (int)(xt[x] & 0xffffu));
+                D.pt_ncx = (D.pitch + PT_CW - 1) / PT_CW;
+                for (int cx = 0; cx < D.pt_ncx; ++cx) {
+                    const int xl = std::min(cx * PT_CW + PT_CW - 1, D.w - 1);
+                    const int X0 = (int)(xt[cx * PT_CW] & 0xffffu) & ~15;
+                    bw = std::max(bw, (int)(xt[xl] & 0xffffu) + 2 - X0);
+                }
+                const int nstrips = (D.h + PT_RH - 1) / PT_RH;
+                for (int st = 0; st < nstrips; ++st) {
+                    const int ye = std::min(st * PT_RH + PT_RH, D.h);
+                    bh = std::max(bh, std::min((int)(yt[ye - 1] & 0xffffu) + 1, S.h - 1) - (int)(yt[st * PT_RH] & 0xffffu) + 1);
+                }
+                D.pt_bw = (int)round_up((size_t)bw, 16); D.pt_bh = bh;
+                D.pt_k = 4;
+                D.pt_ntask = D.pt_ncx * ((nstrips + D.pt_k - 1) / D.pt_k);
+                D.pt_ok = quad_span <= 6 && D.pt_bw <= 256 && D.pt_bh <= 256 && PT_NWARP * pt_warp_bytes(D.pt_bw, D.pt_bh) + 128 <= 160 * 1024;
             }
         }
     }
@@ -258,6 +283,18 @@ int build_fast_maps(orbx_ctx* c)
         const CUresult r = enc(&c->fmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (uint8_t*)c->pyr.p + L.img_off, dims, strides, box, es,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(c, ORBX_E_CUDA, "cuTensorMapEncodeTiled failed for a pyramid level");
+    }
+    memset(&c->pmaps, 0, sizeof c->pmaps);
+    for (int l = 1; l < g.nlevels; ++l) {
+        const LevelGeom& D = g.L[l];
+        const LevelGeom& S = g.L[l - 1];
+        if (!D.pt_ok) continue;
+        const cuuint64_t dims[3] = {(cuuint64_t)S.pitch, (cuuint64_t)S.h, (cuuint64_t)c->max_batch};
+        const cuuint64_t strides[2] = {(cuuint64_t)S.pitch, (cuuint64_t)g.pyr_frame};
+        const cuuint32_t box[3] = {(cuuint32_t)D.pt_bw, (cuuint32_t)D.pt_bh, 1}, es[3] = {1, 1, 1};
+        const CUresult r = enc(&c->pmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (uint8_t*)c->pyr.p + S.img_off, dims, strides, box, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(c, ORBX_E_CUDA, "cuTensorMapEncodeTiled failed for a pyramid source level");
     }
     return ORBX_OK;
 }
@@ -331,7 +368,11 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, bool marks, int f0, int nb,
             if (g.L[l].w <= 0 || g.L[l].h <= 0) continue;
             const int nitems = (g.L[l].pitch / 8) * ((g.L[l].h + PYR_RH - 1) / PYR_RH);     // (column octet, row strip) work items
             const dim3 grd((unsigned)((nitems + PYR_NT - 1) / PYR_NT), B);
-            if (g.L[l].xspan <= 7) k_pyr_down<false><<<grd, PYR_NT, 0, st>>>(g, l, pyr, tabs);
+            static const int old_pyr = getenv("ORBX_PYR_OLD") ? atoi(getenv("ORBX_PYR_OLD")) : 0;   // A/B timing only
+            if (g.L[l].pt_ok && !old_pyr)
+                k_pyr_tma<<<dim3((unsigned)((g.L[l].pt_ntask + PT_NWARP - 1) / PT_NWARP), B), PT_NWARP * 32,
+                            PT_NWARP * pt_warp_bytes(g.L[l].pt_bw, g.L[l].pt_bh) + 128, st>>>(g, c->pmaps.m[l], l, f0, (uint8_t*)c->pyr.p, tabs, status);
+            else if (g.L[l].xspan <= 7) k_pyr_down<false><<<grd, PYR_NT, 0, st>>>(g, l, pyr, tabs);
             else                   k_pyr_down<true><<<grd, PYR_NT, 0, st>>>(g, l, pyr, tabs);
             ++c->launches;
         }
@@ -597,7 +638,8 @@ int orbx_create(orbx_ctx** out, int device, int nfeatures, float scale_factor, i
         cudaFuncSetAttribute(k_hamming_umma2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(k_hamming_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(k_hamming_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute(k_fast_warp<FAST_NWARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_NWARP * FW_WARP_BYTES + 128) != cudaSuccess)
+        cudaFuncSetAttribute(k_fast_warp<FAST_NWARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_NWARP * FW_WARP_BYTES + 128) != cudaSuccess ||
+        cudaFuncSetAttribute(k_pyr_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess)
         return bail(ORBX_E_CUDA);
     *out = c;
     return ORBX_OK;

@@ -35,6 +35,9 @@ struct LevelGeom {
     int blur0, nblur, blur_cgs;  // blur tiles: first tile index, tile count (= column groups x strip groups), column groups
     int blur_rh;              // output rows per blur strip: a multiple of 7 chosen per level so the strips fit the level tightly
     uint32_t xtab, ytab;      // offsets (u32 units) of the INTER_LINEAR_EXACT tap tables: i0 | c1 << 16
+    int pt_ok;                // 1: the TMA pyramid kernel (k_pyr_tma) produces this level; 0: the register-window kernel k_pyr_down
+    int pt_ncx, pt_k, pt_ntask;   // column tiles of 128 outputs, strips per warp task, warp tasks per frame
+    int pt_bw, pt_bh;         // TMA box (bytes x rows) of source level l-1 that covers one (column tile, strip)
     int xspan;                // max over 4-column groups of (left tap of the group's last column) - (its aligned first byte): <= 7 narrow kernel, <= 11 wide
     unsigned long long img_off;   // bytes, inside the frame's pyr block
     unsigned long long cnt_off;   // u32 units, inside the frame's rowcnt block

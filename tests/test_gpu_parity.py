@@ -221,6 +221,119 @@ def test_match_pair_kernel_ragged_sets(orbmod, oracle):
     ctx.close()
 
 
+def _check_knn2(got_best, got_second, q, train, oracle, what):
+    """knnMatch(k = 2) records of one train set against the oracle: [best, second] by (distance, index); fewer than two
+    train rows -> the missing records carry trainIdx = -1."""
+    n = len(train)
+    if n == 0:
+        assert (got_best["trainIdx"] == -1).all() and (got_second["trainIdx"] == -1).all(), f"{what}: empty set"
+        return
+    ref = oracle.match_hamming_knn2(q, train)
+    assert got_best.tobytes() == ref[:, 0].tobytes(), f"{what}: best"
+    if n >= 2:
+        assert got_second.tobytes() == ref[:, 1].tobytes(), f"{what}: second"
+    else:
+        assert (got_second["trainIdx"] == -1).all(), f"{what}: second of a one-row set"
+
+
+def test_match_pair_kernel_knn2_ragged_sets(orbmod, oracle):
+    """The CTA-pair kernel WITH the fused second-minimum (k_hamming_umma2<true>, knnMatch k = 2): 42 ragged train sets x 1203
+    queries (6 padded query tiles x 42 sets >= 148 pairs selects it), sizes on every tile / chunk boundary, the set's last row
+    duplicated earlier (ties across the padded last tile -> lowest index first, the copy second)."""
+    import torch
+    from rgbd_visualodometry_b200.synth import synth_descriptors, synth_map_queries
+    cap, nq = 300, 5 * 256 - 77
+    sizes = [0, 1, 2, 3, 15, 16, 17, 31, 32, 33, 47, 48, 49, 63, 64, 65, 95, 96, 97, 98, 191, 192, 193, 255, 299, 300]
+    sizes = sizes + [int(x) for x in np.random.default_rng(6).integers(0, cap + 1, 42 - len(sizes))]
+    nsets = len(sizes)
+    assert 6 * nsets >= 148
+    trains = np.stack([synth_descriptors(cap, 1900 + i) for i in range(nsets)])
+    for i, n in enumerate(sizes):
+        if n >= 3:
+            trains[i, n - 1] = trains[i, n // 2]
+    q = synth_map_queries(trains[1 + int(np.argmax(sizes[1:]))], nq, 72)
+    q[:50] = trains[25, 150:200]                       # exact hits whose duplicate-free runner-up is a real second neighbour
+    ctx = orbmod.Context(1, 1.2, 1, 64, 64, 1)
+    dq = torch.from_numpy(q).cuda(); dt = torch.from_numpy(trains).cuda()
+    dn = torch.tensor(sizes, dtype=torch.int32, device="cuda")
+    best = torch.zeros((nsets, nq, 4), dtype=torch.int32, device="cuda")
+    second = torch.zeros((nsets, nq, 4), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.match_device_ragged(dq.data_ptr(), nq, dt.data_ptr(), cap, dn.data_ptr(), nsets, best.data_ptr(), second.data_ptr())
+    ctx.synchronize()
+    gb = best.cpu().numpy().view(orbmod.DMATCH_DTYPE).reshape(nsets, nq)
+    gs = second.cpu().numpy().view(orbmod.DMATCH_DTYPE).reshape(nsets, nq)
+    for s, n in enumerate(sizes):
+        _check_knn2(gb[s], gs[s], q, trains[s, :n], oracle, f"pair knn2 set {s} ({n} rows)")
+    ctx.close()
+
+
+def test_match_single_cta_knn2_batched(orbmod, oracle):
+    """The single-CTA kernel with the fused second-minimum over SEVERAL train sets (d_second with nsets > 1): uniform sets through
+    orbx_match_hamming_device and ragged ones through orbx_match_hamming_sets (host buffers)."""
+    import torch
+    from rgbd_visualodometry_b200.synth import synth_descriptors, synth_map_queries
+    nsets, nt, nq = 3, 700, 1300                        # 6 query tiles x 3 sets < 148: the single-CTA kernel
+    trains = np.stack([synth_descriptors(nt, 160 + i) for i in range(nsets)])
+    trains[1, 650:700] = trains[1, 100:150]             # duplicated rows: best = first copy, second = its twin at distance 0
+    q = synth_map_queries(trains[1], nq, 170)
+    ctx = orbmod.Context(1, 1.2, 1, 64, 64, 1)
+    dq = torch.from_numpy(q).cuda(); dt = torch.from_numpy(trains).cuda()
+    best = torch.zeros((nsets, nq, 4), dtype=torch.int32, device="cuda")
+    second = torch.zeros((nsets, nq, 4), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.match_device(dq.data_ptr(), nq, dt.data_ptr(), nt, nsets, best.data_ptr(), second.data_ptr())
+    ctx.synchronize()
+    gb = best.cpu().numpy().view(orbmod.DMATCH_DTYPE).reshape(nsets, nq)
+    gs = second.cpu().numpy().view(orbmod.DMATCH_DTYPE).reshape(nsets, nq)
+    for s in range(nsets):
+        _check_knn2(gb[s], gs[s], q, trains[s], oracle, f"single-CTA knn2 set {s}")
+    counts = np.array([700, 1, 333], np.int32)
+    hb, hs = ctx.match_sets(q, trains, counts, knn2=True)
+    for s in range(nsets):
+        _check_knn2(hb[s], hs[s], q, trains[s, :counts[s]], oracle, f"match_sets knn2 set {s}")
+    ctx.close()
+
+
+def _device_batch_vs_oracle(orbmod, oracle, w, h, nfeat, distinct, batch, shapes):
+    """A device-resident batch (BASELINE configs 4 / 5 shapes): `distinct` different frames repeated to `batch`, every frame's
+    records compared with the oracle's result for its source frame."""
+    import torch
+    from rgbd_visualodometry_b200.synth import synth_frame
+    cap = 2 * nfeat
+    src = [synth_frame(h, w, 7000 + i, shapes=shapes) for i in range(distinct)]
+    frames = np.stack([src[i % distinct] for i in range(batch)])
+    ctx = orbmod.Context(nfeat, 1.2, 8, w, h, batch)
+    d_in = torch.from_numpy(frames).cuda()
+    d_k = torch.zeros((batch, cap, 7), dtype=torch.float32, device="cuda")
+    d_d = torch.zeros((batch, cap, 32), dtype=torch.uint8, device="cuda")
+    d_n = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.detect_and_compute_device(d_in.data_ptr(), batch, w, h, 3 * w, 3 * w * h, 3, d_k.data_ptr(), d_d.data_ptr(), cap, d_n.data_ptr())
+    ctx.synchronize()
+    n = d_n.cpu().numpy(); k = d_k.cpu().numpy().view(orbmod.KP_DTYPE).reshape(batch, cap); d = d_d.cpu().numpy()
+    ref = [oracle.detect_and_compute(fr, nfeat) for fr in src]
+    for i in range(batch):
+        ko, do = ref[i % distinct]
+        _assert_kp_equal(k[i, :n[i]], d[i, :n[i]], ko, do, f"{w}x{h} device frame {i}")
+    ctx.close()
+
+
+def test_orb_device_batch_1080p(orbmod, oracle):
+    """BASELINE config 4: 1920x1080, 2000 features, a device-resident batch of 8 distinct frames, every frame vs the oracle."""
+    _device_batch_vs_oracle(orbmod, oracle, 1920, 1080, 2000, 8, 8, 300)
+
+
+def test_orb_device_batch_1080p_lanes(orbmod, oracle):
+    """The same geometry through the multi-stream lane split (batch >= 3 x 64): 192 frames, 12 distinct, all 192 checked."""
+    _device_batch_vs_oracle(orbmod, oracle, 1920, 1080, 2000, 12, 192, 300)
+
+
+def test_orb_device_batch_4k(orbmod, oracle):
+    """BASELINE config 5: 3840x2160, 5000 features, a device-resident batch of 3 distinct frames, every frame vs the oracle."""
+    _device_batch_vs_oracle(orbmod, oracle, 3840, 2160, 5000, 3, 3, 400)
+
+
 def test_orb_device_resident_full_size(orbmod, oracle):
     """BASELINE config 2 shape: a device-resident batch of 640x480 frames, 1000 features; every frame checked."""
     import torch
