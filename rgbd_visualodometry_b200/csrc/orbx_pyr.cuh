@@ -89,9 +89,8 @@ __global__ void __launch_bounds__(PT_NWARP * 32) k_pyr_tma(const __grid_constant
             tma_load_tile_3d(base_s + b * bufb, &map, X0, s_first, f0 + f, bar_s + 8u * b);
         }
     };
-    // horizontal pass of box row r
-    auto hpass = [&](unsigned buf_s, int r, unsigned* h) {
-        const unsigned ad = buf_s + (unsigned)(r * bw) + a_off;
+    // horizontal pass of the box row whose (lane-adjusted) shared address is ad
+    auto hpass = [&](unsigned ad, unsigned* h) {
         const unsigned w0 = lds_u32(ad), w1 = lds_u32(ad + 4u), w2 = lds_u32(ad + 8u);
         const unsigned lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
 #pragma unroll
@@ -100,6 +99,8 @@ __global__ void __launch_bounds__(PT_NWARP * 32) k_pyr_tma(const __grid_constant
 
     request(strip0, 0u);
     unsigned par0 = 0u, par1 = 0u;
+    const int pitch = D.pitch, sh1 = S.h - 1;
+    const bool store = x < pitch;
     uint8_t* const dst0 = pyr + (size_t)(f0 + f) * g.pyr_frame + D.img_off + x;   // (pyr is the whole buffer: TMA coordinates are absolute frames)
 #pragma unroll 1
     for (int strip = strip0; strip < strip1; ++strip) {
@@ -108,32 +109,32 @@ __global__ void __launch_bounds__(PT_NWARP * 32) k_pyr_tma(const __grid_constant
         const unsigned buf_s = base_s + b * bufb;
         if (!mbar_wait(bar_s + 8u * b, b ? par1 : par0)) { if (lane == 0) atomicOr(&status[f], 2); return; }
         if (b) par1 ^= 1u; else par0 ^= 1u;
-        const int ys = strip * PT_RH, ye = min(ys + PT_RH, D.h);
-        uint32_t ty = __ldg(ytab + ys), ty_next = ys + 1 < ye ? __ldg(ytab + ys + 1) : 0u;
-        const int s_first = (int)(ty & 0xffffu);
-        int have = -1;                                                   // source row whose horizontal pass sits in hp
-        unsigned hp[4] = {0u, 0u, 0u, 0u}, hc[4];
-        uint8_t* dst = dst0 + (size_t)ys * D.pitch;
-#pragma unroll 1
-        for (int y = ys; y < ye; ++y, dst += D.pitch) {
-            const int s0 = (int)(ty & 0xffffu), s1 = min(s0 + 1, S.h - 1);
+        const int ys = strip * PT_RH, nr = min(PT_RH, D.h - ys);
+        // vertical taps of the strip's rows: lane r holds row ys + r, handed out by one shuffle per row
+        const uint32_t ty_all = lane < nr ? __ldg(ytab + ys + lane) : 0u;
+        const int s_first = (int)(__shfl_sync(0xffffffffu, ty_all, 0) & 0xffffu);
+        const unsigned row0_s = buf_s + a_off - (unsigned)(s_first * bw);  // box row of source row s at row0_s + s * bw
+        int have = -1;                                                   // source row whose horizontal pass sits in the "top" registers
+        unsigned hA[4], hB[4];
+        uint8_t* dst = dst0 + (size_t)ys * pitch;
+        // one output row: T = horizontal pass of its upper source row (already there unless the mapping skipped a row), N = lower
+        auto row = [&](int r, unsigned* T, unsigned* N) {
+            const uint32_t ty = __shfl_sync(0xffffffffu, ty_all, r);
+            const int s0 = (int)(ty & 0xffffu), s1 = min(s0 + 1, sh1);
             const unsigned cy1 = ty >> 16, cy0 = 256u - cy1;
-            ty = ty_next;
-            if (y + 2 < ye) ty_next = __ldg(ytab + y + 2);
-            if (s0 != have) hpass(buf_s, s0 - s_first, hp);              // warp-uniform
-            if (s1 != s0) hpass(buf_s, s1 - s_first, hc);
-            else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) hc[k] = hp[k];               // bottom row clamps: both taps read the last source row
-            }
+            if (s0 != have) hpass(row0_s + (unsigned)(s0 * bw), T);      // warp-uniform
+            hpass(row0_s + (unsigned)(s1 * bw), N);                      // (the image's bottom row clamps: s1 == s0, taken twice -- no branch)
             unsigned v[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = hp[k] * cy0 + (hc[k] * cy1 + 32768u);
-            if (x < D.pitch) *reinterpret_cast<uint32_t*>(dst) = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) hp[k] = hc[k];
+            for (int k = 0; k < 4; ++k) v[k] = T[k] * cy0 + (N[k] * cy1 + 32768u);
+            if (store) *reinterpret_cast<uint32_t*>(dst) = __byte_perm(__byte_perm(v[0], v[1], 0x0062), __byte_perm(v[2], v[3], 0x0062), 0x5410);
+            dst += pitch;
             have = s1;
-        }
+        };
+        int r = 0;
+#pragma unroll 1
+        for (; r + 1 < nr; r += 2) { row(r, hA, hB); row(r + 1, hB, hA); }   // ping-pong without register copies
+        if (r < nr) row(r, hA, hB);
         __syncwarp();                                                    // every lane is done with this box
     }
 }
