@@ -26,24 +26,61 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H, NFEAT, NLEVELS, SCALE = 640, 480, 1000, 8, 1.2
+W, H, NFEAT, NLEVELS, SCALE = 640, 480, 1000, 8, 1.2       # the default workload (BASELINE.json configs[1]); kept as module constants for tools/
 BATCH, MAP_M, CAP, MATCHES_PER_FRAME = 256, 2048, 1280, 2
 METRIC = "orb_extract_match_frames_per_s_640x480"
 LEVEL_PIXELS_VGA = 950532          # sum of the 8 pyramid levels of a 640x480 frame
+PROFILE_TAG = "r2_v3"              # profiles/<tag>_ncu_metrics.json / _ncu_dram_traffic.json: the committed ncu capture the roofline keys quote
+INT8_PEAK_FILE = "profiles/r2_int8_peak.json"
+
+# BASELINE.json configs[0..4] as `--config c1 .. c5` (the driver runs the default, c2).  frames: how the synthetic batch is made;
+# ref_sample / cpu_sample: frames per step of the reference arm / of the in-line cpu_baseline (bounded: the CPU needs 2 ms .. 250 ms per frame).
+CONFIGS = {
+    "c1": dict(w=640, h=480, nfeat=500, batch=256, map_m=1500, frames="sequence", nbase=256, ref_sample=256, cpu_sample=64,
+               what="run_vo front-end pattern (config/default.yaml: 500 features) on a synthetic TUM-fr1-shaped 640x480 RGB-D sequence"),
+    "c2": dict(w=W, h=H, nfeat=NFEAT, batch=BATCH, map_m=MAP_M, frames="distinct", nbase=32, ref_sample=256, cpu_sample=64,
+               what="batched ORB extraction 640x480 BGR"),
+    "c3": dict(w=640, h=480, nfeat=2000, batch=32, map_m=100000, frames="distinct", nbase=32, ref_sample=2, cpu_sample=2,
+               what="frame<->map Hamming matching sweep: maps of 1k..100k descriptors vs 32 frames' 2000 descriptors"),
+    "c4": dict(w=1920, h=1080, nfeat=2000, batch=64, map_m=10000, frames="distinct", nbase=16, ref_sample=64, cpu_sample=32,
+               what="1920x1080 ORB extraction + matching"),
+    "c5": dict(w=3840, h=2160, nfeat=5000, batch=64, map_m=10000, frames="distinct", nbase=8, ref_sample=16, cpu_sample=16, total_frames=10000,
+               what="3840x2160 long synthetic sequence (10k frames per run, cycling 64 device-resident frames per GPU)"),
+}
+C3_SWEEP = (1000, 2000, 5000, 10000, 20000, 50000, 100000)
 
 
-def make_frames(batch: int, seed: int) -> np.ndarray:
-    """`batch` distinct frames: 32 independently generated synthetic frames, the rest cheap distinct variants
-    (circular shifts + flips) of them."""
-    from rgbd_visualodometry_b200.synth import synth_frame
-    nbase = min(batch, 32)
-    base = [synth_frame(H, W, seed * 100003 + i) for i in range(nbase)]
+def metric_name(cfg):
+    return METRIC if (cfg["w"], cfg["h"]) == (W, H) and cfg is not CONFIGS["c3"] else (
+        "hamming_match_frames_per_s_map100k_x_2k" if cfg is CONFIGS["c3"] else f"orb_extract_match_frames_per_s_{cfg['w']}x{cfg['h']}")
+
+
+def cap_of(cfg):
+    return CAP if cfg["nfeat"] == NFEAT else int(cfg["nfeat"] * 1.25) + 64
+
+
+def workload_string(cfg):
+    """The workload both arms run, word for word the same in both JSON lines."""
+    if cfg is CONFIGS["c3"]:
+        return f"{cfg['what']}; value = 2 brute-force Hamming matches of a {cfg['map_m']}-descriptor map per frame (exact BFMatcher(NORM_HAMMING).match)"
+    return (f"{cfg['what']}, {cfg['nfeat']} features, scale {SCALE}, {NLEVELS} levels + {MATCHES_PER_FRAME} Hamming matches/frame "
+            f"(map {cfg['map_m']} x frame descriptors)")
+
+
+def make_frames(batch: int, seed: int, w: int = W, h: int = H, nbase: int = 32, kind: str = "distinct") -> np.ndarray:
+    """`batch` distinct frames: `nbase` independently generated synthetic frames, the rest cheap distinct variants
+    (circular shifts + flips) of them; kind "sequence": consecutive views of one slowly moving camera (TUM-fr1 shape)."""
+    from rgbd_visualodometry_b200.synth import synth_frame, synth_sequence
+    if kind == "sequence":
+        return np.stack([c for c, _ in synth_sequence(h, w, batch, seed=seed)])
+    nbase = min(batch, nbase)
+    base = [synth_frame(h, w, seed * 100003 + i) for i in range(nbase)]
     rng = np.random.default_rng(seed)
-    out = np.empty((batch, H, W, 3), np.uint8)
+    out = np.empty((batch, h, w, 3), np.uint8)
     for i in range(batch):
         f = base[i % nbase]
         if i >= nbase:
-            f = np.roll(f, (int(rng.integers(1, H)), int(rng.integers(1, W))), axis=(0, 1))
+            f = np.roll(f, (int(rng.integers(1, h)), int(rng.integers(1, w))), axis=(0, 1))
             if (i // nbase) & 1:
                 f = f[:, ::-1]
         out[i] = f
@@ -89,69 +126,116 @@ class ClockSampler:
                 "samples": len(sm), "period_ms": 100}
 
 
-def cpu_reference_fps(frames: np.ndarray, map_desc: np.ndarray, threads: int, repeats: int = 1):
-    """OpenCV on the host: frame-parallel worker threads (cv2 releases the GIL; ORB itself does not scale with
-    cv threads), each doing the front-end's per-frame pattern: 1 detectAndCompute + 2 BFMatcher.match."""
+def cpu_reference_fps(frames: np.ndarray, map_desc: np.ndarray, threads: int, nfeat: int = NFEAT, extract: bool = True, train=None):
+    """OpenCV on the host, the reference's own operators in the front-end's per-frame pattern (1 detectAndCompute + 2
+    BFMatcher.match, src/frontend.cpp:98-108): frame-parallel worker threads, each with its own operator objects and
+    cv2.setNumThreads(1) (cv2 releases the GIL; ORB itself does not scale with cv threads).  extract = False (config 3): the
+    matches only, against precomputed train sets.  Returns (frames/s, seconds) of one pass."""
     import cv2
     cv2.setNumThreads(1)
-    n = len(frames)
+    n = len(frames) if extract else len(train)
 
     def work(idx):
-        orb = cv2.ORB_create(NFEAT, SCALE, NLEVELS)
+        orb = cv2.ORB_create(nfeat, SCALE, NLEVELS)
         bf = cv2.BFMatcher(cv2.NORM_HAMMING)
         for i in idx:
-            _, d = orb.detectAndCompute(frames[i], None)
+            d = orb.detectAndCompute(frames[i], None)[1] if extract else train[i]
             for _ in range(MATCHES_PER_FRAME):
                 bf.match(map_desc, d)
 
-    best = None
-    for _ in range(repeats):
-        parts = [list(range(t, n, threads)) for t in range(threads)]
-        ths = [threading.Thread(target=work, args=(p,)) for p in parts]
+    if not extract:                                      # BFMatcher.match IS parallelised inside OpenCV: one worker, all cv threads
+        cv2.setNumThreads(threads)
         t0 = time.perf_counter()
-        for t in ths:
-            t.start()
-        for t in ths:
-            t.join()
+        work(range(n))
+        dt = time.perf_counter() - t0
+        cv2.setNumThreads(1)
+        return n / dt, dt
+    parts = [list(range(t, n, threads)) for t in range(threads)]
+    ths = [threading.Thread(target=work, args=(p,)) for p in parts if p]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    return n / dt, dt
+
+
+def flann_lsh_ms(map_desc: np.ndarray, train: np.ndarray, reps: int = 3):
+    """What src/frontend.cpp:33,187 literally runs: cv::FlannBasedMatcher(LshIndexParams(5, 10, 2)).match -- approximate and
+    randomly seeded, so not a parity target; timed once beside the exact matcher."""
+    import cv2
+    best = None
+    for _ in range(reps):
+        fl = cv2.FlannBasedMatcher(dict(algorithm=6, table_number=5, key_size=10, multi_probe_level=2), {})
+        t0 = time.perf_counter()
+        fl.match(map_desc, train)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return n / best, best
+    return best * 1e3
 
 
-def run_reference(args, rank: int, world: int):
+def reference_inputs(cfg, sample: int, seed: int = 0):
+    """Frames (or, config 3, train sets) and the map the reference arm works on: the first `sample` frames of rank 0's batch."""
+    from rgbd_visualodometry_b200.synth import synth_descriptors, synth_map_queries
+    if cfg is CONFIGS["c3"]:
+        train = [synth_descriptors(cfg["nfeat"], 40 + i) for i in range(sample)]
+        return None, train, synth_map_queries(train[0], cfg["map_m"], 41)
+    import cv2
+    frames = make_frames(cfg["batch"], seed, cfg["w"], cfg["h"], cfg["nbase"], cfg["frames"])[:sample]
+    d0 = cv2.ORB_create(cfg["nfeat"], SCALE, NLEVELS).detectAndCompute(frames[0], None)[1]
+    return frames, None, synth_map_queries(d0, cfg["map_m"], 17)
+
+
+def run_reference(args, cfg, rank: int, world: int):
     if rank != 0:
         return
     try:
-        import cv2  # noqa: F401
+        import cv2
     except Exception as e:  # pragma: no cover
         emit({"impl": "reference", "unavailable": f"cv2 not importable: {e}"})
         return
     threads = os.cpu_count() or 1
-    sample = 64
-    frames = make_frames(sample, 0)
-    import cv2
-    _, d0 = cv2.ORB_create(NFEAT, SCALE, NLEVELS).detectAndCompute(frames[0], None)
-    from rgbd_visualodometry_b200.synth import synth_map_queries
-    map_desc = synth_map_queries(d0, MAP_M, 17)
-    for _ in range(max(args.warmup, 1)):
-        cpu_reference_fps(frames[:threads], map_desc, threads)
+    sample = cfg["ref_sample"]
+    frames, train, map_desc = reference_inputs(cfg, sample)
+    ext = cfg is not CONFIGS["c3"]
+    for _ in range(args.warmup):
+        cpu_reference_fps(frames[:threads] if ext else None, map_desc, threads, cfg["nfeat"], ext, None if ext else train[:threads])
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_reference_fps(frames, map_desc, threads)
+        cpu_reference_fps(frames, map_desc, threads, cfg["nfeat"], ext, train)
     dt = time.perf_counter() - t0
     fps = sample * args.steps / dt
-    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+    extra = {}
+    try:
+        tr = train[0] if not ext else cv2.ORB_create(cfg["nfeat"], SCALE, NLEVELS).detectAndCompute(frames[0], None)[1]
+        cv2.setNumThreads(threads)
+        extra = {"flann_lsh_ms_per_match": flann_lsh_ms(map_desc, tr), "note": "FlannBasedMatcher(LshIndexParams(5,10,2)).match(map, frame) incl. index build, all cv threads: "
+                 "the matcher src/frontend.cpp:33,187 literally uses (approximate, randomly seeded; not a parity target)"}
+        t1 = time.perf_counter(); cv2.BFMatcher(cv2.NORM_HAMMING).match(map_desc, tr); extra["bf_ms_per_match_all_cv_threads"] = (time.perf_counter() - t1) * 1e3
+    except Exception as e:  # pragma: no cover
+        extra = {"flann_lsh_ms_per_match": None, "note": str(e)}
+    line = {"impl": "reference", "metric": metric_name(cfg), "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"cv2 {cv2.__version__} ORB({NFEAT},{SCALE},{NLEVELS}) detectAndCompute + {MATCHES_PER_FRAME}x BFMatcher(NORM_HAMMING).match(map {MAP_M} x frame) per 640x480 frame",
-                       "sample_frames_per_step": sample},
+            "config": {"workload": workload_string(cfg), "config_id": args.config, "frames_per_gpu_per_step": cfg["batch"]},
+            "arm": {"implementation": f"cv2 {cv2.__version__} ORB_create({cfg['nfeat']},{SCALE},{NLEVELS}).detectAndCompute + BFMatcher(NORM_HAMMING).match on the host cores",
+                    "frames_timed_per_step": sample},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "reference",
-                             "sample": f"{sample} frames per step, frame-parallel over {threads} host threads, cv2.setNumThreads(1)"},
+                             "sample": f"{sample} of the step's {cfg['batch']} frames per step, frame-parallel over {threads} host threads, cv2.setNumThreads(1)"},
+            "reference_matcher": extra,
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
-def run_orbx(args, rank: int, world: int, local_rank: int):
+def _load_json(rel):
+    try:
+        return json.load(open(os.path.join(ROOT, rel)))
+    except Exception:
+        return None
+
+
+def run_orbx(args, cfg, rank: int, world: int, local_rank: int):
     import torch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the orbx path has no CPU fallback")
@@ -162,36 +246,55 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
         dist = dist_
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from rgbd_visualodometry_b200 import orb
-    from rgbd_visualodometry_b200.synth import synth_map_queries
+    from rgbd_visualodometry_b200.synth import synth_descriptors, synth_map_queries
 
-    B = args.batch
-    frames_np = make_frames(B, rank)
-    ctx = orb.Context(NFEAT, SCALE, NLEVELS, W, H, B, device=local_rank)
-    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+    is_c3 = cfg is CONFIGS["c3"]
+    Wc, Hc, NF, MAPM = cfg["w"], cfg["h"], cfg["nfeat"], cfg["map_m"]
+    B = args.batch or cfg["batch"]
+    cap = cap_of(cfg)
+    steps = args.steps
+    if steps is None:
+        steps = 200 if not cfg.get("total_frames") else max(3, -(-cfg["total_frames"] // (B * world)))
+        if (Wc, Hc) != (W, H):
+            steps = min(steps, 200) if cfg.get("total_frames") else 50
     dev = torch.device("cuda", local_rank)
-    d_in = torch.from_numpy(frames_np).to(dev)
-    d_kps = torch.zeros((B, CAP, 7), dtype=torch.float32, device=dev)
-    d_desc = torch.zeros((B, CAP, 32), dtype=torch.uint8, device=dev)
+    ctx = orb.Context(NF, SCALE, NLEVELS, Wc, Hc, B, device=local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+    ws, hs, _, _ = ctx.level_geometry(Wc, Hc)
+    level_pixels = int((ws.astype(np.int64) * hs).sum())
+    frames_np = None
+    d_kps = torch.zeros((B, cap, 7), dtype=torch.float32, device=dev)
+    d_desc = torch.zeros((B, cap, 32), dtype=torch.uint8, device=dev)
     d_cnt = torch.zeros(B, dtype=torch.int32, device=dev)
-    d_best = torch.zeros((MATCHES_PER_FRAME, B, MAP_M, 4), dtype=torch.int32, device=dev)
+    d_best = torch.zeros((MATCHES_PER_FRAME, B, MAPM, 4), dtype=torch.int32, device=dev)
+    if is_c3:
+        train_np = np.zeros((B, cap, 32), np.uint8)
+        for i in range(B):
+            train_np[i, :NF] = synth_descriptors(NF, 40 + i + 1000 * rank)
+        d_desc.copy_(torch.from_numpy(train_np).to(dev)); d_cnt.fill_(NF)
+        map_np = synth_map_queries(train_np[0, :NF], MAPM, 41)
+    else:
+        frames_np = make_frames(B, rank, Wc, Hc, cfg["nbase"], cfg["frames"])
+        d_in = torch.from_numpy(frames_np).to(dev)
     torch.cuda.synchronize()
 
     def extract():
-        ctx.detect_and_compute_device(d_in.data_ptr(), B, W, H, W * 3, H * W * 3, 3, d_kps.data_ptr(), d_desc.data_ptr(), CAP, d_cnt.data_ptr())
+        if not is_c3:
+            ctx.detect_and_compute_device(d_in.data_ptr(), B, Wc, Hc, Wc * 3, Hc * Wc * 3, 3, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_cnt.data_ptr())
 
     extract()
     ctx.synchronize()
     counts = d_cnt.cpu().numpy()
-    assert counts.max() <= CAP, "capacity too small for this data"
-    desc0 = d_desc[0, :counts[0]].cpu().numpy()
-    map_np = synth_map_queries(desc0, MAP_M, 17)
+    assert counts.max() <= cap, "capacity too small for this data"
+    if not is_c3:
+        map_np = synth_map_queries(d_desc[0, :counts[0]].cpu().numpy(), MAPM, 17)
     d_map = torch.from_numpy(map_np).to(dev)
     torch.cuda.synchronize()
 
     def step():
         extract()
         for m in range(MATCHES_PER_FRAME):
-            ctx.match_device_ragged(d_map.data_ptr(), MAP_M, d_desc.data_ptr(), CAP, d_cnt.data_ptr(), B, d_best[m].data_ptr())
+            ctx.match_device_ragged(d_map.data_ptr(), MAPM, d_desc.data_ptr(), cap, d_cnt.data_ptr(), B, d_best[m].data_ptr())
 
     def barrier():
         if dist is not None:
@@ -199,7 +302,8 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None   # started early; only samples inside the timed region count
-    for _ in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
         step()
     ctx.synchronize()
     barrier()
@@ -207,7 +311,7 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
     t_wall0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record(stream)
     barrier()
@@ -219,7 +323,7 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = world * B * args.steps / (ms_max / 1e3)
+    value = world * B * steps / (ms_max / 1e3)
 
     # ---- per-stage device times (CUDA events between the kernels, on the launching stream), 5 extra steps
     ctx.set_profiling(True)
@@ -231,30 +335,67 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
     ctx.set_profiling(False)
     stage_ms = {k: float(np.mean(v)) for k, v in stage.items()}
 
+    # ---- config 3: the map-size sweep (device-timed, 2 matches per frame as in the value)
+    sweep = None
+    if is_c3:
+        sweep = []
+        for m in C3_SWEEP:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = max(3, min(50, 2000000 // m))
+            for timed in (False, True):
+                if timed:
+                    ev0.record(stream)
+                for _ in range(reps if timed else 2):
+                    ctx.match_device_ragged(d_map.data_ptr(), m, d_desc.data_ptr(), cap, d_cnt.data_ptr(), B, d_best[0].data_ptr())
+                if timed:
+                    ev1.record(stream)
+            ctx.synchronize()
+            t_ms = ev0.elapsed_time(ev1) / reps
+            sweep.append({"map": m, "frames": B, "train_rows_per_frame": NF, "ms": t_ms, "tops": 2.0 * 256 * m * NF * B / (t_ms / 1e3) / 1e12})
+
     # ---- end to end through the host-buffer C-ABI (rank-local), H2D + D2H inside the timed region
-    pin_in = torch.from_numpy(frames_np).pin_memory()
-    kps_h = torch.zeros((B, CAP, 7), dtype=torch.float32).pin_memory()
-    desc_h = torch.zeros((B, CAP, 32), dtype=torch.uint8).pin_memory()
-    cnt_h = np.zeros(B, np.int32)
     import ctypes as C
-    ptrs = (C.c_void_p * B)(*[pin_in[i].data_ptr() for i in range(B)])
-
+    kps_h = torch.zeros((B, cap, 7), dtype=torch.float32).pin_memory()
+    desc_h = torch.zeros((B, cap, 32), dtype=torch.uint8).pin_memory()
+    cnt_h = np.zeros(B, np.int32)
     map_pin = torch.from_numpy(map_np).pin_memory()
-    best_hs = [torch.zeros((B, MAP_M, 4), dtype=torch.int32).pin_memory() for _ in range(MATCHES_PER_FRAME)]
-    qptrs = (C.c_void_p * MATCHES_PER_FRAME)(*[map_pin.data_ptr()] * MATCHES_PER_FRAME)
-    nqs = (C.c_int * MATCHES_PER_FRAME)(*[MAP_M] * MATCHES_PER_FRAME)
-    bptrs = (C.c_void_p * MATCHES_PER_FRAME)(*[t.data_ptr() for t in best_hs])
+    best_hs = [torch.zeros((B, MAPM, 4), dtype=torch.int32).pin_memory() for _ in range(MATCHES_PER_FRAME)]
+    e2e_pageable = None
+    if is_c3:
+        train_pin = torch.from_numpy(train_np).pin_memory()
+        cnt_np = np.full(B, NF, np.int32)
 
-    def e2e_step():
-        # one C-ABI call: frames (host, pinned) -> keypoints, descriptors and the front-end's matches (host, pinned)
-        rc = ctx.lib.orbx_extract_match_batch(ctx.h, ptrs, B, W, H, W * 3, 3, kps_h.data_ptr(), desc_h.data_ptr(), CAP, cnt_h.ctypes.data,
-                                              qptrs, nqs, MATCHES_PER_FRAME, bptrs)
-        assert rc == 0, ctx.lib.orbx_last_error(ctx.h)
+        def e2e_step():
+            for m in range(MATCHES_PER_FRAME):      # host descriptors in, DMatch records out (one map vs every frame's set)
+                rc = ctx.lib.orbx_match_hamming_sets(ctx.h, map_pin.data_ptr(), MAPM, train_pin.data_ptr(), cap, cnt_np.ctypes.data, B, best_hs[m].data_ptr(), None)
+                assert rc == 0, ctx.lib.orbx_last_error(ctx.h)
+        h2d = MATCHES_PER_FRAME * (MAPM * 32 + B * cap * 32 + B * 4)
+        d2h = MATCHES_PER_FRAME * (B * MAPM * 16 + 4)
+        api = "orbx_match_hamming_sets (host descriptors in, DMatch records out; pinned host buffers), wall clock around the synchronous calls"
+    else:
+        pin_in = torch.from_numpy(frames_np).pin_memory()
+        ptrs = (C.c_void_p * B)(*[pin_in[i].data_ptr() for i in range(B)])
+        qptrs = (C.c_void_p * MATCHES_PER_FRAME)(*[map_pin.data_ptr()] * MATCHES_PER_FRAME)
+        nqs = (C.c_int * MATCHES_PER_FRAME)(*[MAPM] * MATCHES_PER_FRAME)
+        bptrs = (C.c_void_p * MATCHES_PER_FRAME)(*[t_.data_ptr() for t_ in best_hs])
+
+        def e2e_call(frame_ptrs):
+            # one C-ABI call: frames (host) -> keypoints, descriptors and the front-end's matches (host, pinned)
+            rc = ctx.lib.orbx_extract_match_batch(ctx.h, frame_ptrs, B, Wc, Hc, Wc * 3, 3, kps_h.data_ptr(), desc_h.data_ptr(), cap, cnt_h.ctypes.data,
+                                                  qptrs, nqs, MATCHES_PER_FRAME, bptrs)
+            assert rc == 0, ctx.lib.orbx_last_error(ctx.h)
+
+        def e2e_step():
+            e2e_call(ptrs)
+        h2d = B * Hc * Wc * 3 + MATCHES_PER_FRAME * MAPM * 32
+        d2h = B * cap * 60 + 2 * B * 4 + MATCHES_PER_FRAME * B * MAPM * 16 + 16
+        api = ("orbx_extract_match_batch (one C-ABI call per step: host frames in, keypoints + descriptors + matches out; pinned host buffers), "
+               "wall clock around the synchronous call")
 
     for _ in range(3):
         e2e_step()
     barrier()
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(steps, 20))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
@@ -264,61 +405,76 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_fps = world * B * e2e_steps / float(te.item())
-    h2d = B * H * W * 3 + MATCHES_PER_FRAME * MAP_M * 32
-    d2h = B * CAP * 60 + 2 * B * 4 + MATCHES_PER_FRAME * B * MAP_M * 16 + 16
+    if not is_c3 and rank == 0:
+        # the reference's frames are pageable cv::Mat buffers (src/frame.cpp:28): the same call on ordinary (unpinned) numpy memory
+        pptrs = (C.c_void_p * B)(*[frames_np[i].ctypes.data for i in range(B)])
+        for _ in range(2):
+            e2e_call(pptrs)
+        n_pg = max(3, min(e2e_steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(n_pg):
+            e2e_call(pptrs)
+        e2e_pageable = {"value": B * n_pg / (time.perf_counter() - t0), "unit": "frames/s", "note": "rank 0 alone, input frames in pageable host memory (as the reference's cv::Mat), outputs pinned"}
 
     if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
         return
     # ---- roofline of the dominant kernel: algorithmic bytes per frame x frames per launch / its duration
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
+    peaks = _load_json("MEASURED_PEAKS.json") or {}
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     n_out = float(counts.mean())
-    b_alg = 3 * W * H + 2 * LEVEL_PIXELS_VGA + 60 * n_out
+    b_alg = 3 * Wc * Hc + 2 * level_pixels + 60 * n_out
     ext_stages = {k: v for k, v in stage_ms.items() if k != "match"}   # gray, pyramid, fast_nms, select_harris, blur, describe
     dom = max(ext_stages, key=ext_stages.get) if ext_stages else None
     ext_total = sum(ext_stages.values())
     roofline = None
-    traffic = None                                       # DRAM bytes of the dominant kernel per launch, from the committed ncu --set full capture
-    traffic_file = "profiles/r1_v15_ncu_dram_traffic.json"
-    try:
-        tj = json.load(open(os.path.join(ROOT, traffic_file)))["kernels"]
-        kname = {"gray": "k_gray", "pyramid": "k_pyr_down", "fast_nms": "k_fast_bands", "select_harris": "k_select", "blur": "k_blur",
-                 "describe": "k_describe"}.get(dom)
-        if kname in tj and B == 256:
-            last = tj[kname][-1]
-            traffic = last["dram_read_bytes"] + last["dram_write_bytes"]
-    except Exception:
-        pass
+    ncu = _load_json(f"profiles/{PROFILE_TAG}_ncu_metrics.json") or {}
+    kname = {"gray": "k_gray", "pyramid": "k_pyr_tma", "fast_nms": "k_fast_warp", "select_harris": "k_select", "blur": "k_blur", "describe": "k_describe"}
     if dom:
+        traffic = None                                   # DRAM bytes of the dominant kernel per launch, from the committed ncu --set full capture
+        k = (ncu.get("kernels") or {}).get(kname.get(dom))
+        if k and args.config == "c2" and B == BATCH:
+            traffic = k["dram_read_bytes"] + k["dram_write_bytes"]
         ach = b_alg * B / (ext_stages[dom] / 1e3) / 1e9
-        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
-                    "traffic_source": f"{traffic_file} (ncu --set full, same 256-frame launch)" if traffic else None,
+        roofline = {"bound": "hbm", "kernel": f"{dom} ({kname.get(dom)})", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic,
+                    "traffic_source": f"profiles/{PROFILE_TAG}_ncu_metrics.json (ncu --set full, same 256-frame launch)" if traffic else None,
                     "peak_source": peak_src, "algorithmic_bytes_per_frame": b_alg, "frames_per_launch": B,
                     "kernel_ms": ext_stages[dom], "kernel_share_of_extraction": ext_stages[dom] / ext_total}
     pipe_ach = b_alg * B / (ext_total / 1e3) / 1e9 if ext_total else None
-    match_ops = 2.0 * 256 * MAP_M * float(counts.sum())
+    match_ops = 2.0 * 256 * MAPM * float(counts.sum())
     roof_match = None
     if "match" in stage_ms:
         tops = match_ops / (stage_ms["match"] / 1e3) / 1e12
-        roof_match = {"bound": "tensor", "kernel": "k_hamming_umma2 (tcgen05 cta_group::2 kind::i8)", "achieved": tops, "peak": 4500.0, "unit": "TOP/s",
-                      "frac": tops / 4500.0, "peak_source": "nominal dense int8 (no measured int8 peak available)", "kernel_ms": stage_ms["match"],
-                      "ncu_tensor_pipe_cycles_active_pct": 76.4, "ncu_source": "profiles/r1_v15_ncu_full_summary.csv (sm__pipe_tensor_cycles_active, same launch shape)"}
+        i8 = _load_json(INT8_PEAK_FILE) or {}
+        mk = next((v for n, v in (ncu.get("kernels") or {}).items() if n.startswith("k_hamming_umma")), None)
+        peak_m = i8.get("int8_tops_burst")
+        roof_match = {"bound": "tensor", "kernel": "k_hamming_umma2 (tcgen05 cta_group::2 kind::i8)" if B * ((MAPM + 255) // 256) >= 148 else "k_hamming_umma (tcgen05 cta_group::1 kind::i8)",
+                      "achieved": tops, "peak": peak_m or 4500.0, "unit": "TOP/s", "frac": tops / (peak_m or 4500.0),
+                      "peak_source": f"measured: {INT8_PEAK_FILE} (pure tcgen05.mma.kind::i8 issue loop, burst)" if peak_m else "nominal dense int8 (no measured peak file)",
+                      "peak_nominal": 4500.0, "frac_of_nominal": tops / 4500.0, "peak_measured_same_shape": i8.get("int8_tops_burst_ts_n96"),
+                      "kernel_ms": stage_ms["match"],
+                      "ncu_tensor_pipe_cycles_active_pct": mk.get("tensor_pipe_pct") if mk else None,
+                      "ncu_source": f"profiles/{PROFILE_TAG}_ncu_metrics.json (sm__pipe_tensor_cycles_active, c2 launch shape)" if mk else None}
 
-    # ---- CPU baseline: the reference's own operators (cv2) on this box's host cores, bounded sample
+    # ---- CPU baseline: the reference's own operators (cv2) on this box's host cores, bounded sample, 3 warm-ups, median of 10
     cpu = None
     try:
-        threads = os.cpu_count() or 1
-        sample = 64
-        cpu_reference_fps(frames_np[:threads], map_np, threads)
-        fps, dt = cpu_reference_fps(frames_np[:sample], map_np, threads, repeats=3)
         import cv2
-        cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "reference",
-               "sample": f"{sample} of the step's {B} frames, best of 3, cv2 {cv2.__version__} frame-parallel over {threads} threads ({dt*1e3:.0f} ms)"}
+        threads = os.cpu_count() or 1
+        sample = min(cfg["cpu_sample"], B)
+        if is_c3:
+            fr, tr = None, [train_np[i, :NF] for i in range(sample)]
+        else:
+            fr, tr = frames_np[:sample], None
+        reps = 10 if sample * (Wc * Hc) <= 64 * 640 * 480 * 2 else 5
+        for _ in range(3):
+            cpu_reference_fps(fr[:threads] if fr is not None else None, map_np, threads, NF, not is_c3, tr[:threads] if tr else None)
+        runs = sorted(cpu_reference_fps(fr, map_np, threads, NF, not is_c3, tr)[0] for _ in range(reps))
+        cpu = {"value": float(np.median(runs)), "unit": "frames/s", "cores": threads, "kind": "reference",
+               "sample": f"{sample} of the step's {B} frames, 3 warm-ups, median of {reps} passes (min {runs[0]:.0f}, max {runs[-1]:.0f}), cv2 {cv2.__version__} "
+                         f"frame-parallel over {threads} threads, cv2.setNumThreads(1)"}
     except Exception as e:  # pragma: no cover
         cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
 
@@ -327,12 +483,19 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
     parity = None
     try:
         import cv2
-        cv2.setNumThreads(1)
-        cvo, cvm = cv2.ORB_create(NFEAT, SCALE, NLEVELS), cv2.BFMatcher(cv2.NORM_HAMMING)
-        chk = sorted({0, B // 3, (2 * B) // 3, B - 1})
+        cv2.setNumThreads(os.cpu_count() or 1)
+        cvo, cvm = cv2.ORB_create(NF, SCALE, NLEVELS), cv2.BFMatcher(cv2.NORM_HAMMING)
+        chk = sorted({0, B // 3, (2 * B) // 3, B - 1}) if Wc * Hc <= 1920 * 1080 else sorted({0, B - 1})
         kp_bad = desc_bad = match_bad = 0
         cnt_d = d_cnt.cpu().numpy()
         for i in chk:
+            if is_c3:
+                cd = train_np[i, :NF]
+                ref_m = np.array([(m.queryIdx, m.trainIdx, m.imgIdx, m.distance) for m in cvm.match(map_np, cd)], dtype=orb.DMATCH_DTYPE)
+                for mm in (d_best[0][i].cpu().numpy(), best_hs[0][i].numpy()):
+                    got_m = np.ascontiguousarray(mm).view(orb.DMATCH_DTYPE).reshape(-1)
+                    match_bad += int((got_m["trainIdx"] != ref_m["trainIdx"]).sum() + (got_m["distance"] != ref_m["distance"]).sum())
+                continue
             ck, cd = cvo.detectAndCompute(frames_np[i], None)
             ref_k = np.array([(k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave, k.class_id) for k in ck], dtype=orb.KP_DTYPE)
             cm = cvm.match(map_np, cd)
@@ -341,31 +504,36 @@ def run_orbx(args, rank: int, world: int, local_rank: int):
                                    (kps_h[i].numpy(), desc_h[i].numpy(), int(cnt_h[i]), best_hs[0][i].numpy())):
                 got_k = np.ascontiguousarray(kk[:nn]).view(orb.KP_DTYPE).reshape(-1)
                 if len(got_k) != len(ref_k):
-                    kp_bad += max(len(got_k), len(ref_k)); desc_bad += 32 * max(len(got_k), len(ref_k)); match_bad += MAP_M
+                    kp_bad += max(len(got_k), len(ref_k)); desc_bad += 32 * max(len(got_k), len(ref_k)); match_bad += MAPM
                     continue
                 kp_bad += int(sum(a.tobytes() != b.tobytes() for a, b in zip(got_k, ref_k)))
                 desc_bad += int((dd[:nn] != cd).sum())
                 got_m = np.ascontiguousarray(mm).view(orb.DMATCH_DTYPE).reshape(-1)
-                match_bad += int(sum(a.tobytes() != b.tobytes() for a, b in zip(got_m, ref_m))) + abs(len(got_m) - len(ref_m))
+                match_bad += int((got_m.view(np.uint8).reshape(-1, 16) != ref_m.view(np.uint8).reshape(-1, 16)).any(axis=1).sum()) + abs(len(got_m) - len(ref_m))
         parity = {"vs": f"cv2 {cv2.__version__} detectAndCompute + BFMatcher(NORM_HAMMING).match on the same frames", "frames_checked": chk,
                   "paths": ["device-resident (timed)", "host-buffer C-ABI (e2e)"], "keypoint_record_mismatches": kp_bad,
                   "descriptor_byte_mismatches": desc_bad, "match_record_mismatches": match_bad, "angle_tie_descriptor_diffs": 0 if desc_bad == 0 else None}
     except Exception as e:  # pragma: no cover
         parity = {"unavailable": str(e)}
 
-    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+    in_bytes = B * Hc * Wc * 3 if not is_c3 else B * cap * 32
+    line = {"metric": metric_name(cfg), "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
-            "config": {"workload": f"batched ORB extraction 640x480 BGR, {NFEAT} features, scale {SCALE}, {NLEVELS} levels + {MATCHES_PER_FRAME} Hamming matches/frame "
-                                   f"(map {MAP_M} x frame descriptors, tcgen05 int8)", "frames_per_gpu_per_step": B, "parallelism": f"frame-sharded x{world}, no collective",
-                       "l2": f"inputs {B * H * W * 3 / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)", "mean_keypoints_per_frame": n_out},
+            "config": {"workload": workload_string(cfg), "config_id": args.config, "frames_per_gpu_per_step": B},
+            "arm": {"implementation": "liborbx.so (sm_100a kernels; matcher on tcgen05 int8)", "parallelism": f"frame-sharded x{world}, no collective",
+                    "l2": f"inputs {in_bytes / 1e6:.0f} MB per step " + ("> 126 MB L2 (no flush needed)" if in_bytes > 126e6 else "(train sets; the matcher is compute-bound)"),
+                    "mean_keypoints_per_frame": n_out, "frames_total": world * B * steps,
+                    "frames_note": f"{B} distinct device-resident frames per GPU, cycled" if cfg.get("total_frames") else None},
             "clocks": clocks,
-            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "api": "orbx_extract_match_batch (one C-ABI call per step: host frames in, keypoints + descriptors + matches out; pinned host buffers), wall clock around the synchronous call"},
+            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": api},
+            "e2e_pageable": e2e_pageable,
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_pipeline": {"achieved": pipe_ach, "peak": hbm_peak, "unit": "GB/s", "frac": pipe_ach / hbm_peak if pipe_ach else None,
                                                          "note": "same algorithmic bytes over the sum of all extraction kernels"},
             "roofline_match": roof_match, "stage_ms": stage_ms, "cpu_baseline": cpu, "parity": parity}
+    if sweep is not None:
+        line["sweep"] = sweep
     emit(line)
     if dist is not None:
         dist.destroy_process_group()
@@ -394,19 +562,23 @@ def emit(obj):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 200 for c1-c3, 50 for c4, 10 000 frames' worth for c5; reference arm: 5)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="orbx", choices=["orbx", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json configs[0..4]; the default c2 is the metric's configuration")
+    ap.add_argument("--batch", type=int, default=0, help="frames per GPU per step (default: the config's)")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     _quiet_stdout()
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        if args.steps is None:
+            args.steps = 5
+        run_reference(args, cfg, rank, world)
     else:
-        run_orbx(args, rank, world, local_rank)
+        run_orbx(args, cfg, rank, world, local_rank)
 
 
 if __name__ == "__main__":

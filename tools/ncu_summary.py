@@ -35,4 +35,24 @@ for r in data:
 json.dump({"note": "dram__bytes_read.sum / dram__bytes_write.sum per launch from ncu --set full --clock-control none, "
                    "ORBX_LANES=1 tools/prof_step.py 256 2 (256 VGA frames per launch)", "kernels": kern},
           open(out + "_ncu_dram_traffic.json", "w"), indent=1)
+# one record per kernel (a kernel launched once per level: the sums over its launches) -- what bench.py quotes
+def col(name):
+    return hdr.index(name) if name in hdr else None
+ci = {k: col(v) for k, v in {"inst": "smsp__inst_executed.sum", "issue": "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                             "alu": "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "fma": "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+                             "tensor": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "dram": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+                             "regs": "launch__registers_per_thread"}.items()}
+met = {}
+for r in data:
+    name = r[ki].split("(")[0].replace("void ", "").split("<")[0].strip()
+    m = met.setdefault(name, {"launches": 0, "time_us": 0.0, "dram_read_bytes": 0.0, "dram_write_bytes": 0.0, "inst_executed": 0.0})
+    tus = float(r[ti]) * {"us": 1, "ms": 1e3, "ns": 1e-3}.get(units[ti], 1)
+    m["launches"] += 1; m["time_us"] += tus
+    m["dram_read_bytes"] += to_bytes(r[ri], units[ri]); m["dram_write_bytes"] += to_bytes(r[wi], units[wi])
+    if ci["inst"] is not None: m["inst_executed"] += float(r[ci["inst"]])
+    if m["launches"] == 1:                               # utilisation figures of the first (largest) launch
+        for k, key in (("issue", "issue_active_pct"), ("alu", "alu_pipe_pct"), ("fma", "fma_pipe_pct"), ("tensor", "tensor_pipe_pct"), ("dram", "dram_throughput_pct"), ("regs", "registers")):
+            if ci[k] is not None and r[ci[k]] != "": m[key] = float(r[ci[k]])
+json.dump({"note": "ncu --set full --clock-control none of ORBX_LANES=1 tools/prof_step.py 256 2 (256 VGA frames per launch, BASELINE config 2): per-kernel sums over "
+                   "its launches; pipe / issue percentages of the first launch", "kernels": met}, open(out + "_ncu_metrics.json", "w"), indent=1)
 print(open(out + "_ncu_full_summary.csv").read())
