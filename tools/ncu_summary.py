@@ -43,7 +43,9 @@ ci = {k: col(v) for k, v in {"inst": "smsp__inst_executed.sum", "issue": "smsp__
                              "tensor": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "dram": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
                              "regs": "launch__registers_per_thread"}.items()}
 met = {}
-for r in data:
+gray_rows = [i for i, r in enumerate(data) if "k_gray" in r[ki]]
+step_rows = data[gray_rows[-1]:] if gray_rows else data     # one whole step: from the last k_gray launch to the end of the capture
+for r in step_rows:
     name = r[ki].split("(")[0].replace("void ", "").split("<")[0].strip()
     m = met.setdefault(name, {"launches": 0, "time_us": 0.0, "dram_read_bytes": 0.0, "dram_write_bytes": 0.0, "inst_executed": 0.0})
     tus = float(r[ti]) * {"us": 1, "ms": 1e3, "ns": 1e-3}.get(units[ti], 1)
@@ -54,5 +56,5 @@ for r in data:
         for k, key in (("issue", "issue_active_pct"), ("alu", "alu_pipe_pct"), ("fma", "fma_pipe_pct"), ("tensor", "tensor_pipe_pct"), ("dram", "dram_throughput_pct"), ("regs", "registers")):
             if ci[k] is not None and r[ci[k]] != "": m[key] = float(r[ci[k]])
 json.dump({"note": "ncu --set full --clock-control none of ORBX_LANES=1 tools/prof_step.py 256 2 (256 VGA frames per launch, BASELINE config 2): per-kernel sums over "
-                   "its launches; pipe / issue percentages of the first launch", "kernels": met}, open(out + "_ncu_metrics.json", "w"), indent=1)
+                   "its launches inside ONE step (from the capture's last k_gray launch on); pipe / issue percentages of the kernel's first launch", "kernels": met}, open(out + "_ncu_metrics.json", "w"), indent=1)
 print(open(out + "_ncu_full_summary.csv").read())
