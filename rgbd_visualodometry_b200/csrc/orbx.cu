@@ -21,6 +21,7 @@
 #include "orbx_match.cuh"
 #include "orbx_fast.cuh"
 #include "orbx_pyr.cuh"
+#include "orbx_select.cuh"
 #include "orbx_map.cuh"
 #include <unordered_map>
 
@@ -65,7 +66,7 @@ struct orbx_ctx {
     int geom_w = 0, geom_h = 0;
     size_t tabs_len = 0;
 
-    Buf pyr, blur, rowcnt, rowent, work, selpos, fincnt, status, tabs, pattern;
+    Buf pyr, blur, rowcnt, rowent, work, selpos, fincnt, selcnt, status, tabs, pattern;
     Buf in, kps, desc, counts;               // host-path staging on the device
     int out_cap = 0;
     const uint8_t* view_desc = nullptr;      // device descriptors / counts of the frames the last host call (or collect) produced
@@ -184,7 +185,7 @@ void build_geom(const orbx_ctx* c, int w, int h, Geom* g, std::vector<uint32_t>*
     level_quotas(c->nfeatures, c->scale_factor, c->nlevels, q);
     g->nlevels = c->nlevels; g->w = w; g->h = h; g->band_rows = FAST_R;
     size_t pyr = 0, cnt = 0, ent = 0, wsz = 0, tab = 0;
-    int bands = 0, blurs = 0;
+    int bands = 0, blurs = 0, hblks = 0, selh = 64;
     for (int l = 0; l < c->nlevels; ++l) {
         LevelGeom& L = g->L[l];
         L.w = std::max(ws[l], 0); L.h = std::max(hs[l], 0);
@@ -207,13 +208,16 @@ void build_geom(const orbx_ctx* c, int w, int h, Geom* g, std::vector<uint32_t>*
             L.nblur = (L.blur_cgs * ((rows + L.blur_rh - 1) / L.blur_rh) + BLUR_NT - 1) / BLUR_NT;
         }
         L.blur0 = blurs; blurs += L.nblur;
+        L.hblk0 = hblks; L.hblk = (2 * L.quota * 5 / 4 + 32 + HARRIS_NT - 1) / HARRIS_NT; hblks += L.hblk;
+        selh = std::max(selh, 2 * L.quota * 5 / 4 + 64);
         L.img_off = pyr; pyr += round_up((size_t)L.pitch * std::max(L.h, 1), 256);
         L.cnt_off = cnt; cnt += round_up((size_t)std::max(L.in_h, 1), 8);
         L.ent_off = ent; ent += (size_t)L.ent_pitch * std::max(L.in_h, 1);
         L.ws_off = wsz; wsz += round_up((size_t)L.ws_cap, 4);
         if (l > 0) { L.xtab = (uint32_t)tab; tab += L.w; L.ytab = (uint32_t)tab; tab += L.h; }
     }
-    g->total_bands = bands; g->total_blur = blurs;
+    g->total_bands = bands; g->total_blur = blurs; g->total_hblk = hblks;
+    g->selh_elems = std::min((selh + 63) / 64 * 64, 16384);
     g->pyr_frame = round_up(pyr, 256); g->cnt_frame = cnt; g->ent_frame = ent; g->ws_frame = wsz;
     if (tabs) {
         tabs->assign(std::max<size_t>(tab, 1), 0);
@@ -348,6 +352,7 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, bool marks, int f0, int nb,
     Elem* work = (Elem*)c->work.p + F * g.ws_frame;
     uint32_t* selpos = (uint32_t*)c->selpos.p + 2 * F * g.ws_frame;
     int* fincnt = (int*)c->fincnt.p + F * g.nlevels;
+    int* selcnt = (int*)c->selcnt.p + F * g.nlevels;
     int* status = (int*)c->status.p + F;
     d_kps += F * cap * 7; d_desc += F * cap * 32; d_counts += F;
     const uint32_t* tabs = (const uint32_t*)c->tabs.p;
@@ -397,8 +402,16 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, bool marks, int f0, int nb,
     //  neither beats running them back to back -- the selection kernel is bound by the latency of its longest CTA, not by
     //  issue slots it could lend to the blur.)
     if (marks) stage_mark(c, 3);
-    k_select<<<dim3(B, (unsigned)g.nlevels), SEL_NT, 0, st>>>(g, pyr, rowcnt, rowent, work, selpos, fincnt, status);
-    ++c->launches;
+    {
+        static const int old_sel = getenv("ORBX_SELECT_OLD") ? atoi(getenv("ORBX_SELECT_OLD")) : 0;   // A/B timing only
+        if (old_sel) { k_select<<<dim3(B, (unsigned)g.nlevels), SEL_NT, 0, st>>>(g, pyr, rowcnt, rowent, work, selpos, fincnt, status); ++c->launches; }
+        else {
+            k_select_fast<<<dim3(B, (unsigned)g.nlevels), 32, 0, st>>>(g, rowcnt, rowent, work, selpos, selcnt, fincnt);
+            if (g.total_hblk > 0) k_harris<<<dim3((unsigned)g.total_hblk, B), HARRIS_NT, 0, st>>>(g, pyr, work, selcnt);
+            k_select_harris<<<dim3(B, (unsigned)g.nlevels), 32, (size_t)g.selh_elems * 12, st>>>(g, work, selpos, selcnt, fincnt, g.selh_elems);
+            c->launches += 3;
+        }
+    }
     if (marks) stage_mark(c, 4);
     if (g.total_blur > 0) {
         k_blur<<<dim3((unsigned)g.total_blur, B), BLUR_NT, 0, st>>>(g, pyr, blur);
@@ -621,7 +634,7 @@ int orbx_create(orbx_ctx** out, int device, int nfeatures, float scale_factor, i
     const size_t B = (size_t)max_batch;
     if (ensure(c, c->pyr, g.pyr_frame * B + (size_t)(96 + 8) * g.L[0].pitch) ||   // + slack: the blur streams up to ~100 rows past a level's end (masked outputs)
         ensure(c, c->blur, g.pyr_frame * B) || ensure(c, c->rowcnt, g.cnt_frame * 4 * B) || ensure(c, c->rowent, g.ent_frame * 4 * B) ||
-        ensure(c, c->work, g.ws_frame * sizeof(Elem) * B) || ensure(c, c->selpos, g.ws_frame * 8 * B) || ensure(c, c->fincnt, sizeof(int) * ORBX_LEVELS_MAX * B) ||
+        ensure(c, c->work, g.ws_frame * sizeof(Elem) * B) || ensure(c, c->selpos, g.ws_frame * 8 * B) || ensure(c, c->fincnt, sizeof(int) * ORBX_LEVELS_MAX * B) || ensure(c, c->selcnt, sizeof(int) * ORBX_LEVELS_MAX * B) ||
         ensure(c, c->status, sizeof(int) * B) || ensure(c, c->pattern, sizeof(float) * 1024) || ensure(c, c->mstatus, sizeof(int) * 16))
         return bail(ORBX_E_NOMEM);
     if (cudaMemset(c->mstatus.p, 0, sizeof(int) * 16) != cudaSuccess) return bail(ORBX_E_CUDA);
@@ -639,7 +652,8 @@ int orbx_create(orbx_ctx** out, int device, int nfeatures, float scale_factor, i
         cudaFuncSetAttribute(k_hamming_umma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(k_hamming_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(k_fast_warp<FAST_NWARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_NWARP * FW_WARP_BYTES + 128) != cudaSuccess ||
-        cudaFuncSetAttribute(k_pyr_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess)
+        cudaFuncSetAttribute(k_pyr_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_select_harris, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12) != cudaSuccess)
         return bail(ORBX_E_CUDA);
     *out = c;
     return ORBX_OK;
@@ -650,7 +664,7 @@ void orbx_destroy(orbx_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    Buf* bufs[] = {&c->pyr, &c->blur, &c->rowcnt, &c->rowent, &c->work, &c->selpos, &c->fincnt, &c->status, &c->tabs, &c->pattern, &c->in, &c->kps,
+    Buf* bufs[] = {&c->pyr, &c->blur, &c->rowcnt, &c->rowent, &c->work, &c->selpos, &c->fincnt, &c->selcnt, &c->status, &c->tabs, &c->pattern, &c->in, &c->kps,
                    &c->desc, &c->counts, &c->mq, &c->mt, &c->mbest, &c->msecond, &c->mkeys, &c->mstatus, &c->mcounts, &c->mtrace,
                    &c->t_desc, &c->t_pos, &c->t_nrm, &c->t_outl, &c->t_slots, &c->t_cand, &c->t_ncand, &c->t_q, &c->t_in, &c->t_best, &c->t_filtered,
                    &c->t_minmax, &c->t_aux};

@@ -32,6 +32,7 @@ struct LevelGeom {
     int ws_cap;               // workspace capacity (entries): ceil(in_w/2)*ceil(in_h/2)
     int band0;                // index of this level's first band in the per-frame band list
     int nbands;
+    int hblk0, hblk;          // k_harris: first block of this level in the per-frame block list, blocks of the level
     int blur0, nblur, blur_cgs;  // blur tiles: first tile index, tile count (= column groups x strip groups), column groups
     int blur_rh;              // output rows per blur strip: a multiple of 7 chosen per level so the strips fit the level tightly
     uint32_t xtab, ytab;      // offsets (u32 units) of the INTER_LINEAR_EXACT tap tables: i0 | c1 << 16
@@ -49,6 +50,8 @@ struct Geom {
     int nlevels, w, h;
     int total_bands;          // per frame
     int total_blur;           // blur tiles per frame
+    int total_hblk;           // k_harris blocks per frame
+    int selh_elems;           // k_select_harris: candidates of one level held in shared memory
     int band_rows;            // rows per FAST band
     unsigned long long pyr_frame, cnt_frame, ent_frame, ws_frame;   // per-frame strides (bytes / u32 / u32 / Elem)
     LevelGeom L[ORBX_LEVELS_MAX];
