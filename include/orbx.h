@@ -88,6 +88,16 @@ int orbx_detect_and_compute(orbx_ctx* ctx, const uint8_t* img, int w, int h, siz
 int orbx_detect_and_compute_batch(orbx_ctx* ctx, const uint8_t* const* imgs, int batch, int w, int h, size_t step,
                                   int channels, orbx_keypoint* kps, uint8_t* desc, int cap, int* n_out);
 
+/* Host buffers of the two calls above (and of orbx_extract_match_batch) may be pageable -- the reference's frames are
+ * cv::Mat (src/frame.cpp:28) and its results std::vector / cv::Mat (frontend.h:69-70): the library then stages them through
+ * its own pinned memory with a few copier threads (ORBX_STAGE_THREADS, default min(8, cores / 2)), so uploads, kernels and
+ * downloads of neighbouring frame ranges still overlap.  Page-locked buffers (cudaHostAlloc, cudaHostRegister, or
+ * orbx_host_register below) are copied from / into directly, which is faster still.
+ * orbx_host_register page-locks a LONG-LIVED caller buffer (e.g. the ring of frame buffers of a capture loop) without the
+ * caller linking CUDA; it must be unregistered before the memory is freed.  Returns ORBX_E_CUDA if the range cannot be locked. */
+int orbx_host_register(orbx_ctx* ctx, void* ptr, size_t bytes);
+int orbx_host_unregister(orbx_ctx* ctx, void* ptr);
+
 /* `batch` frames already DEVICE-resident (frame i at d_imgs + i*frame_stride); outputs to device memory
  * ([batch][cap] records, [batch][cap][32] bytes, d_counts[batch]).  Asynchronous on orbx_stream(); per-frame
  * status is deferred to orbx_synchronize().  d_counts[i] may exceed cap (records beyond cap are not written). */

@@ -14,9 +14,9 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 SO = os.path.join(PKG, "liborbx.so")
-SOURCES = ["orbx.cu", "orbx_kernels.cuh", "orbx_match.cuh", "orbx_map.cuh", "orbx_geom.h", "brief_pattern.inc"]
+SOURCES = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".inc")))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
-              "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared"]
+              "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared", "-diag-suppress", "68", "-lpthread"]
 
 
 def _stale() -> bool:
@@ -68,6 +68,8 @@ SYMBOLS = {
     "orbx_match_hamming_sets": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P, C.c_int, _P, _P]),
     "orbx_extract_match_batch": (C.c_int, [_P, C.POINTER(_P), C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_int, _P, _P, C.c_int, _P,
                                           C.POINTER(_P), C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    "orbx_host_register": (C.c_int, [_P, _P, C.c_size_t]),
+    "orbx_host_unregister": (C.c_int, [_P, _P]),
     "orbx_map_reserve": (C.c_int, [_P, C.c_int]),
     "orbx_map_size": (C.c_int, [_P]),
     "orbx_map_clear": (C.c_int, [_P]),

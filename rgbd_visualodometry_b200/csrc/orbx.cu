@@ -21,8 +21,10 @@
 #include "orbx_match.cuh"
 #include "orbx_fast.cuh"
 #include "orbx_pyr.cuh"
+#include "orbx_desc.cuh"
 #include "orbx_select.cuh"
 #include "orbx_map.cuh"
+#include "orbx_stage.h"
 #include <unordered_map>
 
 using namespace orbx;
@@ -62,6 +64,7 @@ struct orbx_ctx {
     Geom geom{};             // geometry of the current frame size
     FastMaps fmaps{};        // TMA tensor maps (x, y, frame) of the pyramid levels for the current geometry
     PyrMaps pmaps{};         // ... of every level as the SOURCE of the next one (k_pyr_tma boxes)
+    DescMaps dmaps{};        // ... of every pyramid / blurred level with k_describe_tma's window boxes
     Geom geom_max{};         // geometry of (max_w, max_h): sizes the buffers
     int geom_w = 0, geom_h = 0;
     size_t tabs_len = 0;
@@ -74,6 +77,9 @@ struct orbx_ctx {
     int view_frames = 0;
     Buf mq, mt, mbest, msecond, mkeys, mstatus, mcounts, mtrace;
     int* h_small = nullptr;                  // pinned: counts[max_batch] + status[max_batch] + 1
+    uint8_t* h_stage_in = nullptr; size_t h_stage_in_bytes = 0;     // pinned staging of pageable caller frames (device layout)
+    uint8_t* h_stage_out = nullptr; size_t h_stage_out_bytes = 0;   // ... of results bound for pageable caller buffers
+    HostStager* stager = nullptr;            // copier threads, created by the first call that needs them
     int last_batch = 0;
 
     // device-resident map-point table: slot-addressed columns + the host's id -> slot index
@@ -300,6 +306,19 @@ int build_fast_maps(orbx_ctx* c)
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(c, ORBX_E_CUDA, "cuTensorMapEncodeTiled failed for a pyramid source level");
     }
+    memset(&c->dmaps, 0, sizeof c->dmaps);
+    for (int l = 0; l < g.nlevels; ++l) {
+        const LevelGeom& L = g.L[l];
+        if (L.in_w <= 0) continue;
+        const cuuint64_t dims[3] = {(cuuint64_t)L.pitch, (cuuint64_t)L.h, (cuuint64_t)c->max_batch};
+        const cuuint64_t strides[2] = {(cuuint64_t)L.pitch, (cuuint64_t)g.pyr_frame};
+        const cuuint32_t box_ic[3] = {DS_ICW, DS_ICH, 1}, box_bl[3] = {DS_BLW, DS_BLH, 1}, es[3] = {1, 1, 1};
+        if (enc(&c->dmaps.ic[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (uint8_t*)c->pyr.p + L.img_off, dims, strides, box_ic, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS ||
+            enc(&c->dmaps.bl[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (uint8_t*)c->blur.p + L.img_off, dims, strides, box_bl, es,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return fail(c, ORBX_E_CUDA, "cuTensorMapEncodeTiled failed for a descriptor window map");
+    }
     return ORBX_OK;
 }
 
@@ -418,8 +437,20 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, bool marks, int f0, int nb,
         ++c->launches;
     }
     if (marks) stage_mark(c, 5);
-    k_describe<<<dim3((unsigned)((std::max(cap, 1) + DESC_KPB * DESC_KPW - 1) / (DESC_KPB * DESC_KPW)), B), DESC_NT, 0, st>>>(
-        g, pyr, blur, work, fincnt, (const float4*)c->pattern.p, d_kps, d_desc, d_counts, cap);
+    static const int old_desc = getenv("ORBX_DESC_OLD") ? atoi(getenv("ORBX_DESC_OLD")) : 0;   // A/B timing only
+    if (old_desc)
+        k_describe<<<dim3((unsigned)((std::max(cap, 1) + DESC_KPB * DESC_KPW - 1) / (DESC_KPB * DESC_KPW)), B), DESC_NT, 0, st>>>(
+            g, pyr, blur, work, fincnt, (const float4*)c->pattern.p, d_kps, d_desc, d_counts, cap);
+    else {
+        // groups of 4 slots per warp: enough warps for two full waves (148 SMs x 24 resident warps) when the batch is large,
+        // one group per warp (lowest latency) when it is a single frame
+        static const int env_gpw = getenv("ORBX_DESC_GPW") ? atoi(getenv("ORBX_DESC_GPW")) : 0;
+        const long groups = (long)nb * ((std::min(std::max(cap, 1), std::max(c->nfeatures, 1)) + DS_G - 1) / DS_G);
+        const int gpw = env_gpw > 0 ? std::min(env_gpw, DS_MAX_GPW) : (int)std::max(1L, std::min((long)DS_MAX_GPW, groups / (148L * 24 * 2)));
+        const int gcap = (std::max(cap, 1) + DS_G - 1) / DS_G;
+        k_describe_tma<<<dim3((unsigned)((gcap + DS_NW * gpw - 1) / (DS_NW * gpw)), B), DS_NW * 32, DS_NW * DS_WARP_BYTES + 128, st>>>(
+            g, c->dmaps, f0, work, fincnt, (const float4*)c->pattern.p, d_kps, d_desc, d_counts, cap, gpw, status);
+    }
     ++c->launches;
     if (marks) stage_mark(c, 6);
     return ORBX_OK;
@@ -436,7 +467,7 @@ int run_extract(orbx_ctx* c, const uint8_t* d_imgs, int batch, int w, int h, siz
     int rc = set_geometry(c, w, h);
     if (rc) return rc;
     CU(cudaMemsetAsync(c->status.p, 0, sizeof(int) * (size_t)batch, c->stream));
-    static const int env_lanes = getenv("ORBX_LANES") ? atoi(getenv("ORBX_LANES")) : 3;
+    static const int env_lanes = getenv("ORBX_LANES") ? atoi(getenv("ORBX_LANES")) : 1;   // 1: every kernel fills the GPU on its own now (3 lanes measured 4 % slower)
     int lanes = std::max(1, std::min(env_lanes, MAX_LANES));
     if (batch < lanes * LANE_MIN_FRAMES) lanes = 1;
     if (c->profiling) lanes = 1;
@@ -625,8 +656,8 @@ int orbx_create(orbx_ctx** out, int device, int nfeatures, float scale_factor, i
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(ORBX_E_CUDA);
     if (prop.major != 10) return bail(ORBX_E_CUDA);          // sm_100a only: no other code path exists
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(ORBX_E_CUDA);
-    for (int k = 1; k < HOST_MAX_LANES; ++k)
-        if (cudaStreamCreateWithFlags(&c->lane[k], cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming) != cudaSuccess) return bail(ORBX_E_CUDA);
+    for (int k = 0; k < HOST_MAX_LANES; ++k)
+        if ((k > 0 && cudaStreamCreateWithFlags(&c->lane[k], cudaStreamNonBlocking) != cudaSuccess) || cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming) != cudaSuccess) return bail(ORBX_E_CUDA);
     if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(ORBX_E_CUDA);
     for (int i = 0; i < N_STAGES + 2; ++i) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail(ORBX_E_CUDA);
     build_geom(c, max_w, max_h, &c->geom_max, nullptr);
@@ -653,6 +684,7 @@ int orbx_create(orbx_ctx** out, int device, int nfeatures, float scale_factor, i
         cudaFuncSetAttribute(k_hamming_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute(k_fast_warp<FAST_NWARP>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_NWARP * FW_WARP_BYTES + 128) != cudaSuccess ||
         cudaFuncSetAttribute(k_pyr_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_describe_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, DS_NW * DS_WARP_BYTES + 128) != cudaSuccess ||
         cudaFuncSetAttribute(k_select_harris, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12) != cudaSuccess)
         return bail(ORBX_E_CUDA);
     *out = c;
@@ -670,6 +702,9 @@ void orbx_destroy(orbx_ctx* c)
                    &c->t_minmax, &c->t_aux};
     for (Buf* b : bufs) if (b->p) cudaFree(b->p);
     if (c->h_small) cudaFreeHost(c->h_small);
+    delete c->stager;
+    if (c->h_stage_in) cudaFreeHost(c->h_stage_in);
+    if (c->h_stage_out) cudaFreeHost(c->h_stage_out);
     for (auto& a : c->aslot) {
         if (a.h_in) cudaFreeHost(a.h_in);
         if (a.h_out) cudaFreeHost(a.h_out);
@@ -678,7 +713,7 @@ void orbx_destroy(orbx_ctx* c)
         if (a.done) cudaEventDestroy(a.done);
     }
     for (int i = 0; i < N_STAGES + 2; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-    for (int k = 1; k < HOST_MAX_LANES; ++k) { if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); if (c->lane[k]) { cudaStreamSynchronize(c->lane[k]); cudaStreamDestroy(c->lane[k]); } }
+    for (int k = 0; k < HOST_MAX_LANES; ++k) { if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); if (c->lane[k]) { cudaStreamSynchronize(c->lane[k]); cudaStreamDestroy(c->lane[k]); } }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -716,6 +751,175 @@ int orbx_detect_and_compute_device(orbx_ctx* c, const uint8_t* d_imgs, int batch
     return run_extract(c, d_imgs, batch, w, h, step, frame_stride, channels, (float*)d_kps, d_desc, cap, d_counts);
 }
 
+// ---- host-buffer batches: one core for orbx_detect_and_compute_batch (nmaps = 0) and orbx_extract_match_batch.
+// Frame ranges ("lanes") on their own streams: upload -> kernels -> (matches) -> download per lane, so the H2D copy of lane
+// k+1 runs under the kernels of lane k and the D2H of lane k under the kernels of lane k+1 (PCIe is the bound here).
+// Caller buffers that are NOT page-locked (the reference's cv::Mat frames and std::vector results) go through the context's
+// pinned staging, copied by the HostStager threads (orbx_stage.h), so the lanes overlap for them as well.
+static bool host_ptr_is_pinned(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+static int ensure_pinned(orbx_ctx* c, uint8_t*& p, size_t& have, size_t bytes)
+{
+    if (have >= bytes && p) return ORBX_OK;
+    if (p) { cudaFreeHost(p); p = nullptr; have = 0; }
+    bytes = std::max<size_t>(bytes, 4096);
+    if (cudaMallocHost((void**)&p, bytes) != cudaSuccess) { cudaGetLastError(); return fail(c, ORBX_E_NOMEM, "cudaMallocHost failed for the pinned staging buffer"); }
+    have = bytes;
+    return ORBX_OK;
+}
+
+static HostStager* stager_of(orbx_ctx* c)
+{
+    if (!c->stager) {
+        int n = getenv("ORBX_STAGE_THREADS") ? atoi(getenv("ORBX_STAGE_THREADS")) : (int)std::min(8u, std::max(2u, std::thread::hardware_concurrency() / 2));
+        c->stager = new HostStager(std::max(0, std::min(n, 32)));
+    }
+    return c->stager;
+}
+
+static int host_batch(orbx_ctx* c, const uint8_t* const* imgs, int batch, int w, int h, size_t step, int channels,
+                      orbx_keypoint* kps, uint8_t* desc, int cap, int* n_out, const uint8_t* const* queries, const int* nq,
+                      int nmaps, orbx_match* const* best)
+{
+    int rc;
+    CU(cudaSetDevice(c->device));
+    const size_t row = (size_t)w * channels, dstep = round_up(row, 16), fstride = dstep * h;   // 16: k_gray takes 128-bit loads
+    const size_t capz = (size_t)std::max(cap, 1);
+    size_t qrows = 0, mrows = 0;
+    for (int j = 0; j < nmaps; ++j) { qrows += (size_t)nq[j]; mrows += (size_t)nq[j] * batch; }
+    if ((rc = ensure(c, c->in, fstride * batch)) || (rc = ensure(c, c->kps, sizeof(orbx_keypoint) * capz * batch)) ||
+        (rc = ensure(c, c->desc, (size_t)32 * capz * batch)) || (rc = ensure(c, c->counts, sizeof(int) * (size_t)batch)))
+        return rc;
+    if (nmaps > 0 && ((rc = ensure(c, c->mq, std::max<size_t>(qrows, 1) * 32)) || (rc = ensure(c, c->mbest, std::max<size_t>(mrows, 1) * 16)) ||
+                      (rc = ensure(c, c->mstatus, sizeof(int) * 16))))
+        return rc;
+    for (int i = 0; i < batch; ++i) if (!imgs[i]) return fail(c, ORBX_E_ARG, "null frame pointer");
+    if ((rc = set_geometry(c, w, h))) return rc;
+
+    // ---- which caller buffers need staging
+    static const int stage_env = getenv("ORBX_STAGE") ? atoi(getenv("ORBX_STAGE")) : 1;      // 0: never stage (A/B timing only)
+    const bool stage_in = stage_env && !(host_ptr_is_pinned(imgs[0]) && host_ptr_is_pinned(imgs[batch - 1] + (size_t)(h - 1) * step + row - 1));
+    bool stage_out = false;
+    if (stage_env && cap > 0) stage_out = !(host_ptr_is_pinned(kps) && host_ptr_is_pinned(desc));
+    for (int j = 0; j < nmaps && stage_env && !stage_out; ++j) if (nq[j] > 0 && !host_ptr_is_pinned(best[j])) stage_out = true;
+    const size_t o_kps = 0, o_desc = round_up(sizeof(orbx_keypoint) * capz * batch, 256), o_best = o_desc + round_up((size_t)32 * capz * batch, 256);
+    if (stage_in && (rc = ensure_pinned(c, c->h_stage_in, c->h_stage_in_bytes, fstride * batch))) return rc;
+    if (stage_out && (rc = ensure_pinned(c, c->h_stage_out, c->h_stage_out_bytes, o_best + mrows * 16))) return rc;
+    HostStager* hs = (stage_in || stage_out) ? stager_of(c) : nullptr;
+    orbx_keypoint* kps_dl = stage_out ? (orbx_keypoint*)(c->h_stage_out + o_kps) : kps;       // where the D2H copies land
+    uint8_t* desc_dl = stage_out ? c->h_stage_out + o_desc : desc;
+
+    CU(cudaMemsetAsync(c->status.p, 0, sizeof(int) * (size_t)batch, c->stream));
+    {
+        size_t off = 0;
+        for (int j = 0; j < nmaps; ++j) {
+            if (nq[j] > 0) CU(cudaMemcpyAsync((uint8_t*)c->mq.p + off * 32, queries[j], (size_t)nq[j] * 32, cudaMemcpyHostToDevice, c->stream));
+            off += (size_t)nq[j];
+        }
+    }
+    static const int host_lanes_max = std::max(1, std::min(HOST_MAX_LANES, getenv("ORBX_HOST_LANES") ? atoi(getenv("ORBX_HOST_LANES")) : HOST_DEFAULT_LANES));
+    int* h_counts = c->h_small;
+    int* h_status = c->h_small + batch;
+    int* h_mstatus = c->h_small + 2 * batch;
+    const int lanes = c->profiling ? 1 : std::max(1, std::min(host_lanes_max, batch / HOST_LANE_MIN_FRAMES));
+    // staged inputs: all pieces are queued up front, lane by lane, so the copier threads run ahead of the lane loop
+    std::atomic<int> in_done[HOST_MAX_LANES], out_done(0);
+    int in_target[HOST_MAX_LANES] = {}, out_target = 0;
+    struct Drain {                                           // no queued piece may outlive the counters above, whichever way this call ends
+        HostStager* hs; std::atomic<int>* in; int* in_t; int n; std::atomic<int>* out; int* out_t;
+        ~Drain() { if (hs) { for (int k = 0; k < n; ++k) hs->help_until(in[k], in_t[k]); hs->help_until(*out, *out_t); } }
+    } drain{hs, in_done, in_target, stage_in ? lanes : 0, &out_done, &out_target};
+    if (stage_in)
+        for (int k = 0; k < lanes; ++k) {
+            int f0, f1;
+            host_lane_range(batch, lanes, k, &f0, &f1);
+            in_done[k].store(0, std::memory_order_relaxed);
+            for (int i = f0; i < f1; ++i) in_target[k] += hs->submit(c->h_stage_in + fstride * i, dstep, imgs[i], step, row, (size_t)h, &in_done[k]);
+        }
+    CU(cudaEventRecord(c->ev_fork, c->stream));
+    for (int k = 0; k < lanes; ++k) {
+        int f0, f1;
+        host_lane_range(batch, lanes, k, &f0, &f1);
+        const size_t n = (size_t)(f1 - f0);
+        cudaStream_t st = k == 0 ? c->stream : c->lane[k];
+        if (k > 0) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
+        if (stage_in) {
+            hs->help_until(in_done[k], in_target[k]);        // (the pinned image has the device layout: one copy per lane)
+            CU(cudaMemcpyAsync((uint8_t*)c->in.p + fstride * f0, c->h_stage_in + fstride * f0, fstride * n, cudaMemcpyHostToDevice, st));
+        } else if ((rc = upload_frames(c, st, imgs, f0, f1, step, row, h, dstep, fstride))) return rc;
+        if ((rc = run_extract_range(c, st, c->profiling, f0, f1 - f0, (const uint8_t*)c->in.p, dstep,
+                                    fstride, channels, (float*)c->kps.p, (uint8_t*)c->desc.p, cap, (int*)c->counts.p)))
+            return rc;
+        CU(cudaMemcpyAsync(h_counts + f0, (int*)c->counts.p + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(h_status + f0, (int*)c->status.p + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
+        if (cap > 0) {
+            // outputs are [batch][cap] on both sides: bulk copies per lane (records past n_out[i] are unspecified)
+            CU(cudaMemcpyAsync(kps_dl + (size_t)f0 * cap, (orbx_keypoint*)c->kps.p + (size_t)f0 * cap, sizeof(orbx_keypoint) * (size_t)cap * n, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(desc_dl + (size_t)f0 * cap * 32, (uint8_t*)c->desc.p + (size_t)f0 * cap * 32, (size_t)32 * cap * n, cudaMemcpyDeviceToHost, st));
+        }
+        size_t qoff = 0, moff = 0;
+        for (int j = 0; j < nmaps; ++j) {
+            if (nq[j] > 0) {
+                int4* d_best = (int4*)c->mbest.p + moff + (size_t)f0 * nq[j];
+                // train sets = this lane's frames, straight from the extraction outputs ([frame][cap][32] + counts)
+                if ((rc = run_match(c, (const uint8_t*)c->mq.p + qoff * 32, nq[j], (const uint8_t*)c->desc.p + (size_t)f0 * cap * 32, cap, cap,
+                                    (const int*)c->counts.p + f0, (int)n, d_best, nullptr, st, k)))
+                    return rc;
+                orbx_match* dl = stage_out ? (orbx_match*)(c->h_stage_out + o_best) + moff + (size_t)f0 * nq[j] : best[j] + (size_t)f0 * nq[j];
+                CU(cudaMemcpyAsync(dl, d_best, (size_t)16 * nq[j] * n, cudaMemcpyDeviceToHost, st));
+            }
+            qoff += (size_t)nq[j]; moff += (size_t)nq[j] * batch;
+        }
+        if (nmaps > 0) CU(cudaMemcpyAsync(h_mstatus + k, (int*)c->mstatus.p + k, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (k > 0 || stage_out) CU(cudaEventRecord(c->ev_join[k], st));
+        if (k > 0) CU(cudaStreamWaitEvent(c->stream, c->ev_join[k], 0));
+    }
+    CU(cudaGetLastError());
+    c->last_batch = batch;
+    c->out_cap = cap;
+    c->view_desc = (const uint8_t*)c->desc.p; c->view_counts = (const int*)c->counts.p; c->view_frames = batch;
+    if (c->profiling) for (int i = 0; i < 6; ++i) c->stage_valid[i] = true;
+    if (stage_out) {
+        // results leave the pinned staging lane by lane, as soon as a lane's downloads have landed, under the later lanes' work:
+        // only the records a frame really has are copied (the caller's records past n_out[i] stay untouched)
+        for (int k = 0; k < lanes; ++k) {
+            int f0, f1;
+            host_lane_range(batch, lanes, k, &f0, &f1);
+            CU(cudaEventSynchronize(c->ev_join[k]));
+            for (int i = f0; i < f1; ++i) {
+                const size_t ni = (size_t)std::max(0, std::min(h_counts[i], cap));
+                if (ni > 0) {
+                    out_target += hs->submit(kps + (size_t)i * cap, 0, kps_dl + (size_t)i * cap, 0, sizeof(orbx_keypoint) * ni, 1, &out_done);
+                    out_target += hs->submit(desc + (size_t)i * cap * 32, 0, desc_dl + (size_t)i * cap * 32, 0, 32 * ni, 1, &out_done);
+                }
+            }
+            size_t moff = 0;
+            for (int j = 0; j < nmaps; ++j) {
+                if (nq[j] > 0)
+                    out_target += hs->submit(best[j] + (size_t)f0 * nq[j], 0, (orbx_match*)(c->h_stage_out + o_best) + moff + (size_t)f0 * nq[j], 0,
+                                             (size_t)16 * nq[j] * (size_t)(f1 - f0), 1, &out_done);
+                moff += (size_t)nq[j] * batch;
+            }
+        }
+        hs->help_until(out_done, out_target);
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < lanes; ++k) if (nmaps > 0 && h_mstatus[k]) return match_timed_out(c);
+    bool over = false;
+    for (int i = 0; i < batch; ++i) {
+        if (h_status[i]) return fail(c, ORBX_E_INTERNAL, "device-side status set for a frame");
+        n_out[i] = h_counts[i];
+        if (h_counts[i] > cap) over = true;
+    }
+    if (over) return fail(c, ORBX_E_CAPACITY, "output capacity too small; n_out holds the needed counts");
+    return ORBX_OK;
+}
+
 int orbx_detect_and_compute_batch(orbx_ctx* c, const uint8_t* const* imgs, int batch, int w, int h, size_t step, int channels,
                                   orbx_keypoint* kps, uint8_t* desc, int cap, int* n_out)
 {
@@ -725,55 +929,7 @@ int orbx_detect_and_compute_batch(orbx_ctx* c, const uint8_t* const* imgs, int b
     if (batch == 0 || w == 0 || h == 0) return ORBX_OK;     // cv: empty image -> silent return, no keypoints
     if (!imgs || !n_out || (cap > 0 && (!kps || !desc))) return fail(c, ORBX_E_ARG, "null pointer");
     if (step < (size_t)w * channels) return fail(c, ORBX_E_ARG, "step smaller than a row");
-    CU(cudaSetDevice(c->device));
-    const size_t row = (size_t)w * channels, dstep = round_up(row, 16), fstride = dstep * h;   // 16: k_gray takes 128-bit loads
-    if ((rc = ensure(c, c->in, fstride * batch))) return rc;
-    if ((rc = ensure(c, c->kps, sizeof(orbx_keypoint) * (size_t)std::max(cap, 1) * batch))) return rc;
-    if ((rc = ensure(c, c->desc, (size_t)32 * std::max(cap, 1) * batch))) return rc;
-    if ((rc = ensure(c, c->counts, sizeof(int) * (size_t)batch))) return rc;
-    for (int i = 0; i < batch; ++i) if (!imgs[i]) return fail(c, ORBX_E_ARG, "null frame pointer");
-    if ((rc = set_geometry(c, w, h))) return rc;
-    CU(cudaMemsetAsync(c->status.p, 0, sizeof(int) * (size_t)batch, c->stream));
-    static const int host_lanes_max = std::max(1, std::min(HOST_MAX_LANES, getenv("ORBX_HOST_LANES") ? atoi(getenv("ORBX_HOST_LANES")) : HOST_DEFAULT_LANES));
-    int* h_counts = c->h_small;
-    int* h_status = c->h_small + batch;
-    // Frame ranges ("lanes") on their own streams: upload -> kernels -> download per lane, so the H2D copy of lane k+1
-    // runs under the kernels of lane k and the D2H of lane k under the kernels of lane k+1 (PCIe is the bound here).
-    const int lanes = c->profiling ? 1 : std::max(1, std::min(host_lanes_max, batch / HOST_LANE_MIN_FRAMES));
-    if (lanes > 1) CU(cudaEventRecord(c->ev_fork, c->stream));
-    for (int k = 0; k < lanes; ++k) {
-        int f0, f1;
-        host_lane_range(batch, lanes, k, &f0, &f1);
-        cudaStream_t st = k == 0 ? c->stream : c->lane[k];
-        if (k > 0) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
-        if ((rc = upload_frames(c, st, imgs, f0, f1, step, row, h, dstep, fstride))) return rc;
-        if ((rc = run_extract_range(c, st, c->profiling, f0, f1 - f0, (const uint8_t*)c->in.p, dstep,
-                                    fstride, channels, (float*)c->kps.p, (uint8_t*)c->desc.p, cap, (int*)c->counts.p)))
-            return rc;
-        const size_t n = (size_t)(f1 - f0);
-        CU(cudaMemcpyAsync(h_counts + f0, (int*)c->counts.p + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h_status + f0, (int*)c->status.p + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
-        if (cap > 0) {
-            // outputs are [batch][cap] on both sides: bulk copies per lane (records past n_out[i] are unspecified)
-            CU(cudaMemcpyAsync(kps + (size_t)f0 * cap, (orbx_keypoint*)c->kps.p + (size_t)f0 * cap, sizeof(orbx_keypoint) * (size_t)cap * n, cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, (uint8_t*)c->desc.p + (size_t)f0 * cap * 32, (size_t)32 * cap * n, cudaMemcpyDeviceToHost, st));
-        }
-        if (k > 0) { CU(cudaEventRecord(c->ev_join[k], st)); CU(cudaStreamWaitEvent(c->stream, c->ev_join[k], 0)); }
-    }
-    CU(cudaGetLastError());
-    c->last_batch = batch;
-    c->out_cap = cap;
-    c->view_desc = (const uint8_t*)c->desc.p; c->view_counts = (const int*)c->counts.p; c->view_frames = batch;
-    if (c->profiling) for (int i = 0; i < 6; ++i) c->stage_valid[i] = true;
-    CU(cudaStreamSynchronize(c->stream));
-    bool over = false;
-    for (int i = 0; i < batch; ++i) {
-        if (h_status[i]) return fail(c, ORBX_E_INTERNAL, "device-side status set for a frame");
-        n_out[i] = h_counts[i];
-        if (h_counts[i] > cap) over = true;
-    }
-    if (over) return fail(c, ORBX_E_CAPACITY, "output capacity too small; n_out holds the needed counts");
-    return ORBX_OK;
+    return host_batch(c, imgs, batch, w, h, step, channels, kps, desc, cap, n_out, nullptr, nullptr, 0, nullptr);
 }
 
 int orbx_extract_match_batch(orbx_ctx* c, const uint8_t* const* imgs, int batch, int w, int h, size_t step, int channels,
@@ -793,74 +949,25 @@ int orbx_extract_match_batch(orbx_ctx* c, const uint8_t* const* imgs, int batch,
     }
     if (step < (size_t)w * channels) return fail(c, ORBX_E_ARG, "step smaller than a row");
     if (cap >= MT_MAX_TRAIN) return fail(c, ORBX_E_UNSUPPORTED, "capacity larger than 2^20 - 1 rows");
+    return host_batch(c, imgs, batch, w, h, step, channels, kps, desc, cap, n_out, queries, nq, nmaps, best);
+}
+
+int orbx_host_register(orbx_ctx* c, void* ptr, size_t bytes)
+{
+    if (!c) return ORBX_E_ARG;
+    if (!ptr || bytes == 0) return fail(c, ORBX_E_ARG, "null pointer / empty range");
     CU(cudaSetDevice(c->device));
-    const size_t row = (size_t)w * channels, dstep = round_up(row, 16), fstride = dstep * h;
-    size_t qrows = 0, mrows = 0;
-    for (int j = 0; j < nmaps; ++j) { qrows += (size_t)nq[j]; mrows += (size_t)nq[j] * batch; }
-    if ((rc = ensure(c, c->in, fstride * batch)) || (rc = ensure(c, c->kps, sizeof(orbx_keypoint) * (size_t)cap * batch)) ||
-        (rc = ensure(c, c->desc, (size_t)32 * cap * batch)) || (rc = ensure(c, c->counts, sizeof(int) * (size_t)batch)) ||
-        (rc = ensure(c, c->mq, std::max<size_t>(qrows, 1) * 32)) || (rc = ensure(c, c->mbest, std::max<size_t>(mrows, 1) * 16)) ||
-        (rc = ensure(c, c->mstatus, sizeof(int) * 16)))
-        return rc;
-    for (int i = 0; i < batch; ++i) if (!imgs[i]) return fail(c, ORBX_E_ARG, "null frame pointer");
-    if ((rc = set_geometry(c, w, h))) return rc;
-    CU(cudaMemsetAsync(c->status.p, 0, sizeof(int) * (size_t)batch, c->stream));
-    {
-        size_t off = 0;
-        for (int j = 0; j < nmaps; ++j) {
-            if (nq[j] > 0) CU(cudaMemcpyAsync((uint8_t*)c->mq.p + off * 32, queries[j], (size_t)nq[j] * 32, cudaMemcpyHostToDevice, c->stream));
-            off += (size_t)nq[j];
-        }
-    }
-    static const int host_lanes_max = std::max(1, std::min(HOST_MAX_LANES, getenv("ORBX_HOST_LANES") ? atoi(getenv("ORBX_HOST_LANES")) : HOST_DEFAULT_LANES));
-    int* h_counts = c->h_small;
-    int* h_status = c->h_small + batch;
-    int* h_mstatus = c->h_small + 2 * batch;
-    const int lanes = c->profiling ? 1 : std::max(1, std::min(host_lanes_max, batch / HOST_LANE_MIN_FRAMES));
-    CU(cudaEventRecord(c->ev_fork, c->stream));
-    for (int k = 0; k < lanes; ++k) {
-        int f0, f1;
-        host_lane_range(batch, lanes, k, &f0, &f1);
-        const size_t n = (size_t)(f1 - f0);
-        cudaStream_t st = k == 0 ? c->stream : c->lane[k];
-        if (k > 0) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
-        if ((rc = upload_frames(c, st, imgs, f0, f1, step, row, h, dstep, fstride))) return rc;
-        if ((rc = run_extract_range(c, st, c->profiling, f0, f1 - f0, (const uint8_t*)c->in.p, dstep,
-                                    fstride, channels, (float*)c->kps.p, (uint8_t*)c->desc.p, cap, (int*)c->counts.p)))
-            return rc;
-        CU(cudaMemcpyAsync(h_counts + f0, (int*)c->counts.p + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(h_status + f0, (int*)c->status.p + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(kps + (size_t)f0 * cap, (orbx_keypoint*)c->kps.p + (size_t)f0 * cap, sizeof(orbx_keypoint) * (size_t)cap * n, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(desc + (size_t)f0 * cap * 32, (uint8_t*)c->desc.p + (size_t)f0 * cap * 32, (size_t)32 * cap * n, cudaMemcpyDeviceToHost, st));
-        size_t qoff = 0, moff = 0;
-        for (int j = 0; j < nmaps; ++j) {
-            if (nq[j] > 0) {
-                int4* d_best = (int4*)c->mbest.p + moff + (size_t)f0 * nq[j];
-                // train sets = this lane's frames, straight from the extraction outputs ([frame][cap][32] + counts)
-                if ((rc = run_match(c, (const uint8_t*)c->mq.p + qoff * 32, nq[j], (const uint8_t*)c->desc.p + (size_t)f0 * cap * 32, cap, cap,
-                                    (const int*)c->counts.p + f0, (int)n, d_best, nullptr, st, k)))
-                    return rc;
-                CU(cudaMemcpyAsync(best[j] + (size_t)f0 * nq[j], d_best, (size_t)16 * nq[j] * n, cudaMemcpyDeviceToHost, st));
-            }
-            qoff += (size_t)nq[j]; moff += (size_t)nq[j] * batch;
-        }
-        CU(cudaMemcpyAsync(h_mstatus + k, (int*)c->mstatus.p + k, sizeof(int), cudaMemcpyDeviceToHost, st));
-        if (k > 0) { CU(cudaEventRecord(c->ev_join[k], st)); CU(cudaStreamWaitEvent(c->stream, c->ev_join[k], 0)); }
-    }
-    CU(cudaGetLastError());
-    c->last_batch = batch;
-    c->out_cap = cap;
-    c->view_desc = (const uint8_t*)c->desc.p; c->view_counts = (const int*)c->counts.p; c->view_frames = batch;
-    if (c->profiling) for (int i = 0; i < 6; ++i) c->stage_valid[i] = true;
-    CU(cudaStreamSynchronize(c->stream));
-    for (int k = 0; k < lanes; ++k) if (nmaps > 0 && h_mstatus[k]) return match_timed_out(c);
-    bool over = false;
-    for (int i = 0; i < batch; ++i) {
-        if (h_status[i]) return fail(c, ORBX_E_INTERNAL, "device-side status set for a frame");
-        n_out[i] = h_counts[i];
-        if (h_counts[i] > cap) over = true;
-    }
-    if (over) return fail(c, ORBX_E_CAPACITY, "output capacity too small; n_out holds the needed counts");
+    CU(cudaHostRegister(ptr, bytes, cudaHostRegisterPortable));
+    return ORBX_OK;
+}
+
+int orbx_host_unregister(orbx_ctx* c, void* ptr)
+{
+    if (!c) return ORBX_E_ARG;
+    if (!ptr) return fail(c, ORBX_E_ARG, "null pointer");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));                    // nothing of this context may still be copying from / into it
+    CU(cudaHostUnregister(ptr));
     return ORBX_OK;
 }
 
