@@ -102,8 +102,11 @@ struct orbx_ctx {
     int a_head = 0, a_inflight = 0;          // oldest in-flight slot, number in flight
 
     bool profiling = false;
+    int force_kernels = -1;                   // orbx_debug_force_kernels: -1 by launch size, 0 warp-private TMA kernels, 1 CTA-cooperative kernels
     cudaEvent_t ev[N_STAGES + 2] = {};   // 0..6 bracket the six extraction stages, 7..8 the matcher
     cudaStream_t lane[HOST_MAX_LANES] = {};   // extra frame-range pipelines (lane 0 is `stream`)
+    cudaStream_t side[HOST_MAX_LANES] = {};   // per lane: high-priority stream of the small pyramid levels + their FAST bands
+    cudaEvent_t ev_sfork[HOST_MAX_LANES] = {}, ev_sjoin[HOST_MAX_LANES] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[HOST_MAX_LANES] = {};
     float stage_ms[N_STAGES] = {};
     bool stage_valid[N_STAGES] = {};
@@ -357,7 +360,7 @@ static void host_lane_range(int batch, int lanes, int k, int* f0, int* f1)
 
 // The kernel sequence for frames [f0, f0 + nb) on stream `st`.  Every buffer is frame-major, so a frame range is
 // just a base-pointer offset.
-int run_extract_range(orbx_ctx* c, cudaStream_t st, bool marks, int f0, int nb,
+int run_extract_range(orbx_ctx* c, cudaStream_t st, int lane_id, bool marks, int f0, int nb,
                       const uint8_t* d_imgs, size_t step, size_t frame_stride, int channels, float* d_kps, uint8_t* d_desc, int cap,
                       int* d_counts)
 {
@@ -376,47 +379,69 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, bool marks, int f0, int nb,
     d_kps += F * cap * 7; d_desc += F * cap * 32; d_counts += F;
     const uint32_t* tabs = (const uint32_t*)c->tabs.p;
     const unsigned B = (unsigned)nb;
+    cudaStream_t side = c->side[lane_id];
+    cudaEvent_t side_fork = c->ev_sfork[lane_id], side_join = c->ev_sjoin[lane_id];
 
     if (marks) stage_mark(c, 0);
     {
-        {
-            const int aligned16 = ((reinterpret_cast<uintptr_t>(d_imgs) | step | frame_stride) & 15) == 0;
-            const dim3 blk(32, 8);
-            const dim3 grd((unsigned)((g.L[0].pitch / 16 + 31) / 32), (unsigned)((g.L[0].h + 7) / 8), B);
-            if (channels == 3) k_gray<3><<<grd, blk, 0, st>>>(d_imgs, frame_stride, step, aligned16, g, pyr);
-            else               k_gray<1><<<grd, blk, 0, st>>>(d_imgs, frame_stride, step, aligned16, g, pyr);
-            ++c->launches;
-        }
-        if (marks) stage_mark(c, 1);
-        for (int l = 1; l < g.nlevels; ++l) {
-            if (g.L[l].w <= 0 || g.L[l].h <= 0) continue;
-            const int nitems = (g.L[l].pitch / 8) * ((g.L[l].h + PYR_RH - 1) / PYR_RH);     // (column octet, row strip) work items
-            const dim3 grd((unsigned)((nitems + PYR_NT - 1) / PYR_NT), B);
-            static const int old_pyr = getenv("ORBX_PYR_OLD") ? atoi(getenv("ORBX_PYR_OLD")) : 0;   // A/B timing only
-            if (g.L[l].pt_ok && !old_pyr)
-                k_pyr_tma<<<dim3((unsigned)((g.L[l].pt_ntask + PT_NWARP - 1) / PT_NWARP), B), PT_NWARP * 32,
-                            PT_NWARP * pt_warp_bytes(g.L[l].pt_bw, g.L[l].pt_bh) + 128, st>>>(g, c->pmaps.m[l], l, f0, (uint8_t*)c->pyr.p, tabs, status);
-            else if (g.L[l].xspan <= 7) k_pyr_down<false><<<grd, PYR_NT, 0, st>>>(g, l, pyr, tabs);
-            else                   k_pyr_down<true><<<grd, PYR_NT, 0, st>>>(g, l, pyr, tabs);
-            ++c->launches;
-        }
-    }
-    if (marks) stage_mark(c, 2);
-    if (g.total_bands > 0) {
-        static const int old_fast = getenv("ORBX_FAST_OLD") ? atoi(getenv("ORBX_FAST_OLD")) : 0;   // A/B timing only
-        if (old_fast) k_fast_bands<FAST_R, FAST_NT><<<dim3((unsigned)g.total_bands, B), FAST_NT, 0, st>>>(g, pyr, rowcnt, rowent);
-        else {
-            static const int nw = getenv("ORBX_FAST_NWARP") ? atoi(getenv("ORBX_FAST_NWARP")) : FAST_NWARP;   // experiments
-            auto launch = [&](auto tag) {
-                constexpr int NW = decltype(tag)::value;
-                static bool attr = false;
-                if (!attr) { cudaFuncSetAttribute(k_fast_warp<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, NW * FW_WARP_BYTES + 128); attr = true; }
-                k_fast_warp<NW><<<dim3((unsigned)((g.total_bands + NW - 1) / NW), B), NW * 32, NW * FW_WARP_BYTES + 128, st>>>(g, c->fmaps, f0, rowcnt, rowent, status);
-            };
-            if (nw == 2) launch(ic<2>{}); else if (nw == 7) launch(ic<7>{}); else if (nw == 1) launch(ic<1>{}); else launch(ic<FAST_NWARP>{});
-        }
+        const int aligned16 = ((reinterpret_cast<uintptr_t>(d_imgs) | step | frame_stride) & 15) == 0;
+        const dim3 blk(32, 8);
+        const dim3 grd((unsigned)((g.L[0].pitch / 16 + 31) / 32), (unsigned)((g.L[0].h + 7) / 8), B);
+        if (channels == 3) k_gray<3><<<grd, blk, 0, st>>>(d_imgs, frame_stride, step, aligned16, g, pyr);
+        else               k_gray<1><<<grd, blk, 0, st>>>(d_imgs, frame_stride, step, aligned16, g, pyr);
         ++c->launches;
     }
+    if (marks) stage_mark(c, 1);
+    // Kernel choice by the size of the launch: the warp-private TMA kernels (one warp walks a whole band / a stack of strips)
+    // win once there are enough warps to fill the GPU; below about 26 VGA frames' worth of pixels the CTA-cooperative
+    // kernels have the shorter critical path (one 640x480 frame: pyramid + FAST 0.077 ms against 0.115 ms), which is what the
+    // sequential VO loop (one frame per call, src/frontend.cpp:98-108) feels.  ORBX_*_OLD = 1 / 0 forces one or the other.
+    const bool small_launch = (long)nb * g.w * g.h < 8000000L;
+    static const int env_old_pyr = getenv("ORBX_PYR_OLD") ? atoi(getenv("ORBX_PYR_OLD")) : -1;
+    static const int env_old_fast = getenv("ORBX_FAST_OLD") ? atoi(getenv("ORBX_FAST_OLD")) : -1;
+    const bool old_pyr = c->force_kernels >= 0 ? c->force_kernels != 0 : env_old_pyr >= 0 ? env_old_pyr != 0 : small_launch;
+    const bool old_fast = c->force_kernels >= 0 ? c->force_kernels != 0 : env_old_fast >= 0 ? env_old_fast != 0 : small_launch;
+    auto launch_pyr = [&](int l, cudaStream_t s) {
+        if (g.L[l].w <= 0 || g.L[l].h <= 0) return;
+        const int nitems = (g.L[l].pitch / 8) * ((g.L[l].h + PYR_RH - 1) / PYR_RH);     // (column octet, row strip) work items
+        const dim3 grd((unsigned)((nitems + PYR_NT - 1) / PYR_NT), B);
+        if (g.L[l].pt_ok && !old_pyr)
+            k_pyr_tma<<<dim3((unsigned)((g.L[l].pt_ntask + PT_NWARP - 1) / PT_NWARP), B), PT_NWARP * 32,
+                        PT_NWARP * pt_warp_bytes(g.L[l].pt_bw, g.L[l].pt_bh) + 128, s>>>(g, c->pmaps.m[l], l, f0, (uint8_t*)c->pyr.p, tabs, status);
+        else if (g.L[l].xspan <= 7) k_pyr_down<false><<<grd, PYR_NT, 0, s>>>(g, l, pyr, tabs);
+        else                   k_pyr_down<true><<<grd, PYR_NT, 0, s>>>(g, l, pyr, tabs);
+        ++c->launches;
+    };
+    auto launch_fast = [&](int band_lo, int band_hi, cudaStream_t s) {
+        if (band_hi <= band_lo) return;
+        if (old_fast) {
+            if (band_lo == 0) k_fast_bands<FAST_R, FAST_NT><<<dim3((unsigned)g.total_bands, B), FAST_NT, 0, s>>>(g, pyr, rowcnt, rowent);
+        } else
+            k_fast_warp<FAST_NWARP><<<dim3((unsigned)((band_hi - band_lo + FAST_NWARP - 1) / FAST_NWARP), B), FAST_NWARP * 32, FAST_NWARP * FW_WARP_BYTES + 128, s>>>(
+                g, c->fmaps, f0, band_lo, band_hi, rowcnt, rowent, status);
+        ++c->launches;
+    };
+    // The small upper levels are a chain of short, latency-bound launches (at 640x480 levels 4..7 take as long as levels 1..3
+    // for a fifth of the pixels).  They leave the critical path: from level `lt` on, the pyramid chain and the FAST bands of
+    // those levels run on a HIGH-PRIORITY side stream (their few CTAs take the next free slots) underneath the FAST launch of the
+    // large levels, which is issue-bound and has slots to spare for them only in time, not in space.
+    int lt = g.nlevels;                                      // first level of the side chain
+    {
+        static const int tail_px = getenv("ORBX_TAIL_PX") ? atoi(getenv("ORBX_TAIL_PX")) : 100000;   // levels below this many pixels are "small"; 0: no side chain
+        for (int l = g.nlevels - 1; l >= 2 && (long)g.L[l].w * g.L[l].h < tail_px; --l) lt = l;
+        if (old_fast || g.total_bands <= 0) lt = g.nlevels;
+    }
+    for (int l = 1; l < lt; ++l) launch_pyr(l, st);
+    if (marks) stage_mark(c, 2);
+    if (lt < g.nlevels) {
+        CU(cudaEventRecord(side_fork, st));
+        CU(cudaStreamWaitEvent(side, side_fork, 0));
+        for (int l = lt; l < g.nlevels; ++l) launch_pyr(l, side);
+        launch_fast(g.L[lt].band0, g.total_bands, side);
+        CU(cudaEventRecord(side_join, side));
+        launch_fast(0, g.L[lt].band0, st);
+        CU(cudaStreamWaitEvent(st, side_join, 0));
+    } else if (g.total_bands > 0) launch_fast(0, g.total_bands, st);
     // (Selection and blur were also tried as interleaved CTAs of one launch and as concurrent kernels on a side stream:
     //  neither beats running them back to back -- the selection kernel is bound by the latency of its longest CTA, not by
     //  issue slots it could lend to the blur.)
@@ -442,11 +467,11 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, bool marks, int f0, int nb,
         k_describe<<<dim3((unsigned)((std::max(cap, 1) + DESC_KPB * DESC_KPW - 1) / (DESC_KPB * DESC_KPW)), B), DESC_NT, 0, st>>>(
             g, pyr, blur, work, fincnt, (const float4*)c->pattern.p, d_kps, d_desc, d_counts, cap);
     else {
-        // groups of 4 slots per warp: enough warps for two full waves (148 SMs x 24 resident warps) when the batch is large,
-        // one group per warp (lowest latency) when it is a single frame
+        // groups of 4 slots per warp: four per warp when the batch is large (the warp's set-up is shared, and there are still
+        // enough CTAs for several waves), one group per warp (lowest latency) when it is a single frame
         static const int env_gpw = getenv("ORBX_DESC_GPW") ? atoi(getenv("ORBX_DESC_GPW")) : 0;
         const long groups = (long)nb * ((std::min(std::max(cap, 1), std::max(c->nfeatures, 1)) + DS_G - 1) / DS_G);
-        const int gpw = env_gpw > 0 ? std::min(env_gpw, DS_MAX_GPW) : (int)std::max(1L, std::min((long)DS_MAX_GPW, groups / (148L * 24 * 2)));
+        const int gpw = env_gpw > 0 ? std::min(env_gpw, DS_MAX_GPW) : (groups >= 148L * 24 * 8 ? 4 : 1);   // measured at 256 VGA frames: 1 / 2 / 4 / 8 / 16 -> 0.192 / 0.192 / 0.185 / 0.205 / 0.259 ms
         const int gcap = (std::max(cap, 1) + DS_G - 1) / DS_G;
         k_describe_tma<<<dim3((unsigned)((gcap + DS_NW * gpw - 1) / (DS_NW * gpw)), B), DS_NW * 32, DS_NW * DS_WARP_BYTES + 128, st>>>(
             g, c->dmaps, f0, work, fincnt, (const float4*)c->pattern.p, d_kps, d_desc, d_counts, cap, gpw, status);
@@ -472,7 +497,7 @@ int run_extract(orbx_ctx* c, const uint8_t* d_imgs, int batch, int w, int h, siz
     if (batch < lanes * LANE_MIN_FRAMES) lanes = 1;
     if (c->profiling) lanes = 1;
     if (lanes == 1) {
-        rc = run_extract_range(c, c->stream, c->profiling, 0, batch, d_imgs, step,
+        rc = run_extract_range(c, c->stream, 0, c->profiling, 0, batch, d_imgs, step,
                                frame_stride, channels, d_kps, d_desc, cap, d_counts);
         if (rc) return rc;
     } else {
@@ -481,7 +506,7 @@ int run_extract(orbx_ctx* c, const uint8_t* d_imgs, int batch, int w, int h, siz
             const int f0 = (int)((long)batch * k / lanes), f1 = (int)((long)batch * (k + 1) / lanes);
             cudaStream_t st = k == 0 ? c->stream : c->lane[k];
             if (k > 0) CU(cudaStreamWaitEvent(st, c->ev_fork, 0));
-            rc = run_extract_range(c, st, false, f0, f1 - f0, d_imgs, step, frame_stride, channels, d_kps, d_desc, cap, d_counts);
+            rc = run_extract_range(c, st, k, false, f0, f1 - f0, d_imgs, step, frame_stride, channels, d_kps, d_desc, cap, d_counts);
             if (rc) return rc;
             if (k > 0) { CU(cudaEventRecord(c->ev_join[k], st)); CU(cudaStreamWaitEvent(c->stream, c->ev_join[k], 0)); }
         }
@@ -659,6 +684,14 @@ int orbx_create(orbx_ctx** out, int device, int nfeatures, float scale_factor, i
     for (int k = 0; k < HOST_MAX_LANES; ++k)
         if ((k > 0 && cudaStreamCreateWithFlags(&c->lane[k], cudaStreamNonBlocking) != cudaSuccess) || cudaEventCreateWithFlags(&c->ev_join[k], cudaEventDisableTiming) != cudaSuccess) return bail(ORBX_E_CUDA);
     if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) return bail(ORBX_E_CUDA);
+    {
+        int prio_lo = 0, prio_hi = 0;
+        if (cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi) != cudaSuccess) return bail(ORBX_E_CUDA);
+        for (int k = 0; k < HOST_MAX_LANES; ++k)
+            if (cudaStreamCreateWithPriority(&c->side[k], cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+                cudaEventCreateWithFlags(&c->ev_sfork[k], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&c->ev_sjoin[k], cudaEventDisableTiming) != cudaSuccess) return bail(ORBX_E_CUDA);
+    }
     for (int i = 0; i < N_STAGES + 2; ++i) if (cudaEventCreate(&c->ev[i]) != cudaSuccess) return bail(ORBX_E_CUDA);
     build_geom(c, max_w, max_h, &c->geom_max, nullptr);
     const Geom& g = c->geom_max;
@@ -715,6 +748,11 @@ void orbx_destroy(orbx_ctx* c)
     for (int i = 0; i < N_STAGES + 2; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int k = 0; k < HOST_MAX_LANES; ++k) { if (c->ev_join[k]) cudaEventDestroy(c->ev_join[k]); if (c->lane[k]) { cudaStreamSynchronize(c->lane[k]); cudaStreamDestroy(c->lane[k]); } }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    for (int k = 0; k < HOST_MAX_LANES; ++k) {
+        if (c->side[k]) { cudaStreamSynchronize(c->side[k]); cudaStreamDestroy(c->side[k]); }
+        if (c->ev_sfork[k]) cudaEventDestroy(c->ev_sfork[k]);
+        if (c->ev_sjoin[k]) cudaEventDestroy(c->ev_sjoin[k]);
+    }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -811,6 +849,8 @@ static int host_batch(orbx_ctx* c, const uint8_t* const* imgs, int batch, int w,
     if (stage_in && (rc = ensure_pinned(c, c->h_stage_in, c->h_stage_in_bytes, fstride * batch))) return rc;
     if (stage_out && (rc = ensure_pinned(c, c->h_stage_out, c->h_stage_out_bytes, o_best + mrows * 16))) return rc;
     HostStager* hs = (stage_in || stage_out) ? stager_of(c) : nullptr;
+    static const size_t wake_bytes = getenv("ORBX_STAGE_WAKE_BYTES") ? (size_t)atoll(getenv("ORBX_STAGE_WAKE_BYTES")) : (size_t)2 << 20;
+    const bool wake_in = fstride * batch >= wake_bytes, wake_out = (size_t)60 * capz * batch + mrows * 16 >= wake_bytes;
     orbx_keypoint* kps_dl = stage_out ? (orbx_keypoint*)(c->h_stage_out + o_kps) : kps;       // where the D2H copies land
     uint8_t* desc_dl = stage_out ? c->h_stage_out + o_desc : desc;
 
@@ -839,7 +879,7 @@ static int host_batch(orbx_ctx* c, const uint8_t* const* imgs, int batch, int w,
             int f0, f1;
             host_lane_range(batch, lanes, k, &f0, &f1);
             in_done[k].store(0, std::memory_order_relaxed);
-            for (int i = f0; i < f1; ++i) in_target[k] += hs->submit(c->h_stage_in + fstride * i, dstep, imgs[i], step, row, (size_t)h, &in_done[k]);
+            for (int i = f0; i < f1; ++i) in_target[k] += hs->submit(c->h_stage_in + fstride * i, dstep, imgs[i], step, row, (size_t)h, &in_done[k], wake_in);
         }
     CU(cudaEventRecord(c->ev_fork, c->stream));
     for (int k = 0; k < lanes; ++k) {
@@ -852,7 +892,7 @@ static int host_batch(orbx_ctx* c, const uint8_t* const* imgs, int batch, int w,
             hs->help_until(in_done[k], in_target[k]);        // (the pinned image has the device layout: one copy per lane)
             CU(cudaMemcpyAsync((uint8_t*)c->in.p + fstride * f0, c->h_stage_in + fstride * f0, fstride * n, cudaMemcpyHostToDevice, st));
         } else if ((rc = upload_frames(c, st, imgs, f0, f1, step, row, h, dstep, fstride))) return rc;
-        if ((rc = run_extract_range(c, st, c->profiling, f0, f1 - f0, (const uint8_t*)c->in.p, dstep,
+        if ((rc = run_extract_range(c, st, k, c->profiling, f0, f1 - f0, (const uint8_t*)c->in.p, dstep,
                                     fstride, channels, (float*)c->kps.p, (uint8_t*)c->desc.p, cap, (int*)c->counts.p)))
             return rc;
         CU(cudaMemcpyAsync(h_counts + f0, (int*)c->counts.p + f0, sizeof(int) * n, cudaMemcpyDeviceToHost, st));
@@ -894,15 +934,15 @@ static int host_batch(orbx_ctx* c, const uint8_t* const* imgs, int batch, int w,
             for (int i = f0; i < f1; ++i) {
                 const size_t ni = (size_t)std::max(0, std::min(h_counts[i], cap));
                 if (ni > 0) {
-                    out_target += hs->submit(kps + (size_t)i * cap, 0, kps_dl + (size_t)i * cap, 0, sizeof(orbx_keypoint) * ni, 1, &out_done);
-                    out_target += hs->submit(desc + (size_t)i * cap * 32, 0, desc_dl + (size_t)i * cap * 32, 0, 32 * ni, 1, &out_done);
+                    out_target += hs->submit(kps + (size_t)i * cap, 0, kps_dl + (size_t)i * cap, 0, sizeof(orbx_keypoint) * ni, 1, &out_done, wake_out);
+                    out_target += hs->submit(desc + (size_t)i * cap * 32, 0, desc_dl + (size_t)i * cap * 32, 0, 32 * ni, 1, &out_done, wake_out);
                 }
             }
             size_t moff = 0;
             for (int j = 0; j < nmaps; ++j) {
                 if (nq[j] > 0)
                     out_target += hs->submit(best[j] + (size_t)f0 * nq[j], 0, (orbx_match*)(c->h_stage_out + o_best) + moff + (size_t)f0 * nq[j], 0,
-                                             (size_t)16 * nq[j] * (size_t)(f1 - f0), 1, &out_done);
+                                             (size_t)16 * nq[j] * (size_t)(f1 - f0), 1, &out_done, wake_out);
                 moff += (size_t)nq[j] * batch;
             }
         }
@@ -1109,6 +1149,13 @@ int orbx_debug_read_fast(orbx_ctx* c, int frame, int level, int32_t* x, int32_t*
             }
     *n_out = n;
     return n > cap ? ORBX_E_CAPACITY : ORBX_OK;
+}
+
+int orbx_debug_force_kernels(orbx_ctx* c, int mode)
+{
+    if (!c || mode < -1 || mode > 1) return ORBX_E_ARG;
+    c->force_kernels = mode;
+    return ORBX_OK;
 }
 
 int orbx_set_profiling(orbx_ctx* c, int enable)
@@ -1451,7 +1498,7 @@ int orbx_submit_frame(orbx_ctx* c, const uint8_t* img, int w, int h, size_t step
     // everything below is stream-ordered behind the previous frame: the shared per-frame workspace is reused safely
     CU(cudaMemcpyAsync(c->in.p, a.h_in, fstride, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemsetAsync(c->status.p, 0, sizeof(int), c->stream));
-    if ((rc = run_extract_range(c, c->stream, false, 0, 1, (const uint8_t*)c->in.p, dstep, fstride, channels, (float*)a.d_kps.p,
+    if ((rc = run_extract_range(c, c->stream, 0, false, 0, 1, (const uint8_t*)c->in.p, dstep, fstride, channels, (float*)a.d_kps.p,
                                 (uint8_t*)a.d_desc.p, cap, (int*)a.d_counts.p)))
         return rc;
     CU(cudaMemcpyAsync(a.h_out, a.d_counts.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));

@@ -69,15 +69,15 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned bar_s, unsigned bytes)
 
 template <int NWARP>
 __global__ void __launch_bounds__(NWARP * 32, 28 / NWARP) k_fast_warp(const __grid_constant__ Geom g, const __grid_constant__ FastMaps maps, int f0,
-                                                          uint32_t* __restrict__ rowcnt, uint32_t* __restrict__ rowent, int* __restrict__ status)
+                                                          int band_lo, int band_hi, uint32_t* __restrict__ rowcnt, uint32_t* __restrict__ rowent, int* __restrict__ status)
 {
     extern __shared__ __align__(128) uint8_t fw_smem[];
     constexpr int T = ORBX_FAST_T;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned lt = lanemask_lt();
     const int f = blockIdx.y;
-    const int gb = blockIdx.x * NWARP + wid;                 // band index inside the frame
-    if (gb >= g.total_bands) return;                         // (no block-level synchronisation anywhere: warps are independent)
+    const int gb = band_lo + blockIdx.x * NWARP + wid;       // band index inside the frame; this launch covers bands [band_lo, band_hi)
+    if (gb >= band_hi) return;                               // (no block-level synchronisation anywhere: warps are independent)
     int l = 0;
 #pragma unroll 1
     for (int i = 1; i < g.nlevels; ++i) if (gb >= g.L[i].band0) l = i;

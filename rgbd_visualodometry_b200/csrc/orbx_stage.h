@@ -42,7 +42,7 @@ public:
 
     // Queue a 2-D copy cut into pieces of about PIECE bytes (whole rows; one contiguous block when the pitches equal the
     // row length).  Returns the number of pieces, i.e. how much `done` will grow.
-    int submit(void* dst, size_t dpitch, const void* src, size_t spitch, size_t row_bytes, size_t rows, std::atomic<int>* done)
+    int submit(void* dst, size_t dpitch, const void* src, size_t spitch, size_t row_bytes, size_t rows, std::atomic<int>* done, bool wake = true)
     {
         if (rows == 0 || row_bytes == 0) return 0;
         if (dpitch == row_bytes && spitch == row_bytes) { row_bytes *= rows; dpitch = spitch = row_bytes; rows = 1; }
@@ -56,7 +56,7 @@ public:
             for (size_t r = 0; r < rows; r += per, ++n)
                 q_.push_back(Job{(uint8_t*)dst + r * dpitch, (const uint8_t*)src + r * spitch, dpitch, spitch, row_bytes, rows - r < per ? rows - r : per, done});
         }
-        if (n > 1) cv_.notify_all(); else cv_.notify_one();
+        if (wake) { if (n > 1) cv_.notify_all(); else cv_.notify_one(); }   // (!wake: a small job the calling thread takes itself in help_until)
         return n;
     }
 

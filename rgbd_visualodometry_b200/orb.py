@@ -272,6 +272,17 @@ class Context:
         self._check(self.lib.orbx_debug_read_fast(self.h, frame, level, _ptr(x), _ptr(y), _ptr(s), cap, C.byref(n)))
         return x[:n.value], y[:n.value], s[:n.value]
 
+    def force_kernels(self, mode: int):
+        """-1: pyramid / FAST kernel family by launch size (default); 0: warp-private TMA kernels; 1: CTA-cooperative kernels."""
+        self._check(self.lib.orbx_debug_force_kernels(self.h, mode))
+
+    def host_register(self, arr: np.ndarray):
+        """Page-lock a long-lived host buffer (cudaHostRegister behind the C-ABI); pair with host_unregister."""
+        self._check(self.lib.orbx_host_register(self.h, arr.ctypes.data, arr.nbytes))
+
+    def host_unregister(self, arr: np.ndarray):
+        self._check(self.lib.orbx_host_unregister(self.h, arr.ctypes.data))
+
     def set_profiling(self, on: bool):
         self._check(self.lib.orbx_set_profiling(self.h, 1 if on else 0))
 
@@ -284,8 +295,9 @@ class Context:
 class ORB:
     """cv::ORB stand-in (only the parameters the reference sets; the rest are OpenCV's defaults)."""
 
-    def __init__(self, nfeatures=500, scaleFactor=1.2, nlevels=8, device=0):
+    def __init__(self, nfeatures=500, scaleFactor=1.2, nlevels=8, device=0, kernels=-1):
         self.nfeatures, self.scaleFactor, self.nlevels, self.device = nfeatures, scaleFactor, nlevels, device
+        self.kernels = kernels                  # orbx_debug_force_kernels mode (tests run both kernel families)
         self._ctx = None
 
     def _context(self, w, h, b=1):
@@ -294,6 +306,8 @@ class ORB:
             if c is not None:
                 c.close()
             self._ctx = c = Context(self.nfeatures, self.scaleFactor, self.nlevels, max(w, 1), max(h, 1), max(b, 1), self.device)
+            if self.kernels >= 0:
+                c.force_kernels(self.kernels)
         return c
 
     def detectAndCompute(self, image, mask=None):
@@ -312,8 +326,8 @@ class ORB:
         return self._context(images[0].shape[1], images[0].shape[0], len(images)).detect_and_compute_batch(images)
 
 
-def ORB_create(nfeatures=500, scaleFactor=1.2, nlevels=8, device=0) -> ORB:
-    return ORB(nfeatures, scaleFactor, nlevels, device)
+def ORB_create(nfeatures=500, scaleFactor=1.2, nlevels=8, device=0, kernels=-1) -> ORB:
+    return ORB(nfeatures, scaleFactor, nlevels, device, kernels)
 
 
 class BFMatcher:

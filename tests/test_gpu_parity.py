@@ -30,12 +30,18 @@ def _assert_kp_equal(k, d, ko, do, what):
     assert np.array_equal(d, do), f"{what}: {int((d != do).any(axis=1).sum())} descriptors differ"
 
 
+# Pyramid and FAST exist as two kernel families chosen by launch size (orbx_debug_force_kernels): 0 = warp-private TMA
+# kernels (large launches), 1 = CTA-cooperative kernels (small launches).  Single-frame cases are run through both.
+KERNELS = [0, 1]
+
+
+@pytest.mark.parametrize("kernels", KERNELS)
 @pytest.mark.parametrize("name", list(ORB_CASES))
-def test_orb_vs_golden(orbmod, name):
+def test_orb_vs_golden(orbmod, name, kernels):
     mk, n = ORB_CASES[name]
     img = mk()
     g = np.load(os.path.join(GOLD, f"orb_{name}.npz"))
-    k, d = orbmod.ORB_create(n, 1.2, 8).detectAndCompute(img, None)
+    k, d = orbmod.ORB_create(n, 1.2, 8, kernels=kernels).detectAndCompute(img, None)
     gd = g["descriptors"]
     if len(g["keypoints"]) == 0:
         assert len(k) == 0 and d is None          # cv2 returns ((), None)
@@ -43,20 +49,23 @@ def test_orb_vs_golden(orbmod, name):
     _assert_kp_equal(k, d, g["keypoints"], gd, f"golden {name}")
 
 
+@pytest.mark.parametrize("kernels", KERNELS)
 @pytest.mark.parametrize("name", list(ORB_CASES_LARGE))
-def test_orb_vs_oracle_large(orbmod, oracle, name):
+def test_orb_vs_oracle_large(orbmod, oracle, name, kernels):
     mk, n = ORB_CASES_LARGE[name]
     img = mk()
-    k, d = orbmod.ORB_create(n, 1.2, 8).detectAndCompute(img, None)
+    k, d = orbmod.ORB_create(n, 1.2, 8, kernels=kernels).detectAndCompute(img, None)
     ko, do = oracle.detect_and_compute(img, n)
     _assert_kp_equal(k, d, ko, do, f"oracle {name}")
 
 
-def test_orb_stages_vs_oracle(orbmod, oracle):
+@pytest.mark.parametrize("kernels", KERNELS)
+def test_orb_stages_vs_oracle(orbmod, oracle, kernels):
     """Each kernel in isolation: pyramid levels and the raster-ordered FAST+NMS lists."""
     from rgbd_visualodometry_b200.synth import synth_frame
     img = synth_frame(467, 701, 21)
     ctx = orbmod.Context(700, 1.2, 8, 701, 467, 1)
+    ctx.force_kernels(kernels)
     ctx.detect_and_compute(img)
     _, _, dump = oracle.detect_and_compute(img, 700, dump=True)
     ws, hs, sc, q = ctx.level_geometry(701, 467)
@@ -456,15 +465,16 @@ def test_fused_extract_match_batch_equals_separate_calls_and_oracle(orbmod):
     assert best[0][0].tobytes() == O.match_hamming(maps[0], do).tobytes()
 
 
+@pytest.mark.parametrize("kernels", KERNELS)
 @pytest.mark.parametrize("params", [(300, 1.5, 4), (400, 2.0, 3), (600, 1.1, 12), (500, 1.2, 1), (500, 1.3, 6), (250, 2.5, 2)])
-def test_orb_other_scale_factors_and_level_counts(orbmod, params):
+def test_orb_other_scale_factors_and_level_counts(orbmod, params, kernels):
     """cv::ORB::create(nfeatures, scaleFactor, nlevels) with values other than the reference's yaml (1.2 / 8): the narrow
     and the wide pyramid kernels, 1 .. 12 levels.  Oracle == cv2 for these is pinned on the CPU side (test_oracle.py)."""
     from oracle import oracle as O
     from rgbd_visualodometry_b200.synth import synth_frame
     n, sf, nl = params
     img = synth_frame(480, 640, 31)
-    k, d = orbmod.ORB_create(n, sf, nl).detectAndCompute(img, None)
+    k, d = orbmod.ORB_create(n, sf, nl, kernels=kernels).detectAndCompute(img, None)
     ko, do = O.detect_and_compute(img, n, sf, nl)
     _assert_kp_equal(k, d, ko, do, f"ORB({n}, {sf}, {nl})")
 
@@ -474,3 +484,42 @@ def test_orb_rejects_scale_factor_beyond_the_pyramid_kernels(orbmod):
     with pytest.raises(orbmod.OrbxError) as e:
         orbmod.ORB_create(100, 3.5, 2).detectAndCompute(synth_frame(240, 320, 1), None)
     assert e.value.code == -5                                # ORBX_E_UNSUPPORTED, never a silently wrong pyramid
+
+
+def test_host_buffers_pageable_registered_and_strided_agree(orbmod, oracle):
+    """The host-buffer entry points give the same bytes whether the caller's buffers are pageable (staged through the
+    library's pinned memory by its copier threads: the reference's cv::Mat / std::vector case), page-locked with
+    orbx_host_register (copied from / into directly), or pageable with a padded row step -- with and without maps,
+    for a batch large enough to run several frame-range lanes, a partial last lane included."""
+    from rgbd_visualodometry_b200.synth import synth_frame, synth_descriptors
+    B, n, cap = 37, 300, 400
+    base = [synth_frame(240, 320, 900 + i) for i in range(6)]
+    frames = np.stack([np.roll(base[i % 6], 7 * (i // 6), axis=1) for i in range(B)])
+    maps = [synth_descriptors(700, 11), synth_descriptors(33, 12)]
+    ctx = orbmod.Context(n, 1.2, 8, 320, 240, B)
+    kp0, d0, c0, b0 = ctx.extract_match_batch(list(frames), maps, cap)                       # pageable in, pageable out
+    for i in (0, 5, 17, 36):
+        ko, do = oracle.detect_and_compute(frames[i], n)
+        _assert_kp_equal(kp0[i, :c0[i]], d0[i, :c0[i]], ko, do, f"pageable frame {i}")
+        assert b0[0][i].tobytes() == oracle.match_hamming(maps[0], do).tobytes()
+    pinned = frames.copy()
+    ctx.host_register(pinned)
+    try:
+        kp1, d1, c1, b1 = ctx.extract_match_batch(list(pinned), maps, cap)                   # page-locked in, pageable out
+    finally:
+        ctx.host_unregister(pinned)
+    padded = np.zeros((B, 240, 331, 3), np.uint8)
+    padded[:, :, :320] = frames
+    import ctypes as C
+    kp2 = np.zeros((B, cap), orbmod.KP_DTYPE); d2 = np.zeros((B, cap, 32), np.uint8); c2 = np.zeros(B, np.int32)
+    ptrs = (C.c_void_p * B)(*[padded[i].ctypes.data for i in range(B)])
+    rc = ctx.lib.orbx_detect_and_compute_batch(ctx.h, ptrs, B, 320, 240, padded.strides[1], 3, kp2.ctypes.data, d2.ctypes.data, cap,
+                                               c2.ctypes.data)                                 # pageable, step = 993 bytes
+    assert rc == 0
+    assert np.array_equal(c0, c1) and np.array_equal(c0, c2)
+    for i in range(B):
+        assert kp0[i, :c0[i]].tobytes() == kp1[i, :c0[i]].tobytes() == kp2[i, :c0[i]].tobytes(), i
+        assert np.array_equal(d0[i, :c0[i]], d1[i, :c0[i]]) and np.array_equal(d0[i, :c0[i]], d2[i, :c0[i]]), i
+        for j in range(2):
+            assert b0[j][i].tobytes() == b1[j][i].tobytes(), (j, i)
+    ctx.close()
