@@ -30,7 +30,7 @@ W, H, NFEAT, NLEVELS, SCALE = 640, 480, 1000, 8, 1.2       # the default workloa
 BATCH, MAP_M, CAP, MATCHES_PER_FRAME = 256, 2048, 1280, 2
 METRIC = "orb_extract_match_frames_per_s_640x480"
 LEVEL_PIXELS_VGA = 950532          # sum of the 8 pyramid levels of a 640x480 frame
-PROFILE_TAG = "r2_v3"              # profiles/<tag>_ncu_metrics.json / _ncu_dram_traffic.json: the committed ncu capture the roofline keys quote
+PROFILE_TAG = "r2_v4"              # profiles/<tag>_ncu_metrics.json / _ncu_dram_traffic.json: the committed ncu capture the roofline keys quote
 INT8_PEAK_FILE = "profiles/r2_int8_peak.json"
 
 # BASELINE.json configs[0..4] as `--config c1 .. c5` (the driver runs the default, c2).  frames: how the synthetic batch is made;
@@ -442,7 +442,7 @@ def run_orbx(args, cfg, rank: int, world: int, local_rank: int):
     ext_total = sum(ext_stages.values())
     roofline = None
     ncu = _load_json(f"profiles/{PROFILE_TAG}_ncu_metrics.json") or {}
-    kname = {"gray": "k_gray", "pyramid": "k_pyr_tma", "fast_nms": "k_fast_warp", "select_harris": "k_select", "blur": "k_blur", "describe": "k_describe"}
+    kname = {"gray": "k_gray", "pyramid": "k_pyr_tma", "fast_nms": "k_fast_warp", "select_harris": "k_select_fast", "blur": "k_blur", "describe": "k_describe_tma"}
     if dom:
         traffic = None                                   # DRAM bytes of the dominant kernel per launch, from the committed ncu --set full capture
         k = (ncu.get("kernels") or {}).get(kname.get(dom))
@@ -541,7 +541,8 @@ def run_orbx(args, cfg, rank: int, world: int, local_rank: int):
             "e2e_pageable": e2e_pageable,
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_pipeline": {"achieved": pipe_ach, "peak": hbm_peak, "unit": "GB/s", "frac": pipe_ach / hbm_peak if pipe_ach else None,
-                                                         "note": "same algorithmic bytes over the sum of all extraction kernels"},
+                                                         "note": "same algorithmic bytes over the sum of all extraction kernels (stage timers on: one stream, no overlap; the timed "
+                                                                 "step itself runs the small pyramid levels, their FAST bands and the blur on a side stream under the large levels' FAST)"},
             "roofline_match": roof_match, "stage_ms": stage_ms, "cpu_baseline": cpu, "parity": parity}
     if sweep is not None:
         line["sweep"] = sweep

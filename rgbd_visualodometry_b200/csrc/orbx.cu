@@ -5,6 +5,7 @@
 //   cv::DescriptorMatcher::match         src/frontend.cpp:187   -> orbx_match_hamming*
 // There is no CPU fallback anywhere in this file: every entry point either runs the sm_100a kernels or fails.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -46,6 +47,18 @@ constexpr int N_STAGES = 7;
 const char* const k_stage_names[N_STAGES] = {"gray", "pyramid", "fast_nms", "select_harris", "blur", "describe", "match"};
 
 size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// NVTX ranges around every stage's launches and around the C-ABI calls (the reference's only timer is the wall clock around
+// AddFrame, app/run_vo.cpp:104-109); header-only NVTX 3: free when no tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+struct NvtxStages {                      // one open range at a time: next() closes the previous stage's
+    bool open = false;
+    void next(const char* name) { if (open) nvtxRangePop(); nvtxRangePushA(name); open = true; }
+    ~NvtxStages() { if (open) nvtxRangePop(); }
+};
 
 struct Buf {
     void* p = nullptr;
@@ -382,6 +395,8 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, int lane_id, bool marks, int
     cudaStream_t side = c->side[lane_id];
     cudaEvent_t side_fork = c->ev_sfork[lane_id], side_join = c->ev_sjoin[lane_id];
 
+    NvtxStages nv;
+    nv.next("orbx:gray");
     if (marks) stage_mark(c, 0);
     {
         const int aligned16 = ((reinterpret_cast<uintptr_t>(d_imgs) | step | frame_stride) & 15) == 0;
@@ -412,6 +427,11 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, int lane_id, bool marks, int
         else                   k_pyr_down<true><<<grd, PYR_NT, 0, s>>>(g, l, pyr, tabs);
         ++c->launches;
     };
+    // The blur (FMA-pipe-bound, needs only the pyramid) follows the small levels on the side stream, i.e. it also runs under the
+    // large levels' FAST launch (ALU-pipe-bound): 0.959 -> 0.944 ms per 256 VGA frames.  Capping the occupancy of either kernel
+    // so that both are resident in fixed proportions was measured and loses (FAST needs its 7 CTAs per SM).
+    static const int env_co = getenv("ORBX_CO") ? atoi(getenv("ORBX_CO")) : 1;
+    bool blur_done = false;
     auto launch_fast = [&](int band_lo, int band_hi, cudaStream_t s) {
         if (band_hi <= band_lo) return;
         if (old_fast) {
@@ -429,38 +449,53 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, int lane_id, bool marks, int
     {
         static const int tail_px = getenv("ORBX_TAIL_PX") ? atoi(getenv("ORBX_TAIL_PX")) : 100000;   // levels below this many pixels are "small"; 0: no side chain
         for (int l = g.nlevels - 1; l >= 2 && (long)g.L[l].w * g.L[l].h < tail_px; --l) lt = l;
-        if (old_fast || g.total_bands <= 0) lt = g.nlevels;
+        if (old_fast || g.total_bands <= 0 || marks) lt = g.nlevels;   // (stage timers on: one stream, clean per-stage times)
     }
+    nv.next("orbx:pyramid");
     for (int l = 1; l < lt; ++l) launch_pyr(l, st);
     if (marks) stage_mark(c, 2);
+    nv.next("orbx:fast_nms (+ small pyramid levels and blur on the side stream)");
     if (lt < g.nlevels) {
         CU(cudaEventRecord(side_fork, st));
         CU(cudaStreamWaitEvent(side, side_fork, 0));
         for (int l = lt; l < g.nlevels; ++l) launch_pyr(l, side);
         launch_fast(g.L[lt].band0, g.total_bands, side);
+        if (env_co && g.total_blur > 0) {
+            k_blur<<<dim3((unsigned)g.total_blur, B), BLUR_NT, 0, side>>>(g, pyr, blur);
+            ++c->launches; blur_done = true;
+        }
         CU(cudaEventRecord(side_join, side));
         launch_fast(0, g.L[lt].band0, st);
         CU(cudaStreamWaitEvent(st, side_join, 0));
     } else if (g.total_bands > 0) launch_fast(0, g.total_bands, st);
-    // (Selection and blur were also tried as interleaved CTAs of one launch and as concurrent kernels on a side stream:
-    //  neither beats running them back to back -- the selection kernel is bound by the latency of its longest CTA, not by
-    //  issue slots it could lend to the blur.)
+    nv.next("orbx:select_harris");
     if (marks) stage_mark(c, 3);
+    // Selection (three launches of single-warp work per (frame, level): latency-bound, a quarter of the issue slots used) and the
+    // blur (FMA-pipe-bound) are independent -- the blur needs only the pyramid -- so the selection runs on the high-priority side
+    // stream UNDER the blur.  (With stage timers on, everything stays in one stream so that the per-stage times are clean.)
+    static const int env_overlap = getenv("ORBX_OVERLAP") ? atoi(getenv("ORBX_OVERLAP")) : 0;   // measured: 0.983 ms against 0.962 ms for the sequential order
+    const bool overlap_sel = env_overlap && !marks && g.total_blur > 0 && !blur_done;
+    cudaStream_t ss = overlap_sel ? side : st;
+    if (overlap_sel) { CU(cudaEventRecord(side_fork, st)); CU(cudaStreamWaitEvent(side, side_fork, 0)); }
     {
         static const int old_sel = getenv("ORBX_SELECT_OLD") ? atoi(getenv("ORBX_SELECT_OLD")) : 0;   // A/B timing only
-        if (old_sel) { k_select<<<dim3(B, (unsigned)g.nlevels), SEL_NT, 0, st>>>(g, pyr, rowcnt, rowent, work, selpos, fincnt, status); ++c->launches; }
+        if (old_sel) { k_select<<<dim3(B, (unsigned)g.nlevels), SEL_NT, 0, ss>>>(g, pyr, rowcnt, rowent, work, selpos, fincnt, status); ++c->launches; }
         else {
-            k_select_fast<<<dim3(B, (unsigned)g.nlevels), 32, 0, st>>>(g, rowcnt, rowent, work, selpos, selcnt, fincnt);
-            if (g.total_hblk > 0) k_harris<<<dim3((unsigned)g.total_hblk, B), HARRIS_NT, 0, st>>>(g, pyr, work, selcnt);
-            k_select_harris<<<dim3(B, (unsigned)g.nlevels), 32, (size_t)g.selh_elems * 12, st>>>(g, work, selpos, selcnt, fincnt, g.selh_elems);
+            k_select_fast<<<dim3(B, (unsigned)g.nlevels), 32, 0, ss>>>(g, rowcnt, rowent, work, selpos, selcnt, fincnt);
+            if (g.total_hblk > 0) k_harris<<<dim3((unsigned)g.total_hblk, B), HARRIS_NT, 0, ss>>>(g, pyr, work, selcnt);
+            k_select_harris<<<dim3(B, (unsigned)g.nlevels), 32, (size_t)g.selh_elems * 12, ss>>>(g, work, selpos, selcnt, fincnt, g.selh_elems);
             c->launches += 3;
         }
     }
+    if (overlap_sel) CU(cudaEventRecord(side_join, side));
+    nv.next("orbx:blur");
     if (marks) stage_mark(c, 4);
-    if (g.total_blur > 0) {
+    if (g.total_blur > 0 && !blur_done) {
         k_blur<<<dim3((unsigned)g.total_blur, B), BLUR_NT, 0, st>>>(g, pyr, blur);
         ++c->launches;
     }
+    if (overlap_sel) CU(cudaStreamWaitEvent(st, side_join, 0));
+    nv.next("orbx:describe");
     if (marks) stage_mark(c, 5);
     static const int old_desc = getenv("ORBX_DESC_OLD") ? atoi(getenv("ORBX_DESC_OLD")) : 0;   // A/B timing only
     if (old_desc)
@@ -561,6 +596,7 @@ int match_timed_out(orbx_ctx* c)
 int run_match(orbx_ctx* c, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, int stride_rows, const int* d_counts, int nsets,
               int4* d_best, int4* d_second, cudaStream_t st = nullptr, int slot = 0)
 {
+    NvtxRange nvr("orbx:match_hamming");
     const bool lane_call = st != nullptr;
     if (!st) st = c->stream;
     if (nt >= MT_MAX_TRAIN) return fail(c, ORBX_E_UNSUPPORTED, "train set larger than 2^20 - 1 rows");
@@ -825,6 +861,7 @@ static int host_batch(orbx_ctx* c, const uint8_t* const* imgs, int batch, int w,
                       int nmaps, orbx_match* const* best)
 {
     int rc;
+    NvtxRange nvr("orbx:host_batch (stage / upload / extract / match / download)");
     CU(cudaSetDevice(c->device));
     const size_t row = (size_t)w * channels, dstep = round_up(row, 16), fstride = dstep * h;   // 16: k_gray takes 128-bit loads
     const size_t capz = (size_t)std::max(cap, 1);

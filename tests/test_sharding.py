@@ -1,6 +1,7 @@
 """N > 1 host logic on CPU: world-size-2 gloo group, frames sharded with no data-path collective, results gathered in
 frame order, timing reduced as max over ranks.  The per-rank worker here is the CPU oracle (test stand-in for the
-GPU operator, which needs a device)."""
+GPU operator, which needs a device); the driver under test is the one tools/run_sequence.py runs on the GPUs
+(rgbd_visualodometry_b200/sequence.py)."""
 import os
 import socket
 
@@ -69,3 +70,57 @@ def test_two_rank_gloo_gather(oracle, mode):
     for i in range(n_frames):
         k, d = oracle.detect_and_compute(synth_frame(120, 160, 900 + i), 100)
         assert allres[i] == (k.tobytes(), d.tobytes()), f"frame {i} out of order or wrong"
+
+
+def _seq_worker(rank, world, port, n_frames, mode, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as O
+    from rgbd_visualodometry_b200.sequence import run_sharded_sequence
+    from rgbd_visualodometry_b200.synth import synth_descriptors, synth_frame
+    qmap = synth_descriptors(64, 3)
+
+    def process(frames):
+        out = []
+        for fr in frames:
+            k, d = O.detect_and_compute(fr, 80)
+            out.append((k, d, O.match_hamming(qmap, d)))
+        return out
+    digests, kept, secs = run_sharded_sequence(n_frames, lambda i: synth_frame(120, 160, 500 + i), process, rank, world, mode, batch=2, keep=(0, 3, n_frames - 1))
+    q.put((rank, digests, kept, secs))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["contiguous", "round_robin"])
+def test_sharded_sequence_driver_two_ranks(oracle, mode):
+    """The sequence driver: every rank ends up with the same frame-ordered digests, they equal the single-process result,
+    the kept frames carry their full records, and the reported time is one number (the max over ranks)."""
+    from rgbd_visualodometry_b200.sequence import frame_digest
+    from rgbd_visualodometry_b200.synth import synth_descriptors, synth_frame
+    n_frames, world = 7, 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_seq_worker, args=(r, world, port, n_frames, mode, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted((q.get(timeout=180) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, d0, k0, s0), (_, d1, k1, s1) = got
+    assert d0 == d1 and k0 == k1 and s0 == s1
+    qmap = synth_descriptors(64, 3)
+    for i in range(n_frames):
+        k, d = oracle.detect_and_compute(synth_frame(120, 160, 500 + i), 80)
+        m = oracle.match_hamming(qmap, d)
+        assert d0[i] == frame_digest(k, d, m), f"frame {i} out of order or wrong"
+        if i in (0, 3, n_frames - 1):
+            assert k0[i] == (k.tobytes(), d.tobytes(), m.tobytes())

@@ -1,25 +1,66 @@
 #!/usr/bin/env python
-"""Pinned host <-> device copy bandwidth of the box (context for the e2e number: frames are uploaded every step)."""
+"""Pinned host <-> device copy bandwidth of the box (context for the e2e number: frames are uploaded every step).
+
+  python tools/pcie_bw.py                                                       # one GPU
+  python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 tools/pcie_bw.py
+      # every rank copies at the same time: the aggregate is what the host's memory system / PCIe root complexes sustain,
+      # i.e. the ceiling of the N-GPU end-to-end number (each rank uploads 236 MB per step)
+Prints one JSON line (rank 0)."""
+import json
+import os
+import time
+
 import torch
+
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+torch.cuda.set_device(local)
+dist = None
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 n = 236 << 20
 h = torch.empty(n, dtype=torch.uint8).pin_memory()
+h2 = torch.empty(n, dtype=torch.uint8).pin_memory()
 d = torch.empty(n, dtype=torch.uint8, device="cuda")
 s2 = torch.cuda.Stream()
-for name, fn in (("H2D", lambda: d.copy_(h, non_blocking=True)), ("D2H", lambda: h.copy_(d, non_blocking=True))):
-    for _ in range(2): fn()
+REPS = 20
+
+
+def barrier():
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10): fn()
-    e1.record(); torch.cuda.synchronize()
-    print(f"{name}: {10 * n / (e0.elapsed_time(e1) / 1e3) / 1e9:.1f} GB/s")
-h2 = torch.empty(n, dtype=torch.uint8).pin_memory()
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(10):
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def timed(fn):
+    for _ in range(2):
+        fn()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(REPS):
+        fn()
+    s2.synchronize()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)                 # the slowest rank bounds the aggregate
+    return REPS * n / float(t.item()) / 1e9                       # GB/s per rank (at the slowest rank's pace)
+
+
+def both():
     d.copy_(h, non_blocking=True)
     with torch.cuda.stream(s2):
         h2.copy_(d, non_blocking=True)
-e1.record(); s2.synchronize(); torch.cuda.synchronize()
-print(f"H2D + D2H concurrently: {10 * n / (e0.elapsed_time(e1) / 1e3) / 1e9:.1f} GB/s each direction (approx)")
+
+
+res = {"h2d": timed(lambda: d.copy_(h, non_blocking=True)), "d2h": timed(lambda: h.copy_(d, non_blocking=True)), "both_each_direction": timed(both)}
+if rank == 0:
+    print(json.dumps({"tool": "pcie_bw", "n_gpus": world, "bytes_per_copy": n, "host_cpus": os.cpu_count(),
+                      "per_rank_gbs": res, "aggregate_gbs": {k: v * world for k, v in res.items()},
+                      "e2e_frames_per_s_ceiling_640x480": res["both_each_direction"] * world * 1e9 / 921600.0,
+                      "note": "pinned memory, all ranks copy concurrently, wall clock of the slowest rank"}))
+if dist is not None:
+    dist.barrier()
+    dist.destroy_process_group()
