@@ -472,6 +472,8 @@ def run_orbx(args, cfg, rank: int, world: int, local_rank: int):
     # ---- CPU baseline: the reference's own operators (cv2) on this box's host cores, bounded sample, 3 warm-ups, median of 10
     cpu = None
     try:
+        if world > 1:
+            raise RuntimeError("timed at N = 1 only (the contract: rank 0, one GPU); see the N = 1 line and the --impl reference arm")
         import cv2
         threads = os.cpu_count() or 1
         sample = min(cfg["cpu_sample"], B)

@@ -212,10 +212,11 @@ int orbx_debug_read_fast(orbx_ctx* ctx, int frame, int level, int32_t* x, int32_
 int orbx_debug_stage_times(orbx_ctx* ctx, const char** names, float* ms, int cap);
 /* Matcher pipeline trace (only when the environment variable ORBX_MATCH_TRACE is set): 16 tiles x 16 SM-clock stamps. */
 int orbx_debug_match_trace(orbx_ctx* ctx, long long* out);
-/* Pyramid and FAST exist as two kernel families with identical results: warp-private TMA-fed kernels (chosen for launches
- * of about 26 VGA frames' worth of pixels and more) and CTA-cooperative kernels with the shorter critical path (smaller
- * launches, e.g. the one-frame calls of the VO loop).  mode -1: by launch size (default), 0 / 1: always the former / latter
- * (tests run the golden vectors through both). */
+/* Pyramid, FAST and selection exist as two kernel families with identical results: warp-private kernels (pyramid / FAST:
+ * TMA-fed, chosen for launches of about 26 VGA frames' worth of pixels and more; selection: one warp per (frame, level), chosen
+ * for frames up to about 0.6 Mpixel) and CTA-cooperative kernels with the shorter critical path (smaller launches, e.g. the
+ * one-frame calls of the VO loop; selection on large frames).  mode -1: by launch size / frame size (default), 0 / 1: always
+ * the former / latter (tests run the golden vectors through both). */
 int orbx_debug_force_kernels(orbx_ctx* ctx, int mode);
 
 /* Enable (1) / disable (0) per-stage CUDA-event timing (adds event records between kernels). */

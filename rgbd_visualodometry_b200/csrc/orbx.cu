@@ -478,7 +478,11 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, int lane_id, bool marks, int
     cudaStream_t ss = overlap_sel ? side : st;
     if (overlap_sel) { CU(cudaEventRecord(side_fork, st)); CU(cudaStreamWaitEvent(side, side_fork, 0)); }
     {
-        static const int old_sel = getenv("ORBX_SELECT_OLD") ? atoi(getenv("ORBX_SELECT_OLD")) : 0;   // A/B timing only
+        // Selection kernel family by problem size: one WARP per (frame, level) when the candidate lists are short and there are
+        // thousands of them (256 VGA frames: 0.116 ms against 0.17 ms), one 128-thread CTA per (frame, level) when the lists
+        // are long (64 frames of 1920x1080: 0.43 ms against 0.65 ms; 3840x2160: 1.9 ms against 2.6 ms).
+        static const int env_old_sel = getenv("ORBX_SELECT_OLD") ? atoi(getenv("ORBX_SELECT_OLD")) : -1;
+        const bool old_sel = c->force_kernels >= 0 ? c->force_kernels != 0 : env_old_sel >= 0 ? env_old_sel != 0 : (long)g.w * g.h > 600000L;
         if (old_sel) { k_select<<<dim3(B, (unsigned)g.nlevels), SEL_NT, 0, ss>>>(g, pyr, rowcnt, rowent, work, selpos, fincnt, status); ++c->launches; }
         else {
             k_select_fast<<<dim3(B, (unsigned)g.nlevels), 32, 0, ss>>>(g, rowcnt, rowent, work, selpos, selcnt, fincnt);

@@ -28,15 +28,20 @@ def run_sharded_sequence(n_frames: int, make_frame, process_batch, rank: int, wo
     """Process frames [0, n_frames) sharded over `world` ranks.
 
     make_frame(i) -> the i-th frame (numpy, host); process_batch(list of frames) -> list of (kps, desc, matches-or-None).
-    Returns (digests, kept, seconds): `digests[i]` for EVERY frame in frame order (identical on all ranks), `kept[i]` = the full
-    records of the frames listed in `keep` (gathered too), and the wall time of the slowest rank's processing loop."""
+    Returns (digests, kept, seconds, op_seconds): `digests[i]` for EVERY frame in frame order (identical on all ranks), `kept[i]` =
+    the full records of the frames listed in `keep` (gathered too), the wall time of the slowest rank's whole loop (frame
+    production + operator + digests) and the part of it spent inside `process_batch` (max over ranks as well)."""
     mine = shard_indices(n_frames, rank, world, mode)
     keep = set(keep)
     local = []
+    op_seconds = 0.0
     t0 = time.perf_counter()
     for s in range(0, len(mine), batch):
         chunk = mine[s:s + batch]
-        out = process_batch([make_frame(i) for i in chunk])
+        frames = [make_frame(i) for i in chunk]
+        t1 = time.perf_counter()
+        out = process_batch(frames)
+        op_seconds += time.perf_counter() - t1
         if len(out) != len(chunk):
             raise RuntimeError("process_batch returned a different number of frames")
         for i, (k, d, m) in zip(chunk, out):
@@ -46,8 +51,9 @@ def run_sharded_sequence(n_frames: int, make_frame, process_batch, rank: int, wo
     if world > 1:
         allres = gather_in_frame_order(mine, local, n_frames, group)
         seconds = max_over_ranks(seconds, device, group)
+        op_seconds = max_over_ranks(op_seconds, device, group)
     else:
         allres = local
     digests = [r[0] for r in allres]
     kept = {i: allres[i][1] for i in keep if 0 <= i < n_frames}
-    return digests, kept, seconds
+    return digests, kept, seconds, op_seconds

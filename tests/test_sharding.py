@@ -90,7 +90,8 @@ def _seq_worker(rank, world, port, n_frames, mode, q):
             k, d = O.detect_and_compute(fr, 80)
             out.append((k, d, O.match_hamming(qmap, d)))
         return out
-    digests, kept, secs = run_sharded_sequence(n_frames, lambda i: synth_frame(120, 160, 500 + i), process, rank, world, mode, batch=2, keep=(0, 3, n_frames - 1))
+    digests, kept, secs, op_secs = run_sharded_sequence(n_frames, lambda i: synth_frame(120, 160, 500 + i), process, rank, world, mode, batch=2, keep=(0, 3, n_frames - 1))
+    assert 0 < op_secs <= secs
     q.put((rank, digests, kept, secs))
     dist.barrier()
     dist.destroy_process_group()

@@ -29,6 +29,8 @@ for it in range(n_frames):
     elif kind == 5: img = np.ascontiguousarray(np.kron(img[: h // 2 + 1, : w // 2 + 1], np.ones((2, 2) + (() if img.ndim == 2 else (1,)), np.uint8))[:h, :w])
     key = nf
     if key not in ctxs: ctxs[key] = orb.Context(nf, 1.2, 8, 900, 700, 1)
+    fam = it & 1                                                                  # both pyramid / FAST kernel families (orbx_debug_force_kernels)
+    ctxs[key].force_kernels(fam)
     k, d = ctxs[key].detect_and_compute(img)
     ko, do = O.detect_and_compute(img, nf)
     ok = len(k) == len(ko) and k.tobytes() == ko.tobytes() and np.array_equal(d, do)
@@ -38,6 +40,7 @@ for it in range(n_frames):
         ok = m.tobytes() == O.match_hamming(q, do).tobytes()
     if not ok:
         bad += 1
-        print(f"MISMATCH it={it} {w}x{h} ch={ch} nf={nf} kind={kind} gpu={len(k)} oracle={len(ko)}", flush=True)
-print(f"fuzz: {n_frames} frames, {bad} mismatches, {time.time() - t0:.0f} s")
+        print(f"MISMATCH it={it} {w}x{h} ch={ch} nf={nf} kind={kind} kernels={fam} gpu={len(k)} oracle={len(ko)}", flush=True)
+print(f"fuzz: {n_frames} frames (random sizes 100x90 .. 900x700, 1 / 3 channels, 100 .. 2000 features, 6 texture kinds, both kernel families alternating) "
+      f"+ one match each vs the C oracle: {bad} mismatches, {time.time() - t0:.0f} s")
 sys.exit(1 if bad else 0)

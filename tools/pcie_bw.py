@@ -55,11 +55,22 @@ def both():
         h2.copy_(d, non_blocking=True)
 
 
+n_up, n_dn = 236060672, 36440080                                  # what one bench step moves (256 VGA frames up; records + matches down)
+
+
+def step_mix():
+    d[:n_up].copy_(h[:n_up], non_blocking=True)
+    with torch.cuda.stream(s2):
+        h2[:n_dn].copy_(d[:n_dn], non_blocking=True)
+
+
 res = {"h2d": timed(lambda: d.copy_(h, non_blocking=True)), "d2h": timed(lambda: h.copy_(d, non_blocking=True)), "both_each_direction": timed(both)}
+mix_steps_per_s = timed(step_mix) * 1e9 / n                        # timed() returns REPS * n bytes / seconds: back to steps per second
 if rank == 0:
     print(json.dumps({"tool": "pcie_bw", "n_gpus": world, "bytes_per_copy": n, "host_cpus": os.cpu_count(),
                       "per_rank_gbs": res, "aggregate_gbs": {k: v * world for k, v in res.items()},
-                      "e2e_frames_per_s_ceiling_640x480": res["both_each_direction"] * world * 1e9 / 921600.0,
+                      "bench_step_mix": {"h2d_bytes": n_up, "d2h_bytes": n_dn, "steps_per_s_per_rank": mix_steps_per_s,
+                                         "e2e_frames_per_s_ceiling_640x480": mix_steps_per_s * 256 * world},
                       "note": "pinned memory, all ranks copy concurrently, wall clock of the slowest rank"}))
 if dist is not None:
     dist.barrier()
