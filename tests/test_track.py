@@ -191,3 +191,54 @@ def test_tracking_loop_orbx_equals_cv2_frontend():
     err = max(np.linalg.norm(x[4] - x[5]) for x in a)
     assert err < 0.01, err                                   # metres; 1 px at 2 m is ~3.9 mm
     assert min(x[3] for x in a[1:]) >= 30                    # PnP inliers
+
+
+@pytest.mark.gpu
+def test_track_float_intrinsics_and_decision_boundaries(orbmod):
+    """The reference keeps fx_, fy_, cx_, cy_ and depth_scale_ as FLOAT members (include/myslam/camera.h:65) and promotes them to
+    double inside the double-precision expressions of camera.cpp:39-86 / frame.cpp:43-91: both sides get the float values
+    promoted to double (what INTEGRATION.md 3b tells the shim to pass).  Plus points exactly ON the decision boundaries of
+    frame.cpp:73-86: u == 0, u == cols, v == 0, v == rows, z == +0, z == -0, the camera centre itself (0 / 0 = NaN: every comparison
+    false, the point is kept), and normals 1e-9 rad either side of the pi / 6 cone (exactly on it the answer is libm's acos, not
+    specified by the reference)."""
+    from oracle import oracle as O
+    from rgbd_visualodometry_b200.synth import synth_descriptors, synth_map_queries
+    f32 = lambda v: float(np.float32(v))                                   # noqa: E731
+    cam32 = tuple(f32(v) for v in (517.3, 516.5, 325.1, 249.7))             # not representable in float: the promoted values differ from the yaml's
+    assert cam32 != (517.3, 516.5, 325.1, 249.7)
+    m = 2000
+    pose, _, pos, norm, outlier = _scene(21, m)
+    train = synth_descriptors(700, 31)
+    desc = synth_map_queries(train, m, 32)
+    ids = np.arange(m, dtype=np.int64) + 5
+    ctx = orbmod.Context(500, 1.2, 8, 640, 480, 1)
+    ctx.map_upsert(ids, desc, pos, norm, outlier)
+    cand, matches, mn, mx = ctx.track_match(ids, pose, cam32, 640, 480, train=train, match_ratio=2.0)
+    oc, om, omn, omx = T.track_match(pose, cam32, 640, 480, pos, norm, outlier, desc, train, 2.0, O.match_hamming)
+    assert np.array_equal(cand, oc) and matches.tobytes() == om.tobytes() and (mn, mx) == (omn, omx)
+    # depth scale 5000 as a float member; a scale that is NOT a float (5000.1) is rounded to float by both sides
+    rng = np.random.default_rng(8)
+    depth = rng.integers(2000, 30000, size=(480, 640)).astype(np.uint16)
+    kps = np.zeros(500, dtype=orbmod.KP_DTYPE)
+    kps["x"] = rng.uniform(31, 608, len(kps)).astype(np.float32); kps["y"] = rng.uniform(31, 448, len(kps)).astype(np.float32)
+    for scale in (5000.0, 5000.1):
+        p, v = ctx.backproject(kps, depth, scale, cam32, pose)
+        op, ov = T.backproject(kps, depth, scale, cam32, pose)
+        assert np.array_equal(v, ov) and np.allclose(p[v], op[v], rtol=1e-9, atol=1e-12)
+    # ---- decision boundaries: identity pose, power-of-two intrinsics, so that u, v land EXACTLY on 0 / cols / rows
+    eye = np.concatenate([np.eye(3), np.zeros((3, 1))], axis=1)
+    camb = (512.0, 512.0, 320.0, 240.0)
+    a = np.pi / 6
+    pts = np.array([[1.25, 0, 2], [-1.25, 0, 2], [0, 0.9375, 2], [0, -0.9375, 2], [1, 0, 0.0], [1, 0, -0.0], [0, 0, 0.0], [0, 0, 3], [0, 0, 3], [0.3, 0.1, 2.5]], np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        nrm = pts / np.linalg.norm(pts, axis=1, keepdims=True)             # looking straight at the point: angle 0
+    nrm[6] = 0.0
+    nrm[7] = [np.sin(a - 1e-9), 0, np.cos(a - 1e-9)]                       # just inside the cone
+    nrm[8] = [np.sin(a + 1e-9), 0, np.cos(a + 1e-9)]                       # just outside
+    want = T.could_observe(eye, camb, 640, 480, pts, nrm)
+    assert want.tolist() == [False, True, False, True, False, False, True, True, False, True]    # u == cols / v == rows out, u == 0 / v == 0 in, z == +-0 -> u = +-inf out, NaN kept
+    bid = np.arange(len(pts), dtype=np.int64) + 100000
+    ctx.map_upsert(bid, synth_descriptors(len(pts), 5), pts, nrm, np.zeros(len(pts), np.uint8))
+    cand, _, _, _ = ctx.track_match(bid, eye, camb, 640, 480, train=train, match_ratio=2.0)
+    assert cand.tolist() == np.nonzero(want)[0].tolist()
+    ctx.close()
