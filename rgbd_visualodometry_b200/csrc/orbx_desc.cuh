@@ -9,6 +9,10 @@
 // through two-deep rings that are refilled the moment a window has been consumed, with the NEXT group's keypoints already
 // located (their selection records are read a whole group ahead), so in the steady state no load latency is exposed and
 // there is not a single per-lane copy instruction (the cp.async version spent 22 % of its instructions on them).
+// Measured and dropped: PERSISTENT warps (one wave of CTAs, every warp walking (group, frame) items strided over the whole
+// batch, general ring bookkeeping for partial groups in mid-stream): parity-green, but 0.216 ms against 0.185 ms -- short-lived
+// warps that work on neighbouring groups of one frame keep the windows' lines in L1 / L2 and stagger the phases; so do more
+// groups per warp (gpw 8 / 16: 0.205 / 0.259 ms).
 //   phase 1  IC moments of the group's 4 keypoints: lane <-> (row mod 4, 4-column chunk); sum(u I), sum(I) by DP4A on
 //            disc-masked words, m01 = sum(v * row sum); shuffle reduction; lane k keeps the moments of keypoint k
 //   phase 2  LANE-PARALLEL over the 4 keypoints: fastAtan2, the glibc-exact sinf / cosf in FP64 and the seven record fields are
@@ -154,10 +158,10 @@ __global__ void __launch_bounds__(DS_NW * 32, 6) k_describe_tma(const __grid_con
                 m10 = dp4a_us(w, iccoef, m10);
                 m01 += (4 * i - 15 + icq) * dp4a_us(w, 0x01010101u, 0);
             }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, d); m01 += __shfl_xor_sync(0xffffffffu, m01, d); }
+            m10 = __reduce_add_sync(0xffffffffu, m10);       // REDUX: one instruction per sum instead of five shuffle + add steps
+            m01 = __reduce_add_sync(0xffffffffu, m01);
             if (kq == k) { M10 = m10; M01 = m01; }
-            // the window is consumed (the shuffles above ordered every lane's reads): refill its slot with keypoint m + 2
+            // the window is consumed (the reductions above ordered every lane's reads): refill its slot with keypoint m + 2
             if (lane == ((k + 2) & 3)) {
                 if (k < 2) { if (cur.ok) load_ic(cur, b); }
                 else if (nxt.ok) load_ic(nxt, b);
