@@ -483,7 +483,13 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, int lane_id, bool marks, int
         // are long (64 frames of 1920x1080: 0.43 ms against 0.65 ms; 3840x2160: 1.9 ms against 2.6 ms).
         static const int env_old_sel = getenv("ORBX_SELECT_OLD") ? atoi(getenv("ORBX_SELECT_OLD")) : -1;
         const bool old_sel = c->force_kernels >= 0 ? c->force_kernels != 0 : env_old_sel >= 0 ? env_old_sel != 0 : (long)g.w * g.h > 600000L;
-        if (old_sel) { k_select<<<dim3(B, (unsigned)g.nlevels), SEL_NT, 0, ss>>>(g, pyr, rowcnt, rowent, work, selpos, fincnt, status); ++c->launches; }
+        static const int env_sel_nt = getenv("ORBX_SELECT_NT") ? atoi(getenv("ORBX_SELECT_NT")) : 0;   // A/B timing only
+        const bool wide = env_sel_nt ? env_sel_nt > SEL_NT : (long)g.w * g.h > 600000L;
+        if (old_sel) {
+            if (wide) k_select<SEL_NT_WIDE><<<dim3(B, (unsigned)g.nlevels), SEL_NT_WIDE, 0, ss>>>(g, pyr, rowcnt, rowent, work, selpos, fincnt, status);
+            else      k_select<SEL_NT><<<dim3(B, (unsigned)g.nlevels), SEL_NT, 0, ss>>>(g, pyr, rowcnt, rowent, work, selpos, fincnt, status);
+            ++c->launches;
+        }
         else {
             k_select_fast<<<dim3(B, (unsigned)g.nlevels), 32, 0, ss>>>(g, rowcnt, rowent, work, selpos, selcnt, fincnt);
             if (g.total_hblk > 0) k_harris<<<dim3((unsigned)g.total_hblk, B), HARRIS_NT, 0, ss>>>(g, pyr, work, selcnt);

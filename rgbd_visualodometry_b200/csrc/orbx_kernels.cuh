@@ -671,18 +671,19 @@ __device__ int partition_tail_warp(Elem* v, int m, int len, float thr, int lane)
     }
 }
 
-constexpr int SEL_NT = 128;
+constexpr int SEL_NT = 128;             // threads per CTA of the default instantiation
+constexpr int SEL_NT_WIDE = 512;        // ... for frames above 0.6 Mpixel: level 0 holds tens of thousands of candidates there
 constexpr int SEL_SMEM_ELEMS = 2048;
 constexpr int SEL_PAR_MIN = 32;        // ranges up to this length are finished by one warp
 
 struct SelShared {
-    int warp_a[SEL_NT / 32], warp_b[SEL_NT / 32];
+    int warp_a[32], warp_b[32];            // one slot per warp of the widest instantiation
     int n, first, last, depth, ok;
 };
 
-// Whole-CTA KeyPointsFilter::retainBest(v, m).  All SEL_NT threads must call it.  PosT scratch lists Lp / Rp hold
+// Whole-CTA KeyPointsFilter::retainBest(v, m).  All NT threads must call it.  PosT scratch lists Lp / Rp hold
 // `len` positions each.  Returns the new length (valid on every thread); *flag |= 1 on the heap-select fallback.
-template <typename PosT>
+template <typename PosT, int NT>
 __device__ int retain_best_block(Elem* v, int len, int m, PosT* Lp, PosT* Rp, SelShared* sh, int* flag)
 {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -699,7 +700,7 @@ __device__ int retain_best_block(Elem* v, int len, int m, PosT* Lp, PosT* Rp, Se
         __syncthreads();
         const float piv = v[first].response;
         const int lo = first + 1, n = last - lo;
-        const int cs = (n + SEL_NT - 1) / SEL_NT;
+        const int cs = (n + NT - 1) / NT;
         const int b = min(lo + tid * cs, last), e = min(b + cs, last);
         int cL = 0, cR = 0;
         for (int i = b; i < e; ++i) { const float r = v[i].response; cL += !(r > piv); cR += !(piv > r); }
@@ -713,7 +714,7 @@ __device__ int retain_best_block(Elem* v, int len, int m, PosT* Lp, PosT* Rp, Se
         __syncthreads();
         int totL = 0, totR = 0, exL = iL - cL, exR = iR - cR;
 #pragma unroll
-        for (int i = 0; i < SEL_NT / 32; ++i) {
+        for (int i = 0; i < NT / 32; ++i) {
             const int a = sh->warp_a[i], c = sh->warp_b[i];
             if (i < wid) { exL += a; exR += c; }
             totL += a; totR += c;
@@ -729,15 +730,15 @@ __device__ int retain_best_block(Elem* v, int len, int m, PosT* Lp, PosT* Rp, Se
         __syncthreads();
         const int mm = min(totL, totR);
         int cnt = 0;
-        for (int k = tid; k < mm; k += SEL_NT) cnt += ((int)Lp[k] < (int)Rp[k]);
+        for (int k = tid; k < mm; k += NT) cnt += ((int)Lp[k] < (int)Rp[k]);
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
         if (lane == 0) sh->warp_a[wid] = cnt;                // safe: all reads of warp_a finished before the last barrier
         __syncthreads();
         int K = 0;
 #pragma unroll
-        for (int i = 0; i < SEL_NT / 32; ++i) K += sh->warp_a[i];
-        for (int k = tid; k < K; k += SEL_NT) elem_swap(v, (int)Lp[k], (int)Rp[k]);
+        for (int i = 0; i < NT / 32; ++i) K += sh->warp_a[i];
+        for (int k = tid; k < K; k += NT) elem_swap(v, (int)Lp[k], (int)Rp[k]);
         int cut = 0x7fffffff;
         if (K < totL) cut = (int)Lp[K];
         if (K > 0) cut = min(cut, (int)Rp[K - 1]);
@@ -816,6 +817,7 @@ struct SelSmem {
     uint16_t pos[2 * SEL_SMEM_ELEMS];
     SelShared sh;
 };
+template <int NT>
 __device__ __forceinline__ void select_body(const Geom& g, const uint8_t* __restrict__ pyr, const uint32_t* __restrict__ rowcnt,
                                             const uint32_t* __restrict__ rowent, Elem* __restrict__ work, uint32_t* __restrict__ selpos,
                                             int* __restrict__ fincnt, int* __restrict__ status, int l, int f, SelSmem& sm)
@@ -831,7 +833,7 @@ __device__ __forceinline__ void select_body(const Geom& g, const uint8_t* __rest
     const uint32_t* ent = rowent + (size_t)f * g.ent_frame + L.ent_off;
     // ---- gather rows in raster order
     const int nr = L.in_h;
-    const int rpt = (nr + SEL_NT - 1) / SEL_NT;
+    const int rpt = (nr + NT - 1) / NT;
     const int rb = min(tid * rpt, nr), re = min(rb + rpt, nr);
     int mine = 0;
     for (int r = rb; r < re; ++r) mine += (int)cnt[r];
@@ -842,7 +844,7 @@ __device__ __forceinline__ void select_body(const Geom& g, const uint8_t* __rest
     __syncthreads();
     int woff = 0, total = 0;
 #pragma unroll
-    for (int i = 0; i < SEL_NT / 32; ++i) { const int s = sh.warp_a[i]; if (i < wid) woff += s; total += s; }
+    for (int i = 0; i < NT / 32; ++i) { const int s = sh.warp_a[i]; if (i < wid) woff += s; total += s; }
     const int N = total;
     const bool in_smem = N <= SEL_SMEM_ELEMS;
     Elem* v = in_smem ? s_v : gv;
@@ -891,31 +893,32 @@ __device__ __forceinline__ void select_body(const Geom& g, const uint8_t* __rest
     int flag = 0;
     uint32_t* gpos = selpos + 2 * ((size_t)f * g.ws_frame + L.ws_off);
     // ---- retainBest(2 n_l) on the FAST score
-    const int n1 = in_smem ? retain_best_block<uint16_t>(v, N, 2 * L.quota, s_pos, s_pos + SEL_SMEM_ELEMS, &sh, &flag)
-                           : retain_best_block<uint32_t>(v, N, 2 * L.quota, gpos, gpos + N, &sh, &flag);
+    const int n1 = in_smem ? retain_best_block<uint16_t, NT>(v, N, 2 * L.quota, s_pos, s_pos + SEL_SMEM_ELEMS, &sh, &flag)
+                           : retain_best_block<uint32_t, NT>(v, N, 2 * L.quota, gpos, gpos + N, &sh, &flag);
     // ---- Harris on the unblurred level
     const uint8_t* img = pyr + (size_t)f * g.pyr_frame + L.img_off;
-    for (int i = tid; i < n1; i += SEL_NT) {
+    for (int i = tid; i < n1; i += NT) {
         const uint32_t pos = v[i].pos;
         v[i].response = harris_response(img, L.pitch, (int)(pos & 0xffffu), (int)(pos >> 16));
     }
     __syncthreads();
     // ---- retainBest(n_l) on Harris
-    const int n2 = in_smem ? retain_best_block<uint16_t>(v, n1, L.quota, s_pos, s_pos + SEL_SMEM_ELEMS, &sh, &flag)
-                           : retain_best_block<uint32_t>(v, n1, L.quota, gpos, gpos + N, &sh, &flag);
+    const int n2 = in_smem ? retain_best_block<uint16_t, NT>(v, n1, L.quota, s_pos, s_pos + SEL_SMEM_ELEMS, &sh, &flag)
+                           : retain_best_block<uint32_t, NT>(v, n1, L.quota, gpos, gpos + N, &sh, &flag);
     if (tid == 0) { fincnt[f * g.nlevels + l] = n2; if (flag) atomicOr(&status[f], flag); }
-    if (v != gv) for (int i = tid; i < n2; i += SEL_NT) gv[i] = v[i];
+    if (v != gv) for (int i = tid; i < n2; i += NT) gv[i] = v[i];
 }
 
 // grid = (frames, levels): level-major dispatch, so the long level-0 CTAs of every frame start in the first wave and
 // the short upper levels fill the tail
-__global__ void __launch_bounds__(SEL_NT, 8) k_select(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr,
+template <int NT>
+__global__ void __launch_bounds__(NT, NT <= 128 ? 8 : 2) k_select(const __grid_constant__ Geom g, const uint8_t* __restrict__ pyr,
                                                    const uint32_t* __restrict__ rowcnt, const uint32_t* __restrict__ rowent,
                                                    Elem* __restrict__ work, uint32_t* __restrict__ selpos, int* __restrict__ fincnt,
                                                    int* __restrict__ status)
 {
     __shared__ SelSmem sm;
-    select_body(g, pyr, rowcnt, rowent, work, selpos, fincnt, status, blockIdx.y, blockIdx.x, sm);
+    select_body<NT>(g, pyr, rowcnt, rowent, work, selpos, fincnt, status, blockIdx.y, blockIdx.x, sm);
 }
 
 

@@ -12,8 +12,11 @@ by_exec = "--by-exec" in sys.argv
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
-blk = rows[hi[0] + 1: (hi[1] - 1 if len(hi) > 1 else len(rows))]
 hdr = rows[hi[0]]
+# several launches of the kernel may be in the report: take the one that executed the most instructions
+blks = [rows[h + 1: (hi[j + 1] - 1 if j + 1 < len(hi) else len(rows))] for j, h in enumerate(hi)]
+_ie = hdr.index("Instructions Executed")
+blk = max(blks, key=lambda b: sum(int(r[_ie]) for r in b if len(r) > _ie and r[_ie].isdigit()))
 si, src, ie = hdr.index("# Samples"), hdr.index("Source"), hdr.index("Instructions Executed")
 data = [r for r in blk if len(r) > si and r[si].isdigit()]
 with tempfile.TemporaryDirectory() as td:

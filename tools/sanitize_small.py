@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Small end-to-end run for compute-sanitizer (memcheck): every kernel on tiny inputs, including the multi-lane batch path."""
+"""Small end-to-end run for compute-sanitizer (memcheck / racecheck / synccheck): every kernel of both families on tiny inputs,
+the multi-lane host path with pageable buffers (staging threads), maps, and the matcher's kernels.
+  compute-sanitizer --tool memcheck python tools/sanitize_small.py"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -9,7 +11,14 @@ from rgbd_visualodometry_b200.synth import synth_frame, synth_descriptors, synth
 ctx = orb.Context(150, 1.2, 8, 200, 150, 130)
 frames = [synth_frame(150, 200, 7000 + i) for i in range(130)]
 k, d, n = ctx.detect_and_compute_batch(frames)                      # lanes
-k1, d1 = ctx.detect_and_compute(synth_frame(149, 197, 3))           # per-level kernels, odd size
+k1, d1 = ctx.detect_and_compute(synth_frame(149, 197, 3))           # CTA-cooperative family (small launch), odd size
+ctx.force_kernels(0)
+k0, d0 = ctx.detect_and_compute(synth_frame(149, 197, 3))           # warp-private TMA family on the same frame
+assert k0.tobytes() == k1.tobytes() and np.array_equal(d0, d1)
+kb, db, nb = ctx.detect_and_compute_batch(frames[:9])                # ... and on a batch (describe groups, side stream)
+assert all(kb[i, :nb[i]].tobytes() == k[i, :n[i]].tobytes() for i in range(9))
+ctx.force_kernels(-1)
+kp, dp, cp, bp = ctx.extract_match_batch(frames[:40], [synth_descriptors(70, 9)], 200)   # host lanes + matches per lane
 t = synth_descriptors(333, 1); q = synth_map_queries(t, 517, 2)
 m = ctx.match(q, t); m2 = ctx.knn_match2(q, t)
 cnt = np.array([len(t), 0, 97], np.int32)
