@@ -491,10 +491,19 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, int lane_id, bool marks, int
             ++c->launches;
         }
         else {
-            k_select_fast<<<dim3(B, (unsigned)g.nlevels), 32, 0, ss>>>(g, rowcnt, rowent, work, selpos, selcnt, fincnt);
-            if (g.total_hblk > 0) k_harris<<<dim3((unsigned)g.total_hblk, B), HARRIS_NT, 0, ss>>>(g, pyr, work, selcnt);
-            k_select_harris<<<dim3(B, (unsigned)g.nlevels), 32, (size_t)g.selh_elems * 12, ss>>>(g, work, selpos, selcnt, fincnt, g.selh_elems);
-            c->launches += 3;
+            // (the warp going straight on to Harris and the second retainBest -- one launch instead of three -- was measured: 0.1435 ms
+            //  against 0.1159 ms per 256 VGA frames; the 14 serial Harris evaluations per lane cost the level-0 warps more than the
+            //  two launch gaps and the Harris kernel's tail)
+            static const int env_fused = getenv("ORBX_SELECT_FUSED") ? atoi(getenv("ORBX_SELECT_FUSED")) : 0;
+            if (env_fused) {
+                k_select_fast<true><<<dim3(B, (unsigned)g.nlevels), 32, 0, ss>>>(g, pyr, rowcnt, rowent, work, selpos, selcnt, fincnt);
+                ++c->launches;
+            } else {
+                k_select_fast<false><<<dim3(B, (unsigned)g.nlevels), 32, 0, ss>>>(g, pyr, rowcnt, rowent, work, selpos, selcnt, fincnt);
+                if (g.total_hblk > 0) k_harris<<<dim3((unsigned)g.total_hblk, B), HARRIS_NT, 0, ss>>>(g, pyr, work, selcnt);
+                k_select_harris<<<dim3(B, (unsigned)g.nlevels), 32, (size_t)g.selh_elems * 12, ss>>>(g, work, selpos, selcnt, fincnt, g.selh_elems);
+                c->launches += 3;
+            }
         }
     }
     if (overlap_sel) CU(cudaEventRecord(side_join, side));
