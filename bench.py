@@ -30,7 +30,7 @@ W, H, NFEAT, NLEVELS, SCALE = 640, 480, 1000, 8, 1.2       # the default workloa
 BATCH, MAP_M, CAP, MATCHES_PER_FRAME = 256, 2048, 1280, 2
 METRIC = "orb_extract_match_frames_per_s_640x480"
 LEVEL_PIXELS_VGA = 950532          # sum of the 8 pyramid levels of a 640x480 frame
-PROFILE_TAG = "r2_v4"              # profiles/<tag>_ncu_metrics.json / _ncu_dram_traffic.json: the committed ncu capture the roofline keys quote
+PROFILE_TAG = "r2_v5"              # profiles/<tag>_ncu_metrics.json / _ncu_dram_traffic.json: the committed ncu capture the roofline keys quote
 INT8_PEAK_FILE = "profiles/r2_int8_peak.json"
 
 # BASELINE.json configs[0..4] as `--config c1 .. c5` (the driver runs the default, c2).  frames: how the synthetic batch is made;
