@@ -905,6 +905,7 @@ static int host_batch(orbx_ctx* c, const uint8_t* const* imgs, int batch, int w,
     if (stage_in && (rc = ensure_pinned(c, c->h_stage_in, c->h_stage_in_bytes, fstride * batch))) return rc;
     if (stage_out && (rc = ensure_pinned(c, c->h_stage_out, c->h_stage_out_bytes, o_best + mrows * 16))) return rc;
     HostStager* hs = (stage_in || stage_out) ? stager_of(c) : nullptr;
+    static const int stage_nt = getenv("ORBX_STAGE_NT") ? atoi(getenv("ORBX_STAGE_NT")) : 1;   // non-temporal stores into the pinned input staging
     static const size_t wake_bytes = getenv("ORBX_STAGE_WAKE_BYTES") ? (size_t)atoll(getenv("ORBX_STAGE_WAKE_BYTES")) : (size_t)2 << 20;
     const bool wake_in = fstride * batch >= wake_bytes, wake_out = (size_t)60 * capz * batch + mrows * 16 >= wake_bytes;
     orbx_keypoint* kps_dl = stage_out ? (orbx_keypoint*)(c->h_stage_out + o_kps) : kps;       // where the D2H copies land
@@ -935,7 +936,7 @@ static int host_batch(orbx_ctx* c, const uint8_t* const* imgs, int batch, int w,
             int f0, f1;
             host_lane_range(batch, lanes, k, &f0, &f1);
             in_done[k].store(0, std::memory_order_relaxed);
-            for (int i = f0; i < f1; ++i) in_target[k] += hs->submit(c->h_stage_in + fstride * i, dstep, imgs[i], step, row, (size_t)h, &in_done[k], wake_in);
+            for (int i = f0; i < f1; ++i) in_target[k] += hs->submit(c->h_stage_in + fstride * i, dstep, imgs[i], step, row, (size_t)h, &in_done[k], wake_in, stage_nt != 0);
         }
     CU(cudaEventRecord(c->ev_fork, c->stream));
     for (int k = 0; k < lanes; ++k) {

@@ -11,6 +11,10 @@
 #include <stddef.h>
 #include <stdint.h>
 #include <string.h>
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#define ORBX_STAGE_NT 1
+#endif
 #include <atomic>
 #include <condition_variable>
 #include <deque>
@@ -25,6 +29,7 @@ public:
     struct Job {                       // `rows` rows of `row_bytes` from src (pitch spitch) to dst (pitch dpitch)
         uint8_t* dst; const uint8_t* src; size_t dpitch, spitch, row_bytes, rows;
         std::atomic<int>* done;        // incremented once when the piece has landed
+        bool nt;                       // destination is pinned staging that only the DMA engine will read: non-temporal stores
     };
     static constexpr size_t PIECE = 256 * 1024;
 
@@ -42,7 +47,10 @@ public:
 
     // Queue a 2-D copy cut into pieces of about PIECE bytes (whole rows; one contiguous block when the pitches equal the
     // row length).  Returns the number of pieces, i.e. how much `done` will grow.
-    int submit(void* dst, size_t dpitch, const void* src, size_t spitch, size_t row_bytes, size_t rows, std::atomic<int>* done, bool wake = true)
+    // nt = true: the destination is written with non-temporal stores (no read-for-ownership of the destination lines, nothing of it
+    // left in the CPU caches): right for pinned staging that is read next by the GPU's copy engine, wrong for results the caller reads.
+    int submit(void* dst, size_t dpitch, const void* src, size_t spitch, size_t row_bytes, size_t rows, std::atomic<int>* done, bool wake = true,
+               bool nt = false)
     {
         if (rows == 0 || row_bytes == 0) return 0;
         if (dpitch == row_bytes && spitch == row_bytes) { row_bytes *= rows; dpitch = spitch = row_bytes; rows = 1; }
@@ -50,11 +58,11 @@ public:
         std::lock_guard<std::mutex> lk(mu_);
         if (rows == 1) {
             for (size_t o = 0; o < row_bytes; o += PIECE, ++n)
-                q_.push_back(Job{(uint8_t*)dst + o, (const uint8_t*)src + o, 0, 0, row_bytes - o < PIECE ? row_bytes - o : PIECE, 1, done});
+                q_.push_back(Job{(uint8_t*)dst + o, (const uint8_t*)src + o, 0, 0, row_bytes - o < PIECE ? row_bytes - o : PIECE, 1, done, nt});
         } else {
             const size_t per = PIECE / row_bytes > 0 ? PIECE / row_bytes : 1;
             for (size_t r = 0; r < rows; r += per, ++n)
-                q_.push_back(Job{(uint8_t*)dst + r * dpitch, (const uint8_t*)src + r * spitch, dpitch, spitch, row_bytes, rows - r < per ? rows - r : per, done});
+                q_.push_back(Job{(uint8_t*)dst + r * dpitch, (const uint8_t*)src + r * spitch, dpitch, spitch, row_bytes, rows - r < per ? rows - r : per, done, nt});
         }
         if (wake) { if (n > 1) cv_.notify_all(); else cv_.notify_one(); }   // (!wake: a small job the calling thread takes itself in help_until)
         return n;
@@ -76,9 +84,32 @@ public:
     }
 
 private:
+    static void copy_nt(uint8_t* d, const uint8_t* s, size_t n)
+    {
+#ifdef ORBX_STAGE_NT
+        const size_t head = (16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15;
+        if (head && head <= n) { memcpy(d, s, head); d += head; s += head; n -= head; }
+        if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+            for (; n >= 64; n -= 64, d += 64, s += 64) {
+                const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s)), b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 16));
+                const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 32)), e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 48));
+                _mm_stream_si128(reinterpret_cast<__m128i*>(d), a); _mm_stream_si128(reinterpret_cast<__m128i*>(d + 16), b);
+                _mm_stream_si128(reinterpret_cast<__m128i*>(d + 32), c); _mm_stream_si128(reinterpret_cast<__m128i*>(d + 48), e);
+            }
+        }
+#endif
+        if (n) memcpy(d, s, n);
+    }
     static void run(const Job& j)
     {
-        for (size_t r = 0; r < j.rows; ++r) memcpy(j.dst + r * j.dpitch, j.src + r * j.spitch, j.row_bytes);
+        if (j.nt) {
+            for (size_t r = 0; r < j.rows; ++r) copy_nt(j.dst + r * j.dpitch, j.src + r * j.spitch, j.row_bytes);
+#ifdef ORBX_STAGE_NT
+            _mm_sfence();                                   // the streamed lines are globally visible before `done` says so
+#endif
+        } else {
+            for (size_t r = 0; r < j.rows; ++r) memcpy(j.dst + r * j.dpitch, j.src + r * j.spitch, j.row_bytes);
+        }
         j.done->fetch_add(1, std::memory_order_release);
     }
     void worker()

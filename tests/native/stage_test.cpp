@@ -3,6 +3,7 @@
 // with work still queued.  Built and run by tests/test_stage.py.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 #include "../../rgbd_visualodometry_b200/csrc/orbx_stage.h"
 
@@ -30,6 +31,13 @@ int main()
         for (size_t i = 0; i < src.size(); ++i) src[i] = (uint8_t)(i * 2654435761u >> 11);
         std::atomic<int> done(0);
         const int n = hs.submit(dst.data(), dp, src.data(), sp, row, rows, &done, nthreads > 0);
+        // ... and the same copy with non-temporal stores into a deliberately misaligned destination
+        std::vector<uint8_t> dst_nt(dp * rows + 64, 0xEE);
+        std::atomic<int> done_nt(0);
+        const int n_nt = hs.submit(dst_nt.data() + 5, dp, src.data() + 3, sp, row, rows, &done_nt, nthreads > 0, true);
+        hs.help_until(done_nt, n_nt);
+        for (size_t r = 0; r < rows; ++r)
+            if (memcmp(dst_nt.data() + 5 + r * dp, src.data() + 3 + r * sp, row) != 0 || dst_nt[5 + r * dp + row] != 0xEE) { printf("FAIL: non-temporal copy, row %zu\n", r); ++bad; break; }
         if (n < 2) { printf("FAIL: expected several pieces, got %d\n", n); ++bad; }
         hs.help_until(done, n);
         bad += check(dst, dp, src, sp, row, rows, "padded image");
