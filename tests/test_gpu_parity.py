@@ -523,3 +523,39 @@ def test_host_buffers_pageable_registered_and_strided_agree(orbmod, oracle):
         for j in range(2):
             assert b0[j][i].tobytes() == b1[j][i].tobytes(), (j, i)
     ctx.close()
+
+
+def test_two_contexts_on_two_threads_agree_with_sequential_calls(orbmod):
+    """What bench.py's e2e leg does (a caller double-buffering a stream of batches): two contexts driven from two host threads at
+    the same time, each through the synchronous host-buffer call with its own pageable buffers; every call of both threads must
+    return exactly what a lone, sequential call returns (no shared state between contexts, copier threads included)."""
+    import threading
+    from rgbd_visualodometry_b200.synth import synth_frame, synth_descriptors
+    B, n, cap = 24, 300, 400
+    base = [synth_frame(240, 320, 4200 + i) for i in range(4)]
+    batches = [[np.roll(base[(i + s) % 4], 5 * i + s, axis=1) for i in range(B)] for s in range(2)]
+    maps = [synth_descriptors(300, 21)]
+    ref_ctx = orbmod.Context(n, 1.2, 8, 320, 240, B)
+    ref = [ref_ctx.extract_match_batch(batches[s], maps, cap) for s in range(2)]
+    ref_ctx.close()
+    errors = []
+
+    def worker(s):
+        try:
+            ctx = orbmod.Context(n, 1.2, 8, 320, 240, B)
+            for _ in range(6):
+                kp, d, c, b = ctx.extract_match_batch(batches[s], maps, cap)
+                rk, rd, rc, rb = ref[s]
+                assert np.array_equal(c, rc)
+                for i in range(B):
+                    assert kp[i, :c[i]].tobytes() == rk[i, :c[i]].tobytes() and np.array_equal(d[i, :c[i]], rd[i, :c[i]]), (s, i)
+                assert b[0].tobytes() == rb[0].tobytes()
+            ctx.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append((s, repr(e)))
+    th = [threading.Thread(target=worker, args=(s,)) for s in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
