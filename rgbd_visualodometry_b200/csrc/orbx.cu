@@ -470,17 +470,19 @@ int run_extract_range(orbx_ctx* c, cudaStream_t st, int lane_id, bool marks, int
     } else if (g.total_bands > 0) launch_fast(0, g.total_bands, st);
     nv.next("orbx:select_harris");
     if (marks) stage_mark(c, 3);
-    // Selection (three launches of single-warp work per (frame, level): latency-bound, a quarter of the issue slots used) and the
-    // blur (FMA-pipe-bound) are independent -- the blur needs only the pyramid -- so the selection runs on the high-priority side
-    // stream UNDER the blur.  (With stage timers on, everything stays in one stream so that the per-stage times are clean.)
-    static const int env_overlap = getenv("ORBX_OVERLAP") ? atoi(getenv("ORBX_OVERLAP")) : 0;   // measured: 0.983 ms against 0.962 ms for the sequential order
+    // Experiment kept behind ORBX_OVERLAP=1 (and only when the blur did not already go to the side stream): the selection (three
+    // launches of single-warp work per (frame, level), latency-bound) on the high-priority side stream UNDER the blur, which needs
+    // only the pyramid.  Measured slower than the sequential order (0.983 ms against 0.962 ms per 256 VGA frames): the selection's
+    // dependent launches wait for slots the blur's CTAs hold.
+    static const int env_overlap = getenv("ORBX_OVERLAP") ? atoi(getenv("ORBX_OVERLAP")) : 0;
     const bool overlap_sel = env_overlap && !marks && g.total_blur > 0 && !blur_done;
     cudaStream_t ss = overlap_sel ? side : st;
     if (overlap_sel) { CU(cudaEventRecord(side_fork, st)); CU(cudaStreamWaitEvent(side, side_fork, 0)); }
     {
         // Selection kernel family by problem size: one WARP per (frame, level) when the candidate lists are short and there are
-        // thousands of them (256 VGA frames: 0.116 ms against 0.17 ms), one 128-thread CTA per (frame, level) when the lists
-        // are long (64 frames of 1920x1080: 0.43 ms against 0.65 ms; 3840x2160: 1.9 ms against 2.6 ms).
+        // thousands of them (256 VGA frames: 0.116 ms against 0.17 ms), one CTA per (frame, level) when the lists are long -- 512
+        // threads wide there (64 frames of 1920x1080: 0.30 ms against 0.43 ms with 128 threads and 0.65 ms with warps;
+        // 3840x2160: 1.21 against 1.88 and 2.57 ms).
         static const int env_old_sel = getenv("ORBX_SELECT_OLD") ? atoi(getenv("ORBX_SELECT_OLD")) : -1;
         const bool old_sel = c->force_kernels >= 0 ? c->force_kernels != 0 : env_old_sel >= 0 ? env_old_sel != 0 : (long)g.w * g.h > 600000L;
         static const int env_sel_nt = getenv("ORBX_SELECT_NT") ? atoi(getenv("ORBX_SELECT_NT")) : 0;   // A/B timing only
