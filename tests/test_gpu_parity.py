@@ -559,3 +559,43 @@ def test_two_contexts_on_two_threads_agree_with_sequential_calls(orbmod):
     for t in th:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("kernels", KERNELS)
+def test_describe_output_paths_odd_capacity_and_unaligned_device_buffers(orbmod, oracle, kernels):
+    """k_describe_tma writes a group's records as 128-bit stores when it can and falls back otherwise: a capacity that is not a
+    multiple of 4 (record rows of different frames are then not 16-byte aligned), capacities smaller than the count (the frame's
+    last group is cut), and device output pointers offset by 4 bytes (device API).  Every variant must equal the oracle."""
+    import torch
+    from rgbd_visualodometry_b200.synth import synth_frame
+    frames = [synth_frame(240, 320, 8800 + i) for i in range(5)]
+    n = 300
+    want = [oracle.detect_and_compute(f, n) for f in frames]
+    ctx = orbmod.Context(n, 1.2, 8, 320, 240, 8)
+    ctx.force_kernels(kernels)
+    for cap in (333, 401, 302):
+        kps, desc, cnt = ctx.detect_and_compute_batch(frames, cap)
+        for i, (ko, do) in enumerate(want):
+            _assert_kp_equal(kps[i, :cnt[i]], desc[i, :cnt[i]], ko, do, f"cap {cap} frame {i}")
+    # capacity below the count: E_CAPACITY with the needed counts, nothing written past the capacity
+    import ctypes as C
+    small = min(len(k) for k, _ in want) - 3
+    k = np.zeros((5, small + 1), orbmod.KP_DTYPE); d = np.full((5, small + 1, 32), 0xAB, np.uint8); c = np.zeros(5, np.int32)
+    ptrs = (C.c_void_p * 5)(*[f.ctypes.data for f in frames])
+    rc = ctx.lib.orbx_detect_and_compute_batch(ctx.h, ptrs, 5, 320, 240, 960, 3, k.ctypes.data, d.ctypes.data, small, c.ctypes.data)
+    assert rc == orbmod.E_CAPACITY and c.tolist() == [len(w[0]) for w in want]
+    # device API, outputs at 4-byte-offset addresses, odd capacity
+    cap = 335
+    d_in = torch.from_numpy(np.stack(frames)).cuda()
+    raw_k = torch.zeros(5 * cap * 7 + 1, dtype=torch.float32, device="cuda")
+    raw_d = torch.zeros(5 * cap * 32 + 4, dtype=torch.uint8, device="cuda")
+    d_n = torch.zeros(5, dtype=torch.int32, device="cuda")
+    ctx.detect_and_compute_device(d_in.data_ptr(), 5, 320, 240, 960, 240 * 960, 3, raw_k.data_ptr() + 4, raw_d.data_ptr() + 4, cap, d_n.data_ptr())
+    ctx.synchronize()
+    kk = raw_k[1:].cpu().numpy().reshape(5, cap, 7)
+    dd = raw_d[4:].cpu().numpy().reshape(5, cap, 32)
+    nn = d_n.cpu().numpy()
+    for i, (ko, do) in enumerate(want):
+        got = np.ascontiguousarray(kk[i, :nn[i]]).view(orbmod.KP_DTYPE).reshape(-1)
+        _assert_kp_equal(got, dd[i, :nn[i]], ko, do, f"unaligned device outputs, frame {i}")
+    ctx.close()
