@@ -13,13 +13,15 @@ import subprocess
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
-SO = os.path.join(PKG, "liborbx.so")
+SO = os.environ.get("ORBX_LIB") or os.path.join(PKG, "liborbx.so")   # ORBX_LIB: an alternative build of the same sources (A/B experiments)
 SOURCES = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".inc")))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared", "-diag-suppress", "68", "-lpthread"]
 
 
 def _stale() -> bool:
+    if os.environ.get("ORBX_LIB"):
+        return not os.path.exists(SO)
     if not os.path.exists(SO):
         return True
     t = os.path.getmtime(SO)
