@@ -35,3 +35,16 @@ def test_reference_arm_other_ranks_are_silent():
     p = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert p.returncode == 0, p.stderr[-2000:]
     assert p.stdout.strip() == ""
+
+
+def test_orbx_arm_refuses_to_run_without_a_gpu():
+    """The product arm has no CPU fallback: on a box without a CUDA device it must stop with a clear message and print no JSON
+    line (a line from a silent fallback would be read as a measurement)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True, text=True, cwd=ROOT, timeout=600,
+                       env=dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0"))
+    assert p.returncode != 0
+    assert "no CPU fallback" in (p.stderr + p.stdout)
+    assert not any(ln.strip().startswith("{") for ln in p.stdout.splitlines())
