@@ -124,3 +124,27 @@ int main(void) {
                            "-Wl,-rpath," + libdir])
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and "sm_100a" in out.stdout, out.stdout + out.stderr
+
+
+def _build_shim(tmp_path):
+    import subprocess
+    from rgbd_visualodometry_b200 import _lib
+    _lib.load()
+    exe = str(tmp_path / "frontend_shim")
+    libdir = os.path.dirname(_lib.SO)
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "frontend_shim.cpp"),
+                           "-o", exe, "-L", libdir, "-lorbx", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_cpp_frontend_shim_builds_and_has_no_fallback(tmp_path):
+    """INTEGRATION.md's FrontEnd shim as a C++11 translation unit (examples/frontend_shim.cpp) compiles warning-free against
+    include/orbx.h and links liborbx.so; without a GPU its constructor throws (rc 3) instead of falling back to anything."""
+    import subprocess
+    import torch
+    exe = _build_shim(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert out.returncode == 0 and "shim ok" in out.stdout, out.stdout + out.stderr
+    else:
+        assert out.returncode == 3 and "no sm_100 CUDA device" in out.stdout, out.stdout + out.stderr

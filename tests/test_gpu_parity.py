@@ -599,3 +599,30 @@ def test_describe_output_paths_odd_capacity_and_unaligned_device_buffers(orbmod,
         got = np.ascontiguousarray(kk[i, :nn[i]]).view(orbmod.KP_DTYPE).reshape(-1)
         _assert_kp_equal(got, dd[i, :nn[i]], ko, do, f"unaligned device outputs, frame {i}")
     ctx.close()
+
+
+def test_cpp_frontend_shim_equals_python_binding(orbmod, oracle, tmp_path):
+    """The C++ shim of INTEGRATION.md (examples/frontend_shim.cpp: FrontEnd::ExtractKeyPointsAndComputeDescriptors + the match
+    call, on cv::KeyPoint / cv::DMatch-shaped types) run as its own process on one frame: keypoint records, descriptors and
+    matches hash to what the oracle gives for the same frame."""
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.dirname(__file__))
+    from test_abi import _build_shim
+    from rgbd_visualodometry_b200.synth import synth_frame
+
+    def fnv1a(b):
+        h = 2166136261
+        for x in b:
+            h = ((h ^ x) * 16777619) & 0xFFFFFFFF
+        return h
+    img = synth_frame(480, 640, 31337)
+    raw = tmp_path / "frame.bgr"
+    raw.write_bytes(img.tobytes())
+    exe = _build_shim(tmp_path)
+    out = subprocess.run([exe, str(raw)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    ko, do = oracle.detect_and_compute(img, 500)
+    mo = oracle.match_hamming(np.ascontiguousarray(do[::3][: len(do) // 3]), do)
+    want = f"shim: keypoints {len(ko)} kp_fnv {fnv1a(ko.tobytes()):08x} desc_fnv {fnv1a(do.tobytes()):08x} matches {len(mo)} match_fnv {fnv1a(mo.tobytes()):08x}"
+    assert want in out.stdout, (out.stdout, want)
